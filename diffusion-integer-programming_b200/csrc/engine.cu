@@ -1,0 +1,528 @@
+// Host-side orchestration of one wave (B samples of one instance) of the guided sampler:
+// denoiser forward, decoder forward with saved activations, K2 guidance, decoder input-gradient
+// backward, fused DDIM/DDPM update -- model/diffusion.py:594-644 / 429-454 as a fixed sequence of
+// kernel launches on the caller's stream.  No device synchronisation, no allocation in the step.
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+namespace dip {
+
+constexpr int MAX_LAYERS = 8;
+
+struct BlockW {
+    float *ln1_w, *ln1_b, *in_w, *in_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
+    float *in_wT, *out_wT, *fc_wT, *proj_wT;   // transposed copies for the input-gradient GEMMs
+};
+
+__global__ void transpose_kernel(float* __restrict__ out, const float* __restrict__ in, int rows, int cols) {
+    int64_t total = (int64_t)rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+        out[(int64_t)c * rows + r] = in[i];
+    }
+}
+
+struct Pool {
+    std::vector<void*> ptrs;
+    int alloc(float** p, size_t n_floats) {
+        void* q = nullptr;
+        DIP_CUDA(cudaMalloc(&q, n_floats * sizeof(float)));
+        ptrs.push_back(q);
+        *p = reinterpret_cast<float*>(q);
+        return 0;
+    }
+    void release() {
+        for (void* q : ptrs) cudaFree(q);
+        ptrs.clear();
+    }
+};
+
+}  // namespace dip
+
+using namespace dip;
+
+struct dip_engine {
+    int n_den = 0, n_dec = 0;
+    BlockW den[MAX_LAYERS], dec[MAX_LAYERS];
+    float *w1 = nullptr, *w1m = nullptr, *w1x = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    float *proj_w = nullptr, *proj_b = nullptr;
+    Pool den_pool, dec_pool, inst_pool;
+    bool has_den = false, has_dec = false, has_inst = false, mproj_valid = false;
+    dip_instance inst;
+    float* mproj = nullptr;
+    uint8_t *mask_den = nullptr, *mask_dec = nullptr;
+    int inst_cap_L = 0;
+};
+
+namespace dip {
+
+static int copy_block(Pool& pool, BlockW& w, const dip_block_weights& s, cudaStream_t st) {
+    struct Item { float** dst; const float* src; size_t n; };
+    Item items[] = {
+        {&w.ln1_w, s.ln1_w, D}, {&w.ln1_b, s.ln1_b, D}, {&w.in_w, s.in_proj_w, 3 * D * D}, {&w.in_b, s.in_proj_b, 3 * D},
+        {&w.out_w, s.out_proj_w, D * D}, {&w.out_b, s.out_proj_b, D}, {&w.ln2_w, s.ln2_w, D}, {&w.ln2_b, s.ln2_b, D},
+        {&w.fc_w, s.fc_w, D * D}, {&w.fc_b, s.fc_b, D}, {&w.proj_w, s.proj_w, D * D}, {&w.proj_b, s.proj_b, D},
+    };
+    for (auto& it : items) {
+        DIP_REQUIRE(it.src, "block weights: null pointer");
+        DIP_TRY(pool.alloc(it.dst, it.n));
+        DIP_CUDA(cudaMemcpyAsync(*it.dst, it.src, it.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    DIP_TRY(pool.alloc(&w.in_wT, 3 * D * D));
+    DIP_TRY(pool.alloc(&w.out_wT, D * D));
+    DIP_TRY(pool.alloc(&w.fc_wT, D * D));
+    DIP_TRY(pool.alloc(&w.proj_wT, D * D));
+    transpose_kernel<<<64, 256, 0, st>>>(w.in_wT, w.in_w, 3 * D, D);
+    DIP_LAUNCHED();
+    transpose_kernel<<<32, 256, 0, st>>>(w.out_wT, w.out_w, D, D);
+    DIP_LAUNCHED();
+    transpose_kernel<<<32, 256, 0, st>>>(w.fc_wT, w.fc_w, D, D);
+    DIP_LAUNCHED();
+    transpose_kernel<<<32, 256, 0, st>>>(w.proj_wT, w.proj_w, D, D);
+    DIP_LAUNCHED();
+    return 0;
+}
+
+// ---- workspace carving -------------------------------------------------------------------------
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(reinterpret_cast<char*>(b)) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct LayerSave {
+    float *mean1, *rstd1, *qkv, *ao, *lse, *xmid, *mean2, *rstd2, *u, *xout;
+};
+
+struct Workspace {
+    // denoiser
+    float *hd, *tmp, *tmp2, *qkv1, *ao1;
+    // decoder
+    LayerSave ls[MAX_LAYERS];
+    float *h, *h2;
+    float *dxa, *dxb, *dxm, *dt1, *dt2, *dao, *dqkv, *delta;
+    float *p_full, *dz, *viol, *obj, *mean_buf;
+    size_t bytes;
+};
+
+static Workspace carve(const dip_engine* e, int B, void* base) {
+    Workspace w;
+    Carver c(base);
+    const size_t L = e->inst.L, T1 = L + 1, T2 = 2 * L;
+    const size_t R1 = (size_t)B * T1, R2 = (size_t)B * T2;
+    w.hd = c.take<float>(R1 * D);
+    w.tmp = c.take<float>(R1 * D);
+    w.tmp2 = c.take<float>(R1 * D);
+    w.qkv1 = c.take<float>(R1 * 3 * D);
+    w.ao1 = c.take<float>(R1 * D);
+    for (int l = 0; l < e->n_dec; ++l) {
+        LayerSave& s = w.ls[l];
+        s.mean1 = c.take<float>(R2); s.rstd1 = c.take<float>(R2);
+        s.qkv = c.take<float>(R2 * 3 * D);
+        s.ao = c.take<float>(R2 * D);
+        s.lse = c.take<float>(R2);
+        s.xmid = c.take<float>(R2 * D);
+        s.mean2 = c.take<float>(R2); s.rstd2 = c.take<float>(R2);
+        s.u = c.take<float>(R2 * D);
+        s.xout = c.take<float>(R2 * D);
+    }
+    w.h = c.take<float>(R2 * D);
+    w.h2 = c.take<float>(R2 * D);
+    w.dxa = c.take<float>(R2 * D);
+    w.dxb = c.take<float>(R2 * D);
+    w.dxm = c.take<float>(R2 * D);
+    w.dt1 = c.take<float>(R2 * D);
+    w.dt2 = c.take<float>(R2 * D);
+    w.dao = c.take<float>(R2 * D);
+    w.dqkv = c.take<float>(R2 * 3 * D);
+    w.delta = c.take<float>(R2);
+    w.p_full = c.take<float>((size_t)B * L);
+    w.dz = c.take<float>((size_t)B * L);
+    w.viol = c.take<float>(B);
+    w.obj = c.take<float>(B);
+    w.mean_buf = c.take<float>((size_t)B * L * D);
+    w.bytes = (c.off + 255) & ~(size_t)255;
+    return w;
+}
+
+static dip_gemm_args gemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int64_t M, int N, int K, int act) {
+    dip_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
+    g.M = (int)M; g.N = N; g.K = K; g.act = act;
+    return g;
+}
+
+static dip_rows plain_rows(const float* p, int T) {
+    dip_rows r;
+    r.shared = nullptr; r.batch = p; r.T = T; r.split = 0;
+    return r;
+}
+
+// One ResidualAttentionBlock forward (model/modules.py:293-296).  xin -> xmid -> xout; h, h2 are
+// transients.  Statistics / lse / u are saved when non-null.
+static int block_fwd(const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, float* qkv, float* ao, float* lse,
+                     float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask, int B, int T, dip_stream_t st) {
+    const int64_t R = (int64_t)B * T;
+    DIP_REQUIRE(R < (1ll << 31), "wave too large: B*T = %lld rows", (long long)R);
+    DIP_TRY(dip_layernorm_fwd(h, mean1, rstd1, xin, w.ln1_w, w.ln1_b, R, st));
+    dip_gemm_args g = gemm(h, D, w.in_w, w.in_b, qkv, 3 * D, R, 3 * D, D, DIP_ACT_NONE);
+    DIP_TRY(dip_gemm_nt(&g, st));
+    DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
+    g = gemm(ao, D, w.out_w, w.out_b, xmid, D, R, D, D, DIP_ACT_NONE);
+    g.res = xin;
+    DIP_TRY(dip_gemm_nt(&g, st));
+    DIP_TRY(dip_layernorm_fwd(h, mean2, rstd2, plain_rows(xmid, T), w.ln2_w, w.ln2_b, R, st));
+    g = gemm(h, D, w.fc_w, w.fc_b, h2, D, R, D, D, DIP_ACT_QUICKGELU);
+    g.preact = u;
+    DIP_TRY(dip_gemm_nt(&g, st));
+    g = gemm(h2, D, w.proj_w, w.proj_b, xout, D, R, D, D, DIP_ACT_NONE);
+    g.res = plain_rows(xmid, T);
+    DIP_TRY(dip_gemm_nt(&g, st));
+    return 0;
+}
+
+// Input-gradient backward of one block.  dxout -> dxin (rows with t >= t_min only).
+static int block_bwd(const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int B, int T, float* dt1,
+                     float* dt2, float* dxm, float* dao, float* dqkv, float* delta, float* dxin, int t_min, dip_stream_t st) {
+    const int64_t R = (int64_t)B * T;
+    // dU = (dxout . W_proj) * gelu'(u)
+    dip_gemm_args g = gemm(dxout, D, w.proj_wT, nullptr, dt1, D, R, D, D, DIP_ACT_MUL_QUICKGELU_GRAD);
+    g.aux = s.u;
+    DIP_TRY(dip_gemm_nt(&g, st));
+    // dH2 = dU . W_fc
+    g = gemm(dt1, D, w.fc_wT, nullptr, dt2, D, R, D, D, DIP_ACT_NONE);
+    DIP_TRY(dip_gemm_nt(&g, st));
+    // dxmid = dxout + LN2'(dH2)
+    DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, 0, st));
+    // dAO = dxmid . W_out
+    g = gemm(dxm, D, w.out_wT, nullptr, dao, D, R, D, D, DIP_ACT_NONE);
+    DIP_TRY(dip_gemm_nt(&g, st));
+    DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
+    // dH1 = dQKV . W_in
+    g = gemm(dqkv, 3 * D, w.in_wT, nullptr, dt1, D, R, D, 3 * D, DIP_ACT_NONE);
+    DIP_TRY(dip_gemm_nt(&g, st));
+    // dxin = dxmid + LN1'(dH1)
+    DIP_TRY(dip_layernorm_bwd(dxin, dt1, xin, s.mean1, s.rstd1, w.ln1_w, dxm, R, t_min, st));
+    return 0;
+}
+
+static int check_ready(const dip_engine* e, bool need_den, bool need_dec, int B, size_t ws_bytes, void* ws) {
+    DIP_REQUIRE(e, "null engine");
+    DIP_REQUIRE(e->has_inst, "dip_engine_set_instance has not been called");
+    DIP_REQUIRE(!need_den || e->has_den, "dip_engine_set_denoiser has not been called");
+    DIP_REQUIRE(!need_dec || e->has_dec, "dip_engine_set_decoder has not been called");
+    DIP_REQUIRE(B > 0, "empty wave");
+    DIP_REQUIRE(ws != nullptr, "null workspace");
+    size_t need = carve(e, B, nullptr).bytes;
+    DIP_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu bytes", ws_bytes, need);
+    DIP_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+    return 0;
+}
+
+// denoiser forward into ws.hd (B, L+1, 128); the model output is rows 1..L of every sample
+static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, float t, dip_stream_t st) {
+    const int L = e->inst.L, T1 = L + 1;
+    const int64_t R1 = (int64_t)B * T1;
+    if (!e->mproj_valid) {
+        // mip . W1[:, :128]^T + b1 -- constant over samples and steps, hoisted out of the loop
+        dip_gemm_args g = gemm(e->inst.mip, D, e->w1m, e->b1, e->mproj, D, L, D, D, DIP_ACT_NONE);
+        DIP_TRY(dip_gemm_nt(&g, st));
+        e->mproj_valid = true;
+    }
+    DIP_TRY(dip_time_token(w.tmp, B, T1, t, e->w1, e->b1, st));
+    dip_gemm_args g = gemm(x, D, e->w1x, nullptr, w.tmp, D, (int64_t)B * L, D, D, DIP_ACT_QUICKGELU);
+    g.rows_in = L; g.rows_out = T1; g.row_off = 1; g.addmat = e->mproj;
+    DIP_TRY(dip_gemm_nt(&g, st));
+    g = gemm(w.tmp, D, e->w2, e->b2, w.hd, D, R1, D, D, DIP_ACT_QUICKGELU);
+    DIP_TRY(dip_gemm_nt(&g, st));
+    for (int l = 0; l < e->n_den; ++l)
+        DIP_TRY(block_fwd(e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.ao1, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, e->mask_den, B, T1, st));
+    return 0;
+}
+
+// decoder forward with saved activations; final hidden state in ws.ls[n_dec-1].xout, p in ws.p_full
+static int decode(dip_engine* e, const Workspace& w, const float* x, int B, dip_stream_t st) {
+    const int L = e->inst.L, T2 = 2 * L;
+    for (int l = 0; l < e->n_dec; ++l) {
+        dip_rows xin;
+        if (l == 0) { xin.shared = e->inst.mip; xin.batch = x; xin.T = T2; xin.split = L; }
+        else xin = plain_rows(w.ls[l - 1].xout, T2);
+        const LayerSave& s = w.ls[l];
+        DIP_TRY(block_fwd(e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, s.qkv, s.ao, s.lse, s.mean1, s.rstd1, s.mean2, s.rstd2, s.u,
+                          e->mask_dec, B, T2, st));
+    }
+    DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, e->inst.kpm, st));
+    return 0;
+}
+
+// guidance gradient: returns pointer to d loss / d x rows (sample stride 2L*128)
+static int guidance_grad(dip_engine* e, const Workspace& w, const float* x, int B, float lam, const float** grad, int64_t* grad_stride,
+                         dip_stream_t st) {
+    const int L = e->inst.L, T2 = 2 * L;
+    DIP_TRY(decode(e, w, x, B, st));
+    const dip_instance& in = e->inst;
+    DIP_TRY(dip_guidance(w.dz, w.viol, w.obj, nullptr, nullptr, w.p_full, in.pos_of_col, in.csr_rowptr, in.csr_col, in.csr_val, in.csc_colptr,
+                         in.csc_row, in.csc_val, in.b, in.c, lam, B, L, in.n, in.M, in.nnz, st));
+    float* dcur = w.dxa;
+    float* dnext = w.dxb;
+    DIP_TRY(dip_decoder_head_bwd(dcur, w.dz, B, T2, L, e->proj_w, st));
+    for (int l = e->n_dec - 1; l >= 0; --l) {
+        dip_rows xin;
+        if (l == 0) { xin.shared = in.mip; xin.batch = x; xin.T = T2; xin.split = L; }
+        else xin = plain_rows(w.ls[l - 1].xout, T2);
+        // the gradient w.r.t. the (constant) mip tokens of layer 0 is never used: skip those rows
+        DIP_TRY(block_bwd(e->dec[l], dcur, xin, w.ls[l], e->mask_dec, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.dqkv, w.delta, dnext,
+                          l == 0 ? L : 0, st));
+        float* t = dcur; dcur = dnext; dnext = t;
+    }
+    *grad = dcur + (int64_t)L * D;
+    *grad_stride = (int64_t)T2 * D;
+    return 0;
+}
+
+static int final_decode(dip_engine* e, const Workspace& w, const float* x, int B, float* p_full, uint8_t* xbits, float* penalty,
+                        int64_t* viol_int, int64_t* obj_int, dip_stream_t st) {
+    const dip_instance& in = e->inst;
+    DIP_TRY(decode(e, w, x, B, st));
+    if (p_full) DIP_CUDA(cudaMemcpyAsync(p_full, w.p_full, (size_t)B * in.L * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(st)));
+    if (xbits || penalty || viol_int || obj_int)
+        DIP_TRY(dip_round_feasibility(xbits, penalty, viol_int, obj_int, w.p_full, in.pos_of_col, in.csr_rowptr, in.csr_col, in.csr_val,
+                                      in.csr_val_int, in.b, in.b_int, in.c_int, B, in.L, in.n, in.M, in.nnz, st));
+    return 0;
+}
+
+}  // namespace dip
+
+extern "C" {
+
+int dip_engine_create(dip_engine** out) {
+    DIP_REQUIRE(out, "dip_engine_create: null out");
+    int dev = 0;
+    DIP_CUDA(cudaGetDevice(&dev));
+    DIP_TRY(dip_check_device(dev, nullptr, nullptr, nullptr));
+    *out = new dip_engine();
+    memset(&(*out)->inst, 0, sizeof(dip_instance));
+    return 0;
+}
+
+void dip_engine_destroy(dip_engine* e) {
+    if (!e) return;
+    e->den_pool.release();
+    e->dec_pool.release();
+    e->inst_pool.release();
+    delete e;
+}
+
+int dip_engine_set_denoiser(dip_engine* e, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const dip_block_weights* blocks, int n_layers, dip_stream_t stream) {
+    DIP_REQUIRE(e && w1 && b1 && w2 && b2 && blocks, "dip_engine_set_denoiser: null argument");
+    DIP_REQUIRE(n_layers >= 0 && n_layers <= MAX_LAYERS, "dip_engine_set_denoiser: n_layers %d out of range", n_layers);
+    cudaStream_t st = as_stream(stream);
+    DIP_CUDA(cudaStreamSynchronize(st));
+    e->den_pool.release();
+    e->has_den = false;
+    e->mproj_valid = false;
+    DIP_TRY(e->den_pool.alloc(&e->w1, 2 * D * D));
+    DIP_TRY(e->den_pool.alloc(&e->w1m, D * D));
+    DIP_TRY(e->den_pool.alloc(&e->w1x, D * D));
+    DIP_TRY(e->den_pool.alloc(&e->b1, D));
+    DIP_TRY(e->den_pool.alloc(&e->w2, D * D));
+    DIP_TRY(e->den_pool.alloc(&e->b2, D));
+    DIP_CUDA(cudaMemcpyAsync(e->w1, w1, 2 * D * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // split linear_1 (128, 256) into its mip half [:, :128] and its x half [:, 128:] (diffusion.py:156)
+    DIP_CUDA(cudaMemcpy2DAsync(e->w1m, D * sizeof(float), w1, 2 * D * sizeof(float), D * sizeof(float), D, cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpy2DAsync(e->w1x, D * sizeof(float), w1 + D, 2 * D * sizeof(float), D * sizeof(float), D, cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->b1, b1, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->w2, w2, D * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->b2, b2, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < n_layers; ++l) DIP_TRY(copy_block(e->den_pool, e->den[l], blocks[l], st));
+    e->n_den = n_layers;
+    e->has_den = true;
+    return 0;
+}
+
+int dip_engine_set_decoder(dip_engine* e, const dip_block_weights* blocks, int n_layers, const float* proj_w, const float* proj_b,
+                           dip_stream_t stream) {
+    DIP_REQUIRE(e && blocks && proj_w && proj_b, "dip_engine_set_decoder: null argument");
+    DIP_REQUIRE(n_layers >= 1 && n_layers <= MAX_LAYERS, "dip_engine_set_decoder: n_layers %d out of range", n_layers);
+    cudaStream_t st = as_stream(stream);
+    DIP_CUDA(cudaStreamSynchronize(st));
+    e->dec_pool.release();
+    e->has_dec = false;
+    DIP_TRY(e->dec_pool.alloc(&e->proj_w, D));
+    DIP_TRY(e->dec_pool.alloc(&e->proj_b, 1));
+    DIP_CUDA(cudaMemcpyAsync(e->proj_w, proj_w, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->proj_b, proj_b, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < n_layers; ++l) DIP_TRY(copy_block(e->dec_pool, e->dec[l], blocks[l], st));
+    e->n_dec = n_layers;
+    e->has_dec = true;
+    return 0;
+}
+
+int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_t stream) {
+    DIP_REQUIRE(e && inst, "dip_engine_set_instance: null argument");
+    DIP_REQUIRE(inst->L > 0 && inst->n > 0 && inst->n <= inst->L && inst->M > 0 && inst->nnz >= 0, "dip_engine_set_instance: bad sizes L=%d n=%d M=%d",
+                inst->L, inst->n, inst->M);
+    DIP_REQUIRE(inst->mip && inst->kpm && inst->pos_of_col && inst->csr_rowptr && inst->csr_col && inst->csr_val && inst->csc_colptr &&
+                    inst->csc_row && inst->csc_val && inst->b && inst->c,
+                "dip_engine_set_instance: null array");
+    cudaStream_t st = as_stream(stream);
+    if (inst->L > e->inst_cap_L) {
+        DIP_CUDA(cudaStreamSynchronize(st));
+        e->inst_pool.release();
+        float* m1 = nullptr; float* m2 = nullptr;
+        DIP_TRY(e->inst_pool.alloc(&e->mproj, (size_t)inst->L * D));
+        DIP_TRY(e->inst_pool.alloc(&m1, (inst->L + 1 + 3) / 4 + 64));
+        DIP_TRY(e->inst_pool.alloc(&m2, (2 * inst->L + 3) / 4 + 64));
+        e->mask_den = reinterpret_cast<uint8_t*>(m1);
+        e->mask_dec = reinterpret_cast<uint8_t*>(m2);
+        e->inst_cap_L = inst->L;
+    }
+    e->inst = *inst;
+    // key masks: denoiser [False | kpm] (diffusion.py:162-165), decoder [kpm | kpm] (decoder.py:42)
+    DIP_CUDA(cudaMemsetAsync(e->mask_den, 0, 1, st));
+    DIP_CUDA(cudaMemcpyAsync(e->mask_den + 1, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->mask_dec, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->mask_dec + inst->L, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
+    e->has_inst = true;
+    e->mproj_valid = false;
+    return 0;
+}
+
+size_t dip_engine_workspace_bytes(const dip_engine* e, int B) {
+    if (!e || !e->has_inst || B <= 0) return 0;
+    return carve(e, B, nullptr).bytes;
+}
+
+int dip_engine_denoise(dip_engine* e, float* out, const float* x, int B, float t, void* workspace, size_t workspace_bytes,
+                       dip_stream_t stream) {
+    DIP_TRY(check_ready(e, true, false, B, workspace_bytes, workspace));
+    DIP_REQUIRE(out && x, "dip_engine_denoise: null argument");
+    Workspace w = carve(e, B, workspace);
+    DIP_TRY(denoise(e, w, x, B, t, stream));
+    const int L = e->inst.L;
+    DIP_CUDA(cudaMemcpy2DAsync(out, (size_t)L * D * sizeof(float), w.hd + D, (size_t)(L + 1) * D * sizeof(float), (size_t)L * D * sizeof(float), B,
+                               cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return 0;
+}
+
+int dip_engine_decode(dip_engine* e, float* p_full, float* y_last, const float* x, int B, void* workspace, size_t workspace_bytes,
+                      dip_stream_t stream) {
+    DIP_TRY(check_ready(e, false, true, B, workspace_bytes, workspace));
+    DIP_REQUIRE(p_full && x, "dip_engine_decode: null argument");
+    Workspace w = carve(e, B, workspace);
+    DIP_TRY(final_decode(e, w, x, B, p_full, nullptr, nullptr, nullptr, nullptr, stream));
+    if (y_last) {
+        const int L = e->inst.L;
+        DIP_CUDA(cudaMemcpy2DAsync(y_last, (size_t)L * D * sizeof(float), w.ls[e->n_dec - 1].xout + (size_t)L * D, (size_t)2 * L * D * sizeof(float),
+                                   (size_t)L * D * sizeof(float), B, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    }
+    return 0;
+}
+
+int dip_engine_guidance_grad(dip_engine* e, float* grad, float* p_full, float* viol, float* obj, const float* x, int B, float lam,
+                             void* workspace, size_t workspace_bytes, dip_stream_t stream) {
+    DIP_TRY(check_ready(e, false, true, B, workspace_bytes, workspace));
+    DIP_REQUIRE(grad && x, "dip_engine_guidance_grad: null argument");
+    Workspace w = carve(e, B, workspace);
+    const float* g = nullptr;
+    int64_t gs = 0;
+    DIP_TRY(guidance_grad(e, w, x, B, lam, &g, &gs, stream));
+    const int L = e->inst.L;
+    cudaStream_t st = as_stream(stream);
+    DIP_CUDA(cudaMemcpy2DAsync(grad, (size_t)L * D * sizeof(float), g, (size_t)gs * sizeof(float), (size_t)L * D * sizeof(float), B,
+                               cudaMemcpyDeviceToDevice, st));
+    if (p_full) DIP_CUDA(cudaMemcpyAsync(p_full, w.p_full, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (viol) DIP_CUDA(cudaMemcpyAsync(viol, w.viol, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (obj) DIP_CUDA(cudaMemcpyAsync(obj, w.obj, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dip_engine_guided_ddim_step(dip_engine* e, float* x, float* x0_out, int B, const dip_ddim_coeffs* co, float gs, float lam,
+                                int eps_param, const float* noise, void* workspace, size_t workspace_bytes, dip_stream_t stream) {
+    DIP_TRY(check_ready(e, true, true, B, workspace_bytes, workspace));
+    DIP_REQUIRE(x && co, "dip_engine_guided_ddim_step: null argument");
+    DIP_REQUIRE(noise || co->sigma == 0.0f, "dip_engine_guided_ddim_step: sigma != 0 needs noise");
+    Workspace w = carve(e, B, workspace);
+    const int L = e->inst.L;
+    DIP_TRY(denoise(e, w, x, B, co->t, stream));
+    const float* g = nullptr;
+    int64_t gstride = 0;
+    DIP_TRY(guidance_grad(e, w, x, B, lam, &g, &gstride, stream));
+    DIP_TRY(dip_ddim_step(x, x0_out, x, w.hd + D, (int64_t)(L + 1) * D, g, gstride, co->sigma != 0.0f ? noise : nullptr, B, L, co->sqrt_at,
+                          co->s1m, co->c_dir, co->sqrt_aprev, co->sigma, gs, eps_param, stream));
+    return 0;
+}
+
+int dip_engine_ddim_step(dip_engine* e, float* x, float* x0_out, int B, const dip_ddim_coeffs* co, int eps_param, const float* noise,
+                         void* workspace, size_t workspace_bytes, dip_stream_t stream) {
+    DIP_TRY(check_ready(e, true, false, B, workspace_bytes, workspace));
+    DIP_REQUIRE(x && co, "dip_engine_ddim_step: null argument");
+    DIP_REQUIRE(noise || co->sigma == 0.0f, "dip_engine_ddim_step: sigma != 0 needs noise");
+    Workspace w = carve(e, B, workspace);
+    const int L = e->inst.L;
+    DIP_TRY(denoise(e, w, x, B, co->t, stream));
+    DIP_TRY(dip_ddim_step(x, x0_out, x, w.hd + D, (int64_t)(L + 1) * D, nullptr, 0, co->sigma != 0.0f ? noise : nullptr, B, L, co->sqrt_at,
+                          co->s1m, co->c_dir, co->sqrt_aprev, co->sigma, 0.0f, eps_param, stream));
+    return 0;
+}
+
+int dip_engine_final_decode(dip_engine* e, const float* x, int B, float* p_full, uint8_t* xbits, float* penalty, int64_t* viol_int,
+                            int64_t* obj_int, void* workspace, size_t workspace_bytes, dip_stream_t stream) {
+    DIP_TRY(check_ready(e, false, true, B, workspace_bytes, workspace));
+    DIP_REQUIRE(x, "dip_engine_final_decode: null argument");
+    Workspace w = carve(e, B, workspace);
+    return final_decode(e, w, x, B, p_full, xbits, penalty, viol_int, obj_int, stream);
+}
+
+int dip_engine_sample_guided_ddim(dip_engine* e, float* x, int B, const dip_ddim_coeffs* steps, int S, float gs, float lam, int eps_param,
+                                  uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int, void* workspace,
+                                  size_t workspace_bytes, dip_stream_t stream) {
+    DIP_REQUIRE(steps && S > 0, "dip_engine_sample_guided_ddim: empty schedule");
+    for (int s = 0; s < S; ++s) {
+        DIP_REQUIRE(steps[s].sigma == 0.0f, "dip_engine_sample_guided_ddim: eta > 0 needs the per-step entry point with explicit noise");
+        DIP_TRY(dip_engine_guided_ddim_step(e, x, nullptr, B, &steps[s], gs, lam, eps_param, nullptr, workspace, workspace_bytes, stream));
+    }
+    return dip_engine_final_decode(e, x, B, nullptr, xbits, penalty, viol_int, obj_int, workspace, workspace_bytes, stream);
+}
+
+int dip_engine_guided_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_coeffs* co, float gs, float lam, int eps_param,
+                                const float* noise, void* workspace, size_t workspace_bytes, dip_stream_t stream) {
+    DIP_TRY(check_ready(e, true, true, B, workspace_bytes, workspace));
+    DIP_REQUIRE(x && co, "dip_engine_guided_ddpm_step: null argument");
+    DIP_REQUIRE(noise || co->nonzero == 0.0f, "dip_engine_guided_ddpm_step: noise required for t != 0");
+    Workspace w = carve(e, B, workspace);
+    const int L = e->inst.L;
+    DIP_TRY(denoise(e, w, x, B, co->t, stream));
+    DIP_TRY(dip_ddpm_mean(w.mean_buf, x, w.hd + D, (int64_t)(L + 1) * D, B, L, co->c1, co->c2, eps_param, co->sqrt_recip, co->sqrt_recipm1, stream));
+    const float* g = nullptr;
+    int64_t gstride = 0;
+    DIP_TRY(guidance_grad(e, w, w.mean_buf, B, lam, &g, &gstride, stream));   // guidance at the posterior mean (diffusion.py:433-435)
+    DIP_TRY(dip_ddpm_update(x, w.mean_buf, g, gstride, noise, B, L, co->std, gs, co->nonzero, stream));
+    return 0;
+}
+
+int dip_engine_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_coeffs* co, int eps_param, const float* noise, void* workspace,
+                         size_t workspace_bytes, dip_stream_t stream) {
+    DIP_TRY(check_ready(e, true, false, B, workspace_bytes, workspace));
+    DIP_REQUIRE(x && co, "dip_engine_ddpm_step: null argument");
+    DIP_REQUIRE(noise || co->nonzero == 0.0f, "dip_engine_ddpm_step: noise required for t != 0");
+    Workspace w = carve(e, B, workspace);
+    const int L = e->inst.L;
+    DIP_TRY(denoise(e, w, x, B, co->t, stream));
+    DIP_TRY(dip_ddpm_mean(w.mean_buf, x, w.hd + D, (int64_t)(L + 1) * D, B, L, co->c1, co->c2, eps_param, co->sqrt_recip, co->sqrt_recipm1, stream));
+    DIP_TRY(dip_ddpm_update(x, w.mean_buf, nullptr, 0, noise, B, L, co->std, 0.0f, co->nonzero, stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// K2: constraint-and-objective guidance (model/diffusion.py:623-633) and the round + feasibility
+// check of the driver tail (sample.py:164-174).  One CTA per sample; the probability vector p and
+// the hinge indicator h live in shared memory, the CSR/CSC of A is streamed from L2 (it is shared
+// by every sample of the wave).  Rows / columns are reduced by fixed-width lane groups with a
+// shuffle tree, so the summation order -- and with it the hinge active set -- is reproducible
+// run to run and for any sharding of the samples.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+#include <math.h>
+#include "common.cuh"
+
+namespace dip {
+
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum in a fixed order; result valid in thread 0
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    T t = 0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += scratch[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) guidance_kernel(
+    float* __restrict__ dz, float* __restrict__ viol, float* __restrict__ obj, float* __restrict__ r_out, float* __restrict__ dp_out,
+    const float* __restrict__ p_full, const int32_t* __restrict__ pos_of_col, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, const float* __restrict__ val, const int32_t* __restrict__ colptr,
+    const int32_t* __restrict__ crow, const float* __restrict__ cval, const float* __restrict__ bvec, const float* __restrict__ cvec,
+    float one_minus_lam, float lam, int L, int n, int M, int Gr, int Gc) {
+    extern __shared__ __align__(16) float sm[];
+    float* p_s = sm;
+    float* h_s = sm + n;
+    __shared__ float red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+
+    for (int j = tid; j < n; j += blockDim.x) p_s[j] = p_full[(int64_t)b * L + pos_of_col[j]];
+    for (int t = tid; t < L; t += blockDim.x) dz[(int64_t)b * L + t] = 0.f;
+    __syncthreads();
+
+    // r = A p - b ; h ; viol
+    float v_part = 0.f;
+    {
+        const int groups = blockDim.x / Gr, gid = tid / Gr, gl = tid % Gr;
+        for (int i0 = 0; i0 < M; i0 += groups) {
+            int i = i0 + gid;
+            float acc = 0.f;
+            if (i < M)
+                for (int e = rowptr[i] + gl; e < rowptr[i + 1]; e += Gr) acc = fmaf(val[e], p_s[col[e]], acc);
+            acc = group_sum(acc, Gr);
+            if (i < M && gl == 0) {
+                float r = acc - bvec[i];
+                h_s[i] = r > 0.f ? 1.0f : (r == 0.f ? 0.5f : 0.f);
+                v_part += fmaxf(r, 0.f);
+                if (r_out) r_out[(int64_t)b * M + i] = r;
+            }
+        }
+    }
+    float vt = block_sum(v_part, red);   // contains the __syncthreads that publishes h_s
+    if (tid == 0 && viol) viol[b] = vt;
+
+    // dp = (1-lam) A^T h + lam c ; dz = dp * p (1-p) ; obj = p.c
+    float o_part = 0.f;
+    {
+        const int groups = blockDim.x / Gc, gid = tid / Gc, gl = tid % Gc;
+        for (int j0 = 0; j0 < n; j0 += groups) {
+            int j = j0 + gid;
+            float acc = 0.f;
+            if (j < n)
+                for (int e = colptr[j] + gl; e < colptr[j + 1]; e += Gc) acc = fmaf(cval[e], h_s[crow[e]], acc);
+            acc = group_sum(acc, Gc);
+            if (j < n && gl == 0) {
+                float pj = p_s[j], cj = cvec[j];
+                float dp = one_minus_lam * acc + lam * cj;
+                dz[(int64_t)b * L + pos_of_col[j]] = (dp * (1.0f - pj)) * pj;   // sigmoid backward, torch order
+                if (dp_out) dp_out[(int64_t)b * n + j] = dp;
+                o_part += pj * cj;
+            }
+        }
+    }
+    float ot = block_sum(o_part, red);
+    if (tid == 0 && obj) obj[b] = ot;
+}
+
+__global__ void __launch_bounds__(256) round_feas_kernel(
+    uint8_t* __restrict__ xbits, float* __restrict__ penalty, long long* __restrict__ viol_int, long long* __restrict__ obj_int,
+    const float* __restrict__ p_full, const int32_t* __restrict__ pos_of_col, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, const float* __restrict__ val, const int32_t* __restrict__ val_int,
+    const float* __restrict__ bvec, const int32_t* __restrict__ b_int, const int32_t* __restrict__ c_int, int L, int n, int M, int Gr) {
+    extern __shared__ __align__(16) float sm[];
+    float* x_s = sm;
+    __shared__ float redf[8];
+    __shared__ long long redi[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    long long o_part = 0;
+    for (int j = tid; j < n; j += blockDim.x) {
+        float x = rintf(p_full[(int64_t)b * L + pos_of_col[j]]);   // torch.round: half to even (sample.py:164)
+        x_s[j] = x;
+        if (xbits) xbits[(int64_t)b * n + j] = (uint8_t)x;
+        if (c_int) o_part += (long long)c_int[j] * (long long)x;
+    }
+    __syncthreads();
+    float pen = 0.f;
+    long long vi = 0;
+    const int groups = blockDim.x / Gr, gid = tid / Gr, gl = tid % Gr;
+    for (int i0 = 0; i0 < M; i0 += groups) {
+        int i = i0 + gid;
+        float acc = 0.f;
+        long long acci = 0;
+        if (i < M)
+            for (int e = rowptr[i] + gl; e < rowptr[i + 1]; e += Gr) {
+                float x = x_s[col[e]];
+                acc = fmaf(val[e], x, acc);
+                if (val_int) acci += (long long)val_int[e] * (long long)x;
+            }
+        acc = group_sum(acc, Gr);
+        acci = group_sum(acci, Gr);
+        if (i < M && gl == 0) {
+            pen += fmaxf(acc - bvec[i], 0.f);
+            if (val_int) {
+                long long d = acci - (long long)b_int[i];
+                vi += d > 0 ? d : 0;
+            }
+        }
+    }
+    float pt = block_sum(pen, redf);
+    long long vt = block_sum(vi, redi);
+    long long ot = block_sum(o_part, redi);
+    if (tid == 0) {
+        if (penalty) penalty[b] = pt;
+        if (viol_int) viol_int[b] = val_int ? vt : -1;
+        if (obj_int) obj_int[b] = c_int ? ot : 0;
+    }
+}
+
+static int pick_group(int64_t nnz, int segments) {
+    int64_t avg = segments > 0 ? (nnz + segments - 1) / segments : 1;
+    int g = 1;
+    while (g < 32 && g < avg) g <<= 1;
+    return g;
+}
+
+}  // namespace dip
+
+using namespace dip;
+
+extern "C" {
+
+int dip_guidance(float* dz, float* viol, float* obj, float* r_out, float* dp_out, const float* p_full, const int32_t* pos_of_col,
+                 const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_val, const int32_t* csc_colptr,
+                 const int32_t* csc_row, const float* csc_val, const float* b, const float* c, float lam, int B, int L, int n, int M,
+                 int64_t nnz, dip_stream_t stream) {
+    DIP_REQUIRE(dz && p_full && pos_of_col && csr_rowptr && csr_col && csr_val && csc_colptr && csc_row && csc_val && b && c,
+                "dip_guidance: null argument");
+    DIP_REQUIRE(B > 0 && L > 0 && n > 0 && n <= L && M > 0, "dip_guidance: bad sizes B=%d L=%d n=%d M=%d", B, L, n, M);
+    size_t smem = (size_t)(n + M) * sizeof(float);
+    DIP_REQUIRE(smem <= 200 * 1024, "dip_guidance: n + M = %d exceeds the shared-memory staging limit", n + M);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DIP_CUDA(cudaFuncSetAttribute(guidance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    int Gr = pick_group(nnz, M), Gc = pick_group(nnz, n);
+    // (1 - lam) is formed in double like the reference's Python float and rounded once (diffusion.py:633)
+    float oml = (float)(1.0 - (double)lam);
+    guidance_kernel<<<B, 256, smem, as_stream(stream)>>>(dz, viol, obj, r_out, dp_out, p_full, pos_of_col, csr_rowptr, csr_col, csr_val,
+                                                         csc_colptr, csc_row, csc_val, b, c, oml, lam, L, n, M, Gr, Gc);
+    DIP_LAUNCHED();
+    return 0;
+}
+
+int dip_round_feasibility(uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int, const float* p_full,
+                          const int32_t* pos_of_col, const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_val,
+                          const int32_t* csr_val_int, const float* b, const int32_t* b_int, const int32_t* c_int, int B, int L, int n,
+                          int M, int64_t nnz, dip_stream_t stream) {
+    DIP_REQUIRE(p_full && pos_of_col && csr_rowptr && csr_col && csr_val && b, "dip_round_feasibility: null argument");
+    DIP_REQUIRE(B > 0 && L > 0 && n > 0 && n <= L && M > 0, "dip_round_feasibility: bad sizes");
+    DIP_REQUIRE((csr_val_int == nullptr) == (b_int == nullptr), "dip_round_feasibility: csr_val_int and b_int go together");
+    size_t smem = (size_t)n * sizeof(float);
+    DIP_REQUIRE(smem <= 200 * 1024, "dip_round_feasibility: n too large");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DIP_CUDA(cudaFuncSetAttribute(round_feas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    round_feas_kernel<<<B, 256, smem, as_stream(stream)>>>(xbits, penalty, reinterpret_cast<long long*>(viol_int),
+                                                           reinterpret_cast<long long*>(obj_int), p_full, pos_of_col, csr_rowptr, csr_col,
+                                                           csr_val, csr_val_int, b, b_int, c_int, L, n, M, pick_group(nnz, M));
+    DIP_LAUNCHED();
+    return 0;
+}
+
+int dip_coo_to_csr_csc_host(int64_t nnz, const int64_t* rows, const int64_t* cols, const float* vals, int M, int n,
+                            int32_t* csr_rowptr, int32_t* csr_col, float* csr_val, int32_t* csc_colptr, int32_t* csc_row,
+                            float* csc_val, int64_t* nnz_out) {
+    DIP_REQUIRE(nnz >= 0 && M > 0 && n > 0 && csr_rowptr && csc_colptr && nnz_out, "dip_coo_to_csr_csc_host: bad argument");
+    DIP_REQUIRE(nnz == 0 || (rows && cols && vals && csr_col && csr_val && csc_row && csc_val), "dip_coo_to_csr_csc_host: null array");
+    for (int64_t e = 0; e < nnz; ++e)
+        DIP_REQUIRE(rows[e] >= 0 && rows[e] < M && cols[e] >= 0 && cols[e] < n, "dip_coo_to_csr_csc_host: entry %lld out of range", (long long)e);
+    std::vector<int64_t> order(nnz);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        return rows[a] != rows[b] ? rows[a] < rows[b] : cols[a] < cols[b];
+    });
+    // coalesce: sum duplicates in their original order (torch CPU coalesce semantics)
+    int64_t m = 0;
+    std::vector<int32_t> cr, cc;
+    std::vector<float> cv;
+    cr.reserve(nnz); cc.reserve(nnz); cv.reserve(nnz);
+    for (int64_t s = 0; s < nnz;) {
+        int64_t e = s;
+        float acc = vals[order[s]];
+        while (++e < nnz && rows[order[e]] == rows[order[s]] && cols[order[e]] == cols[order[s]]) acc += vals[order[e]];
+        cr.push_back((int32_t)rows[order[s]]); cc.push_back((int32_t)cols[order[s]]); cv.push_back(acc);
+        s = e; ++m;
+    }
+    for (int i = 0; i <= M; ++i) csr_rowptr[i] = 0;
+    for (int j = 0; j <= n; ++j) csc_colptr[j] = 0;
+    for (int64_t e = 0; e < m; ++e) { csr_rowptr[cr[e] + 1]++; csc_colptr[cc[e] + 1]++; }
+    for (int i = 0; i < M; ++i) csr_rowptr[i + 1] += csr_rowptr[i];
+    for (int j = 0; j < n; ++j) csc_colptr[j + 1] += csc_colptr[j];
+    std::vector<int32_t> fill(csc_colptr, csc_colptr + n);
+    for (int64_t e = 0; e < m; ++e) {
+        csr_col[e] = cc[e]; csr_val[e] = cv[e];
+        int32_t pos = fill[cc[e]]++;
+        csc_row[pos] = cr[e]; csc_val[pos] = cv[e];   // rows ascending within a column
+    }
+    *nnz_out = m;
+    return 0;
+}
+
+}  // extern "C"

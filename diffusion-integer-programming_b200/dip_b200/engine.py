@@ -1,0 +1,318 @@
+"""Python handle on the C engine (include/dip_b200.h, "engine" section).
+
+PyTorch is plumbing here: it owns device memory (weights, latents, workspace) and the CUDA stream;
+every computation of the sampling path is a kernel of libdip_b200.so.  Tensors handed to the
+engine are borrowed by raw pointer, so the handle keeps references to them.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+D = 128
+
+BLOCK_KEYS = [
+    ("ln1_w", "ln_1.weight"), ("ln1_b", "ln_1.bias"), ("in_proj_w", "attn.in_proj_weight"), ("in_proj_b", "attn.in_proj_bias"),
+    ("out_proj_w", "attn.out_proj.weight"), ("out_proj_b", "attn.out_proj.bias"), ("ln2_w", "ln_2.weight"), ("ln2_b", "ln_2.bias"),
+    ("fc_w", "mlp.c_fc.weight"), ("fc_b", "mlp.c_fc.bias"), ("proj_w", "mlp.c_proj.weight"), ("proj_b", "mlp.c_proj.bias"),
+]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t, dtype=torch.float32, device=None):
+    """contiguous tensor of `dtype` on the CUDA device (numpy / torch accepted)."""
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    t = t.detach()
+    if device is None:
+        device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return t.to(device=device, dtype=dtype).contiguous()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.DipError("diffusion-integer-programming_b200 needs a CUDA device (sm_100a); there is no CPU path")
+
+
+def coo_to_csr_csc(rows, cols, vals, M, n):
+    """Host CSR + CSC of the coalesced matrix via the library's own builder (numpy in / out)."""
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float32)
+    nnz = len(rows)
+    out = {
+        "csr_rowptr": np.zeros(M + 1, np.int32), "csr_col": np.zeros(max(nnz, 1), np.int32), "csr_val": np.zeros(max(nnz, 1), np.float32),
+        "csc_colptr": np.zeros(n + 1, np.int32), "csc_row": np.zeros(max(nnz, 1), np.int32), "csc_val": np.zeros(max(nnz, 1), np.float32),
+    }
+    nnz_out = C.c_int64(0)
+    check(lib.dip_coo_to_csr_csc_host(nnz, ptr(rows), ptr(cols), ptr(vals), M, n, ptr(out["csr_rowptr"]), ptr(out["csr_col"]),
+                                      ptr(out["csr_val"]), ptr(out["csc_colptr"]), ptr(out["csc_row"]), ptr(out["csc_val"]),
+                                      C.byref(nnz_out)))
+    m = nnz_out.value
+    for k in ("csr_col", "csr_val", "csc_row", "csc_val"):
+        out[k] = out[k][:max(m, 1)]
+    out["nnz"] = m
+    return out
+
+
+class Engine:
+    """One engine per process / GPU (the reference's samplers are not re-entrant either)."""
+
+    def __init__(self, device=None):
+        require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.device):
+            h = C.c_void_p()
+            check(self.lib.dip_engine_create(C.byref(h)))
+        self.h = h
+        self._keep = {}
+        self._ws = None
+        self.inst = None
+        self.n_den = self.n_dec = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.dip_engine_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------------
+    def _blocks(self, sd, prefix, n_layers, keep):
+        arr = (_lib.BlockWeights * max(n_layers, 1))()
+        for i in range(n_layers):
+            for field, key in BLOCK_KEYS:
+                t = _dev(sd["%s%d.%s" % (prefix, i, key)], device=self.device)
+                keep.append(t)
+                setattr(arr[i], field, t.data_ptr())
+        return arr
+
+    @staticmethod
+    def count_layers(sd, prefix):
+        i = 0
+        while ("%s%d.ln_1.weight" % (prefix, i)) in sd:
+            i += 1
+        return i
+
+    def set_denoiser(self, sd, prefix="predict_model."):
+        """sd: state_dict-like of DDPMTrainer (keys ``predict_model.*``)."""
+        keep = []
+        n = self.count_layers(sd, prefix + "resblocks.")
+        arr = self._blocks(sd, prefix + "resblocks.", n, keep)
+        w1, b1, w2, b2 = (_dev(sd[prefix + k], device=self.device) for k in
+                          ("mlp_xt.linear_1.weight", "mlp_xt.linear_1.bias", "mlp_xt.linear_2.weight", "mlp_xt.linear_2.bias"))
+        if tuple(w1.shape) != (D, 2 * D) or tuple(w2.shape) != (D, D):
+            raise _lib.DipError("denoiser width must be 128 (got linear_1 %s)" % (tuple(w1.shape),))
+        with torch.cuda.device(self.device):
+            check(self.lib.dip_engine_set_denoiser(self.h, ptr(w1), ptr(b1), ptr(w2), ptr(b2), arr, n, _stream()))
+            torch.cuda.current_stream().synchronize()   # weights were copied; sources may go away
+        self.n_den = n
+
+    def set_decoder(self, sd):
+        keep = []
+        n = self.count_layers(sd, "resblocks.")
+        arr = self._blocks(sd, "resblocks.", n, keep)
+        pw = _dev(sd["linear_proj.linear_projection.weight"], device=self.device)
+        pb = _dev(sd["linear_proj.linear_projection.bias"], device=self.device)
+        if tuple(pw.shape) != (1, D):
+            raise _lib.DipError("decoder width must be 128")
+        with torch.cuda.device(self.device):
+            check(self.lib.dip_engine_set_decoder(self.h, arr, n, ptr(pw), ptr(pb), _stream()))
+            torch.cuda.current_stream().synchronize()
+        self.n_dec = n
+
+    # ---- instance ------------------------------------------------------------------------------
+    def set_instance(self, mip, kpm, rows, cols, vals, M, b, c, a_int=None, b_int=None, c_int=None):
+        """mip (L,128) conditions of ONE instance; kpm (L,) bool; A as COO (rows, cols, vals) of shape
+        (M, n) with n = number of unmasked positions; b (M,), c (n,).  Optional exact-integer twin
+        a_int (aligned with rows/cols/vals, duplicates not allowed then), b_int, c_int."""
+        dev = self.device
+        mip = _dev(mip, device=dev)
+        L = mip.shape[0]
+        kpm_t = _dev(kpm, torch.bool, device=dev).view(-1)
+        if kpm_t.numel() != L:
+            raise _lib.DipError("key_padding_mask length %d != padding_len %d" % (kpm_t.numel(), L))
+        pos = torch.nonzero(~kpm_t).view(-1).to(torch.int32).contiguous()
+        n = int(pos.numel())
+        c = _dev(c, device=dev).view(-1)
+        b = _dev(b, device=dev).view(-1)
+        if c.numel() != n:
+            # the reference's `pred_x.squeeze() @ c` raises for the same mismatch
+            raise _lib.DipError("objective vector has %d entries but %d variables are unmasked" % (c.numel(), n))
+        if b.numel() != M:
+            raise _lib.DipError("rhs has %d entries, A has %d rows" % (b.numel(), M))
+        to_np = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+        rows_np, cols_np, vals_np = to_np(rows), to_np(cols), to_np(vals)
+        csr = coo_to_csr_csc(rows_np, cols_np, vals_np, M, n)
+        keep = {"mip": mip, "kpm": kpm_t.to(torch.uint8).contiguous(), "pos": pos, "b": b, "c": c}
+        for k in ("csr_rowptr", "csr_col", "csr_val", "csc_colptr", "csc_row", "csc_val"):
+            keep[k] = torch.from_numpy(csr[k]).to(dev)
+        inst = _lib.Instance()
+        inst.L, inst.n, inst.M, inst.nnz = L, n, int(M), int(csr["nnz"])
+        if a_int is not None:
+            if csr["nnz"] != len(rows_np):
+                raise _lib.DipError("integer twin needs a duplicate-free COO")
+            ci = coo_to_csr_csc(rows_np, cols_np, np.asarray(to_np(a_int), dtype=np.float32), M, n)
+            keep["csr_val_int"] = torch.from_numpy(np.rint(ci["csr_val"]).astype(np.int32)).to(dev)
+            keep["b_int"] = _dev(np.asarray(to_np(b_int), dtype=np.int32), torch.int32, device=dev)
+            keep["c_int"] = _dev(np.asarray(to_np(c_int), dtype=np.int32), torch.int32, device=dev)
+        for f, k in (("mip", "mip"), ("kpm", "kpm"), ("pos_of_col", "pos"), ("csr_rowptr", "csr_rowptr"), ("csr_col", "csr_col"),
+                     ("csr_val", "csr_val"), ("csc_colptr", "csc_colptr"), ("csc_row", "csc_row"), ("csc_val", "csc_val"),
+                     ("b", "b"), ("c", "c"), ("csr_val_int", "csr_val_int"), ("b_int", "b_int"), ("c_int", "c_int")):
+            setattr(inst, f, keep[k].data_ptr() if k in keep else None)
+        with torch.cuda.device(dev):
+            check(self.lib.dip_engine_set_instance(self.h, C.byref(inst), _stream()))
+        self._keep["inst"] = keep
+        self.inst = {"L": L, "n": n, "M": int(M), "nnz": int(csr["nnz"]), "has_int": a_int is not None}
+        return self.inst
+
+    def set_conditions(self, mip, kpm):
+        """Instance without constraints (unguided sampling / plain decoding): an empty 1-row system."""
+        kpm = kpm.view(-1)
+        n = int((~kpm.to(torch.bool)).sum())
+        z = np.zeros(0, dtype=np.int64)
+        return self.set_instance(mip, kpm, z, z, np.zeros(0, dtype=np.float32), 1, np.zeros(1, dtype=np.float32),
+                                 np.zeros(n, dtype=np.float32))
+
+    # ---- workspace -----------------------------------------------------------------------------
+    def workspace(self, B):
+        need = self.lib.dip_engine_workspace_bytes(self.h, int(B))
+        if need == 0:
+            raise _lib.DipError("set_instance must be called before sampling")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        base = self._ws.data_ptr()
+        off = (-base) % 256
+        return base + off, self._ws.numel() - off
+
+    def _x(self, x):
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise _lib.DipError("latents must be a contiguous fp32 CUDA tensor")
+        if x.dim() != 3 or x.shape[1] != self.inst["L"] or x.shape[2] != D:
+            raise _lib.DipError("latents must be (B, %d, 128), got %s" % (self.inst["L"], tuple(x.shape)))
+        return x
+
+    # ---- networks ------------------------------------------------------------------------------
+    def denoise(self, x, t):
+        x = self._x(x)
+        out = torch.empty_like(x)
+        ws, nb = self.workspace(x.shape[0])
+        check(self.lib.dip_engine_denoise(self.h, ptr(out), ptr(x), x.shape[0], float(t), ws, nb, _stream()))
+        return out
+
+    def decode(self, x, want_hidden=False):
+        x = self._x(x)
+        B = x.shape[0]
+        p = torch.empty((B, self.inst["L"]), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x) if want_hidden else None
+        ws, nb = self.workspace(B)
+        check(self.lib.dip_engine_decode(self.h, ptr(p), ptr(y), ptr(x), B, ws, nb, _stream()))
+        return (p, y) if want_hidden else p
+
+    def guidance_grad(self, x, lam):
+        x = self._x(x)
+        B = x.shape[0]
+        grad = torch.empty_like(x)
+        p = torch.empty((B, self.inst["L"]), dtype=torch.float32, device=x.device)
+        viol = torch.empty(B, dtype=torch.float32, device=x.device)
+        obj = torch.empty(B, dtype=torch.float32, device=x.device)
+        ws, nb = self.workspace(B)
+        check(self.lib.dip_engine_guidance_grad(self.h, ptr(grad), ptr(p), ptr(viol), ptr(obj), ptr(x), B, float(lam), ws, nb, _stream()))
+        return grad, p, viol, obj
+
+    # ---- sampler steps -------------------------------------------------------------------------
+    @staticmethod
+    def ddim_coeffs(t, sqrt_at, s1m, c_dir, sqrt_aprev, sigma):
+        return _lib.DdimCoeffs(float(t), float(sqrt_at), float(s1m), float(c_dir), float(sqrt_aprev), float(sigma))
+
+    def guided_ddim_step(self, x, co, gs, lam, eps_param=False, noise=None, x0_out=None):
+        x = self._x(x)
+        ws, nb = self.workspace(x.shape[0])
+        check(self.lib.dip_engine_guided_ddim_step(self.h, ptr(x), ptr(x0_out), x.shape[0], C.byref(co), float(gs), float(lam),
+                                                   int(eps_param), ptr(noise), ws, nb, _stream()))
+        return x
+
+    def ddim_step(self, x, co, eps_param=False, noise=None, x0_out=None):
+        x = self._x(x)
+        ws, nb = self.workspace(x.shape[0])
+        check(self.lib.dip_engine_ddim_step(self.h, ptr(x), ptr(x0_out), x.shape[0], C.byref(co), int(eps_param), ptr(noise), ws, nb, _stream()))
+        return x
+
+    def guided_ddpm_step(self, x, co, gs, lam, eps_param=False, noise=None):
+        x = self._x(x)
+        ws, nb = self.workspace(x.shape[0])
+        check(self.lib.dip_engine_guided_ddpm_step(self.h, ptr(x), x.shape[0], C.byref(co), float(gs), float(lam), int(eps_param),
+                                                   ptr(noise), ws, nb, _stream()))
+        return x
+
+    def ddpm_step(self, x, co, eps_param=False, noise=None):
+        x = self._x(x)
+        ws, nb = self.workspace(x.shape[0])
+        check(self.lib.dip_engine_ddpm_step(self.h, ptr(x), x.shape[0], C.byref(co), int(eps_param), ptr(noise), ws, nb, _stream()))
+        return x
+
+    def final_decode(self, x, want_p=True):
+        """Decode + round + feasibility (sample.py:162-174).  Returns dict of device tensors."""
+        x = self._x(x)
+        B, n, L = x.shape[0], self.inst["n"], self.inst["L"]
+        dev = x.device
+        out = {
+            "p_full": torch.empty((B, L), dtype=torch.float32, device=dev) if want_p else None,
+            "xbits": torch.empty((B, n), dtype=torch.uint8, device=dev),
+            "penalty": torch.empty(B, dtype=torch.float32, device=dev),
+            "viol_int": torch.empty(B, dtype=torch.int64, device=dev),
+            "obj_int": torch.empty(B, dtype=torch.int64, device=dev),
+        }
+        ws, nb = self.workspace(B)
+        check(self.lib.dip_engine_final_decode(self.h, ptr(x), B, ptr(out["p_full"]), ptr(out["xbits"]), ptr(out["penalty"]),
+                                               ptr(out["viol_int"]), ptr(out["obj_int"]), ws, nb, _stream()))
+        return out
+
+    def sample_guided_ddim(self, x, steps, gs, lam, eps_param=False):
+        """Whole S-step loop + final decode in ONE library call (in place on x)."""
+        x = self._x(x)
+        B, n = x.shape[0], self.inst["n"]
+        dev = x.device
+        arr = (_lib.DdimCoeffs * len(steps))(*steps)
+        out = {
+            "xbits": torch.empty((B, n), dtype=torch.uint8, device=dev),
+            "penalty": torch.empty(B, dtype=torch.float32, device=dev),
+            "viol_int": torch.empty(B, dtype=torch.int64, device=dev),
+            "obj_int": torch.empty(B, dtype=torch.int64, device=dev),
+        }
+        ws, nb = self.workspace(B)
+        check(self.lib.dip_engine_sample_guided_ddim(self.h, ptr(x), B, arr, len(steps), float(gs), float(lam), int(eps_param),
+                                                     ptr(out["xbits"]), ptr(out["penalty"]), ptr(out["viol_int"]), ptr(out["obj_int"]),
+                                                     ws, nb, _stream()))
+        out["x"] = x
+        return out
+
+
+_default = None
+
+
+def default_engine():
+    """Process-wide engine shared by the drop-in ``model.*`` classes."""
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
+
+
+def randn(shape, seed, subseq, device=None):
+    """Counter-based N(0,1) tensor from the library's Philox generator."""
+    require_cuda()
+    lib = _lib.load()
+    out = torch.empty(shape, dtype=torch.float32, device=device or torch.device("cuda", torch.cuda.current_device()))
+    check(lib.dip_randn(ptr(out), out.numel(), int(seed), int(subseq), _stream()))
+    return out

@@ -1,0 +1,239 @@
+"""Kernel-level Python wrappers over the C-ABI (one function per exported kernel launcher).
+
+Used by the parity tests (each kernel against the oracle), by the instance encoder and by the
+stand-alone module forwards.  Inputs must be contiguous fp32 CUDA tensors; outputs are new tensors.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, Rows, GemmArgs
+from .engine import _stream, require_cuda
+
+D = 128
+ACT = {None: 0, "none": 0, "quickgelu": 1, "relu": 2, "sigmoid": 3, "mul_quickgelu_grad": 4}
+
+
+def _f32(t, name="tensor"):
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise _lib.DipError("%s must be a contiguous fp32 CUDA tensor" % name)
+    return t
+
+
+def gemm_nt(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=0, addmat=None, res=None,
+            res_shared=None, res_T=0, res_split=0, row_bias_scale=None, preact=None, aux=None, out_rows=None):
+    """act(A @ W.T + bias*row_bias_scale + addmat[t] + residual); see dip_gemm_nt in include/dip_b200.h."""
+    lib = _lib.load()
+    A, W = _f32(A, "A"), _f32(W, "W")
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise _lib.DipError("gemm_nt: K mismatch")
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, N), dtype=torch.float32, device=A.device)
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.bias, g.C, g.ldc = ptr(A), K, ptr(W), ptr(bias), ptr(out), N
+    g.M, g.N, g.K, g.act = M, N, K, ACT[act]
+    g.rows_in, g.rows_out, g.row_off = rows_in, rows_out, row_off
+    g.addmat = ptr(addmat)
+    g.res = Rows(ptr(res_shared), ptr(res), int(res_T), int(res_split))
+    g.row_bias_scale, g.preact, g.aux = ptr(row_bias_scale), ptr(preact), ptr(aux)
+    check(lib.dip_gemm_nt(C.byref(g), _stream()))
+    return out
+
+
+def linear_smallk(x, W, bias=None, shift=None, scale=None, act=None):
+    lib = _lib.load()
+    x, W = _f32(x), _f32(W)
+    rows, K = x.shape
+    if tuple(W.shape) != (D, K):
+        raise _lib.DipError("linear_smallk: weight must be (128, K)")
+    y = torch.empty((rows, D), dtype=torch.float32, device=x.device)
+    check(lib.dip_linear_smallk(ptr(y), ptr(x), rows, K, ptr(shift), ptr(scale), ptr(W), ptr(bias), ACT[act], _stream()))
+    return y
+
+
+def layernorm_fwd(x, gamma, beta, shared=None, T=0, split=0, save_stats=False, rows=None):
+    lib = _lib.load()
+    x = _f32(x)
+    n_rows = rows if rows is not None else x.numel() // D
+    y = torch.empty((n_rows, D), dtype=torch.float32, device=x.device)
+    mean = torch.empty(n_rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(n_rows, dtype=torch.float32, device=x.device) if save_stats else None
+    check(lib.dip_layernorm_fwd(ptr(y), ptr(mean), ptr(rstd), Rows(ptr(shared), ptr(x), int(T), int(split)), ptr(gamma), ptr(beta),
+                                n_rows, _stream()))
+    return (y, mean, rstd) if save_stats else y
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, shared=None, T=0, split=0, t_min=0):
+    lib = _lib.load()
+    dy = _f32(dy)
+    n_rows = dy.numel() // D
+    dx = torch.zeros((n_rows, D), dtype=torch.float32, device=dy.device)
+    check(lib.dip_layernorm_bwd(ptr(dx), ptr(dy), Rows(ptr(shared), ptr(x), int(T), int(split)), ptr(mean), ptr(rstd), ptr(gamma),
+                                ptr(dres), n_rows, int(t_min), _stream()))
+    return dx
+
+
+def attn_fwd(qkv, B, T, key_mask=None, mask_stride=None):
+    """qkv: (B*T, 384) packed [q|k|v].  key_mask: (B,T) or (T,) bool/uint8.  Returns (o (B*T,128), lse (B*T))."""
+    lib = _lib.load()
+    qkv = _f32(qkv)
+    o = torch.empty((B * T, D), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty(B * T, dtype=torch.float32, device=qkv.device)
+    km, ms = _mask(key_mask, B, T, mask_stride)
+    base = qkv.data_ptr()
+    check(lib.dip_attn_fwd(ptr(o), ptr(lse), base, base + 4 * D, base + 8 * D, 3 * D, ptr(km), ms, B, T, _stream()))
+    return o, lse
+
+
+def attn_bwd(qkv, o, d_o, lse, B, T, key_mask=None, mask_stride=None):
+    lib = _lib.load()
+    qkv, o, d_o = _f32(qkv), _f32(o), _f32(d_o)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B * T, dtype=torch.float32, device=qkv.device)
+    km, ms = _mask(key_mask, B, T, mask_stride)
+    base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+    check(lib.dip_attn_bwd(dbase, dbase + 4 * D, dbase + 8 * D, 3 * D, base, base + 4 * D, base + 8 * D, 3 * D, ptr(o), ptr(d_o),
+                           ptr(lse), ptr(km), ms, ptr(delta), B, T, _stream()))
+    return dqkv
+
+
+def _mask(key_mask, B, T, mask_stride):
+    if key_mask is None:
+        return None, 0
+    km = key_mask.to(torch.uint8).contiguous()
+    if mask_stride is None:
+        mask_stride = T if km.dim() == 2 and km.shape[0] == B and B > 1 else (0 if km.numel() == T else T)
+    return km, mask_stride
+
+
+def ddim_step(x, model_out, coeffs, grad=None, gs=0.0, noise=None, eps_param=False, want_x0=False):
+    """coeffs: dict with sqrt_at, s1m, c_dir, sqrt_aprev, sigma.  Out of place; returns x_prev (and x0)."""
+    lib = _lib.load()
+    x, model_out = _f32(x), _f32(model_out)
+    B, L = x.shape[0], x.shape[1]
+    xp = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_x0 else None
+    check(lib.dip_ddim_step(ptr(xp), ptr(x0), ptr(x), ptr(model_out), L * D, ptr(grad), L * D if grad is not None else 0, ptr(noise),
+                            B, L, coeffs["sqrt_at"], coeffs["s1m"], coeffs["c_dir"], coeffs["sqrt_aprev"], coeffs["sigma"], float(gs),
+                            int(eps_param), _stream()))
+    return (xp, x0) if want_x0 else xp
+
+
+def ddpm_mean(x, model_out, c1, c2, eps_param=False, sqrt_recip=0.0, sqrt_recipm1=0.0):
+    lib = _lib.load()
+    x, model_out = _f32(x), _f32(model_out)
+    B, L = x.shape[0], x.shape[1]
+    mean = torch.empty_like(x)
+    check(lib.dip_ddpm_mean(ptr(mean), ptr(x), ptr(model_out), L * D, B, L, float(c1), float(c2), int(eps_param), float(sqrt_recip),
+                            float(sqrt_recipm1), _stream()))
+    return mean
+
+
+def ddpm_update(mean, std, grad=None, gs=0.0, noise=None, nonzero=1.0):
+    lib = _lib.load()
+    mean = _f32(mean)
+    B, L = mean.shape[0], mean.shape[1]
+    xp = torch.empty_like(mean)
+    check(lib.dip_ddpm_update(ptr(xp), ptr(mean), ptr(grad), L * D if grad is not None else 0, ptr(noise), B, L, float(std), float(gs),
+                              float(nonzero), _stream()))
+    return xp
+
+
+def time_token(B, T, t, W1, b1, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.zeros((B, T, D), dtype=torch.float32, device=W1.device)
+    check(lib.dip_time_token(ptr(out), B, T, float(t), ptr(W1), ptr(b1), _stream()))
+    return out
+
+
+def decoder_head_fwd(y, B, T, L, w, beta, kpm):
+    lib = _lib.load()
+    p = torch.empty((B, L), dtype=torch.float32, device=y.device)
+    km = kpm.to(torch.uint8).contiguous()
+    check(lib.dip_decoder_head_fwd(ptr(p), ptr(_f32(y)), B, T, L, ptr(w), ptr(beta), ptr(km), _stream()))
+    return p
+
+
+def decoder_head_bwd(dz, B, T, L, w):
+    lib = _lib.load()
+    dy = torch.empty((B, T, D), dtype=torch.float32, device=dz.device)
+    check(lib.dip_decoder_head_bwd(ptr(dy), ptr(_f32(dz)), B, T, L, ptr(w), _stream()))
+    return dy
+
+
+def guidance(p_full, pos_of_col, csr, b, c, lam, M, want_r=False):
+    """csr: dict of device int32/fp32 tensors (csr_rowptr, csr_col, csr_val, csc_colptr, csc_row, csc_val, nnz)."""
+    lib = _lib.load()
+    p_full = _f32(p_full)
+    B, L = p_full.shape
+    n = pos_of_col.numel()
+    dev = p_full.device
+    dz = torch.empty((B, L), dtype=torch.float32, device=dev)
+    viol = torch.empty(B, dtype=torch.float32, device=dev)
+    obj = torch.empty(B, dtype=torch.float32, device=dev)
+    r = torch.empty((B, M), dtype=torch.float32, device=dev) if want_r else None
+    dp = torch.empty((B, n), dtype=torch.float32, device=dev) if want_r else None
+    check(lib.dip_guidance(ptr(dz), ptr(viol), ptr(obj), ptr(r), ptr(dp), ptr(p_full), ptr(pos_of_col), ptr(csr["csr_rowptr"]),
+                           ptr(csr["csr_col"]), ptr(csr["csr_val"]), ptr(csr["csc_colptr"]), ptr(csr["csc_row"]), ptr(csr["csc_val"]),
+                           ptr(b), ptr(c), float(lam), B, L, n, M, int(csr["nnz"]), _stream()))
+    return {"dz": dz, "viol": viol, "obj": obj, "r": r, "dp": dp}
+
+
+def round_feasibility(p_full, pos_of_col, csr, b, M, csr_val_int=None, b_int=None, c_int=None):
+    lib = _lib.load()
+    p_full = _f32(p_full)
+    B, L = p_full.shape
+    n = pos_of_col.numel()
+    dev = p_full.device
+    xbits = torch.empty((B, n), dtype=torch.uint8, device=dev)
+    pen = torch.empty(B, dtype=torch.float32, device=dev)
+    vi = torch.empty(B, dtype=torch.int64, device=dev)
+    oi = torch.empty(B, dtype=torch.int64, device=dev)
+    check(lib.dip_round_feasibility(ptr(xbits), ptr(pen), ptr(vi), ptr(oi), ptr(p_full), ptr(pos_of_col), ptr(csr["csr_rowptr"]),
+                                    ptr(csr["csr_col"]), ptr(csr["csr_val"]), ptr(csr_val_int), ptr(b), ptr(b_int), ptr(c_int), B, L, n, M,
+                                    int(csr["nnz"]), _stream()))
+    return {"xbits": xbits, "penalty": pen, "viol_int": vi, "obj_int": oi}
+
+
+def conv_reduce(PL, PR, we, s, a_shift, a_scale, seg_ptr, nbr, a):
+    lib = _lib.load()
+    n_target = PL.shape[0]
+    acc = torch.empty((n_target, D), dtype=torch.float32, device=PL.device)
+    deg = torch.empty(n_target, dtype=torch.float32, device=PL.device)
+    check(lib.dip_conv_reduce(ptr(acc), ptr(deg), ptr(_f32(PL)), ptr(_f32(PR)), ptr(_f32(we)), float(s), float(a_shift), float(a_scale),
+                              ptr(seg_ptr), ptr(nbr), ptr(a), n_target, _stream()))
+    return acc, deg
+
+
+def spmm_csr(X, seg_ptr, nbr, val, n_rows, add=None):
+    lib = _lib.load()
+    y = torch.empty((n_rows, D), dtype=torch.float32, device=X.device)
+    check(lib.dip_spmm_csr(ptr(y), ptr(_f32(X)), ptr(add), ptr(seg_ptr), ptr(nbr), ptr(val), n_rows, _stream()))
+    return y
+
+
+def gather_pad(src, idx, L):
+    lib = _lib.load()
+    idx = idx.to(torch.int64).contiguous()
+    out = torch.empty((L, D), dtype=torch.float32, device=src.device)
+    check(lib.dip_gather_pad(ptr(out), ptr(_f32(src)), ptr(idx), idx.numel(), L, _stream()))
+    return out
+
+
+def block_forward(x, w, key_mask=None):
+    """One ResidualAttentionBlock forward (reference: model/modules.py:293-296) on (B,T,128).
+    ``w``: dict with the block's state_dict keys (ln_1.weight, attn.in_proj_weight, ...)."""
+    require_cuda()
+    B, T, _ = x.shape
+    x2 = _f32(x.contiguous()).view(B * T, D)
+    h = layernorm_fwd(x2, w["ln_1.weight"], w["ln_1.bias"])
+    qkv = gemm_nt(h, w["attn.in_proj_weight"], w["attn.in_proj_bias"])
+    o, _ = attn_fwd(qkv, B, T, key_mask)
+    xm = gemm_nt(o, w["attn.out_proj.weight"], w["attn.out_proj.bias"], res=x2)
+    h = layernorm_fwd(xm, w["ln_2.weight"], w["ln_2.bias"])
+    g = gemm_nt(h, w["mlp.c_fc.weight"], w["mlp.c_fc.bias"], act="quickgelu")
+    return gemm_nt(g, w["mlp.c_proj.weight"], w["mlp.c_proj.bias"], res=xm).view(B, T, D)

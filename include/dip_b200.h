@@ -1,0 +1,305 @@
+/*
+ * dip_b200.h -- C-ABI of the B200-native guided DDIM/DDPM sampling path for integer programs.
+ *
+ * One shared library (libdip_b200.so, built from diffusion-integer-programming_b200/csrc by
+ * __graft_entry__.build()) exports everything below with C linkage: plain pointers and sizes,
+ * no torch types.  Device pointers are ordinary CUDA device addresses (e.g. tensor.data_ptr());
+ * `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success and a non-zero
+ * code on failure; dip_last_error() then holds a message (thread-local).  Nothing here falls back
+ * to the CPU: a missing GPU / failed launch is an error.
+ *
+ * The reference (agent-lab/diffusion-integer-programming) is pure Python on torch ops -- it has no
+ * FFI of its own.  Each entry point therefore cites the reference Python lines whose torch ops it
+ * replaces (paths relative to the reference root); INTEGRATION.md shows the ctypes binding a
+ * maintainer adds inside model/diffusion.py, model/decoder.py and model/cmsp.py.
+ *
+ * Fixed model width: emb_dim = 128, one attention head (sample.py:21-37).  All floating-point
+ * tensors are fp32, row-major, innermost dimension DIP_D.
+ */
+#ifndef DIP_B200_H
+#define DIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIP_D 128
+#define DIP_ABI_VERSION 1
+
+typedef void* dip_stream_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+int dip_abi_version(void);
+const char* dip_last_error(void);
+/* Fails unless device `dev` is compute capability 10.x (the library holds sm_100a code only). */
+int dip_check_device(int dev, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------ */
+/* host-side helper (CPU, no GPU needed)                                                      */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces the two A.coalesce() sorts the reference runs on EVERY step (model/diffusion.py:624):
+ * sorts COO by (row, col), sums duplicates in input order, emits CSR (rowptr[M+1], col[nnz'],
+ * val[nnz']) and CSC (colptr[n+1], row[nnz'], val[nnz']).  Output arrays must hold `nnz` entries;
+ * *nnz_out receives the coalesced count. */
+int dip_coo_to_csr_csc_host(int64_t nnz, const int64_t* rows, const int64_t* cols, const float* vals,
+                            int M, int n, int32_t* csr_rowptr, int32_t* csr_col, float* csr_val,
+                            int32_t* csc_colptr, int32_t* csc_row, float* csc_val, int64_t* nnz_out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* row sources                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+/* A (B*T, 128) activation whose first `split` rows of every sample come from one batch-shared
+ * (split,128) tensor and the remaining T-split rows from a per-sample (B, T-split, 128) tensor.
+ * This is how the seq-concat torch.concat([mip, x], dim=1) of model/decoder.py:40 is consumed
+ * without being materialised.  split == 0: an ordinary contiguous (B*T,128) tensor in `batch`. */
+typedef struct {
+    const float* shared;
+    const float* batch;
+    int T;
+    int split;
+} dip_rows;
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1 -- fused sampler updates                                                                */
+/* ------------------------------------------------------------------------------------------ */
+/* One guided/unguided DDIM update, model/diffusion.py:610,638-643 (guided) and :686-699:
+ *   x0-param:  e = (x - out*sqrt_at)/s1m ;  eps-param: e = out, x0 = (x - s1m*e)/sqrt_at
+ *   e -= gs*grad (if grad);  x_prev = sqrt_aprev*x0 + c_dir*e + sigma*noise (if noise)
+ * fp32, same operation order and rounding as the reference's separate torch ops (no FMA
+ * contraction) so the result is bit-identical to the CPU reference for identical inputs.
+ * x, x_prev: (B, L*128) contiguous.  model_out / grad: element (b,i) at ptr[b*stride + i].
+ * x0_out (nullable): contiguous (B, L*128) copy of pred_x0. */
+int dip_ddim_step(float* x_prev, float* x0_out, const float* x, const float* model_out, int64_t out_stride,
+                  const float* grad, int64_t grad_stride, const float* noise, int B, int L,
+                  float sqrt_at, float s1m, float c_dir, float sqrt_aprev, float sigma, float gs,
+                  int eps_param, dip_stream_t stream);
+
+/* DDPM posterior mean, model/diffusion.py:463-485: mean = c1*x0 + c2*x
+ * (eps-param: x0 = sqrt_recip*x - sqrt_recipm1*out first, :487-491). */
+int dip_ddpm_mean(float* mean, const float* x, const float* model_out, int64_t out_stride, int B, int L,
+                  float c1, float c2, int eps_param, float sqrt_recip, float sqrt_recipm1, dip_stream_t stream);
+/* DDPM ancestral update, model/diffusion.py:445-454: x_prev = (mean - gs*std*grad) + nonzero*std*noise. */
+int dip_ddpm_update(float* x_prev, const float* mean, const float* grad, int64_t grad_stride,
+                    const float* noise, int B, int L, float std, float gs, float nonzero, dip_stream_t stream);
+
+/* Counter-based N(0,1) generator (Philox4x32-10 + Box-Muller): element i of stream (seed, subseq)
+ * depends only on (seed, subseq, i) -- any sharding of samples over GPUs draws identical noise.
+ * Replaces torch.randn_like / noise_like (model/diffusion.py:583, model/utils.py:183-186). */
+int dip_randn(float* out, int64_t n, uint64_t seed, uint64_t subseq, dip_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K4 -- transformer block pieces (fp32 SIMT path)                                            */
+/* ------------------------------------------------------------------------------------------ */
+#define DIP_ACT_NONE 0
+#define DIP_ACT_QUICKGELU 1
+#define DIP_ACT_RELU 2
+#define DIP_ACT_SIGMOID 3
+#define DIP_ACT_MUL_QUICKGELU_GRAD 4   /* C = acc * d/du[u*sigmoid(1.702u)] at u = aux */
+
+/* C = act(A . W^T + bias*row_bias_scale + addmat[t] + residual), the torch.nn.Linear calls of
+ * model/modules.py:293-296 and model/diffusion.py:160 with their elementwise neighbours fused.
+ * A: (M,K) row-major, lda.  W: (N,K) row-major (nn.Linear layout).  N % 128 == 0, K % 16 == 0.
+ * Row remap (rows_in > 0): input row r = b*rows_in + t is written to output row
+ * b*rows_out + row_off + t, and addmat row t (rows_in, N) is added -- this is how the feature-concat
+ * + time-token concat of model/diffusion.py:156-158 is consumed without being built.
+ * residual (nullable via res.batch == NULL): added before the activation.
+ * preact (nullable): receives the pre-activation value (saved for the backward pass).
+ * aux: operand of DIP_ACT_MUL_QUICKGELU_GRAD, (M,N) with ldc. */
+typedef struct {
+    const float* A; int lda;
+    const float* W;
+    const float* bias;
+    float* C; int ldc;
+    int M, N, K;
+    int act;
+    int rows_in, rows_out, row_off;
+    const float* addmat;
+    dip_rows res;
+    const float* row_bias_scale;
+    float* preact;
+    const float* aux;
+} dip_gemm_args;
+int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream);
+
+/* y = LayerNorm(x) over 128 features, eps 1e-5, affine (model/modules.py:280,288).  mean / rstd
+ * (nullable) receive the per-row statistics for the backward pass. */
+int dip_layernorm_fwd(float* y, float* mean, float* rstd, dip_rows x, const float* gamma, const float* beta,
+                      int64_t rows, dip_stream_t stream);
+/* dx = dres + dLayerNorm/dx (dy)   (input gradient only -- no dgamma/dbeta: the sampler never uses
+ * weight gradients).  row_begin..row_end restrict the rows written
+ * (rows are global indices b*T+t of `x`); rows_per_batch/t_min skip rows with t < t_min. */
+int dip_layernorm_bwd(float* dx, const float* dy, dip_rows x, const float* mean, const float* rstd,
+                      const float* gamma, const float* dres, int64_t rows, int t_min, dip_stream_t stream);
+
+/* softmax(Q K^T / sqrt(128) + keymask) V  for one head of width 128 -- the
+ * F.scaled_dot_product_attention inside nn.MultiheadAttention (model/modules.py:291).
+ * q,k,v: row (b*T+t) at ptr + row*ld (ld = 384 for the packed in_proj output).  key_mask: bytes,
+ * sample b's T flags start at key_mask + b*mask_stride (stride 0: one mask shared by the wave);
+ * non-zero = masked key (key_padding_mask semantics), nullable.  o: (B*T,128) ld 128.
+ * lse: (B*T) natural-log row sums (saved for the backward pass). */
+int dip_attn_fwd(float* o, float* lse, const float* q, const float* k, const float* v, int ld,
+                 const uint8_t* key_mask, int64_t mask_stride, int B, int T, dip_stream_t stream);
+/* Input gradients dq, dk, dv (row stride ld_d) from do; deterministic (no atomics).
+ * delta_ws: (B*T) floats of scratch. */
+int dip_attn_bwd(float* dq, float* dk, float* dv, int ld_d, const float* q, const float* k, const float* v, int ld,
+                 const float* o, const float* d_o, const float* lse, const uint8_t* key_mask, int64_t mask_stride,
+                 float* delta_ws, int B, int T, dip_stream_t stream);
+
+/* Row 0 of every sample of the denoiser's first hidden layer: QuickGELU(W1 . temb(t) + b1) with
+ * temb the 256-wide sinusoidal embedding of model/diffusion.py:39-74.  out: (B, T, 128), row 0. */
+int dip_time_token(float* out, int B, int T, float t, const float* W1, const float* b1, dip_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* decoder head + K2 guidance                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+/* p_full[b,t] = sigmoid(y[b, T-L+t,:].w + beta), 0 at padded t (model/decoder.py:47-50).
+ * y: (B, T, 128) -- the last L rows of each sample are used.  kpm: (L) bytes (shared by the wave). */
+int dip_decoder_head_fwd(float* p_full, const float* y, int B, int T, int L, const float* w, const float* beta,
+                         const uint8_t* kpm, dip_stream_t stream);
+/* dy[b, t, :] = 0 for t < T-L, dz[b, t-(T-L)] * w for the last L rows. */
+int dip_decoder_head_bwd(float* dy, const float* dz, int B, int T, int L, const float* w, dip_stream_t stream);
+
+/* The guidance loss and its gradient w.r.t. the decoder logits, model/diffusion.py:623-633:
+ *   p = p_full[:, pos_of_col];  r = A p - b;  h = 1[r>0] + .5*1[r==0];
+ *   dp = (1-lam) A^T h + lam c;  dz[:, pos_of_col] = dp * p (1-p)   (0 elsewhere)
+ *   viol[b] = sum_i max(r_i,0);  obj[b] = p.c;  r_out (nullable): (B,M).
+ * CSR/CSC from dip_coo_to_csr_csc_host (device copies).  One CTA per sample; p and h staged in
+ * shared memory; per-row / per-column reductions by warp shuffles in a fixed order. */
+int dip_guidance(float* dz, float* viol, float* obj, float* r_out, float* dp_out, const float* p_full,
+                 const int32_t* pos_of_col, const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_val,
+                 const int32_t* csc_colptr, const int32_t* csc_row, const float* csc_val,
+                 const float* b, const float* c, float lam, int B, int L, int n, int M, int64_t nnz,
+                 dip_stream_t stream);
+
+/* round + feasibility, sample.py:164-174 / sample_partialsol.py:166-170:
+ *   xbits = round-half-even(p) ;  penalty[b] = sum_i max((A x)_i - b_i, 0)  (fp32, reference form)
+ * and, when the integer instance (csr_val_int, b_int, c_int) is given, the exact twin
+ *   viol_int[b] = sum_i max((A_int x)_i - b_int_i, 0),  obj_int[b] = c_int . x. */
+int dip_round_feasibility(uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int,
+                          const float* p_full, const int32_t* pos_of_col,
+                          const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_val,
+                          const int32_t* csr_val_int, const float* b, const int32_t* b_int, const int32_t* c_int,
+                          int B, int L, int n, int M, int64_t nnz, dip_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K3 -- bipartite GNN encoder pieces (model/modules.py:104-268)                              */
+/* ------------------------------------------------------------------------------------------ */
+/* y = act((x + shift) * scale . W^T + bias) for tiny K (5 / 17 input features): PreNormLayer +
+ * first embedding Linear, model/modules.py:219-238.  shift/scale nullable (K entries). */
+int dip_linear_smallk(float* y, const float* x, int64_t rows, int K, const float* shift, const float* scale,
+                      const float* W, const float* bias, int act, dip_stream_t stream);
+/* Half-convolution segment reduce, model/modules.py:203-212 with the per-edge final Linear hoisted
+ * after the sum:  acc[i,:] = sum_{e in seg(i)} relu(s * (PL[i,:] + we[:]*a'_e + PR[nbr_e,:])),
+ * a'_e = (a_e + a_shift) * a_scale (the edge PreNormLayer, modules.py:228-230), deg[i] = |seg(i)|.
+ * seg = CSR over targets (ptr, nbr, raw edge value a_e). */
+int dip_conv_reduce(float* acc, float* deg, const float* PL, const float* PR, const float* we, float s,
+                    float a_shift, float a_scale, const int32_t* ptr, const int32_t* nbr, const float* a,
+                    int n_target, dip_stream_t stream);
+/* y[i,:] = sum_e val_e * X[nbr_e,:] + add[i,:]   (A.mm(f) + C, model/modules.py:159-160). */
+int dip_spmm_csr(float* y, const float* X, const float* add, const int32_t* ptr, const int32_t* nbr,
+                 const float* val, int n_rows, dip_stream_t stream);
+/* out[t,:] = t < n ? src[idx[t],:] : 0   (gather int_indices + zero pad, model/cmsp.py:54-60). */
+int dip_gather_pad(float* out, const float* src, const int64_t* idx, int n, int L, dip_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* engine -- the S-step guided sampler over one wave of B samples of one instance             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct dip_engine dip_engine;
+
+/* One ResidualAttentionBlock's parameters (model/modules.py:274-296), device pointers, reference
+ * state_dict layout: in_proj_weight (384,128), out_proj.weight (128,128), c_fc / c_proj (128,128). */
+typedef struct {
+    const float *ln1_w, *ln1_b, *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b;
+    const float *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
+} dip_block_weights;
+
+int dip_engine_create(dip_engine** out);
+void dip_engine_destroy(dip_engine* e);
+
+/* NoisePredictV2 (model/diffusion.py:120-151): mlp_xt.linear_1 (128,256), linear_2 (128,128), blocks.
+ * Weights are copied (and pre-transposed for the backward GEMMs) into engine-owned memory. */
+int dip_engine_set_denoiser(dip_engine* e, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const dip_block_weights* blocks, int n_layers, dip_stream_t stream);
+/* MipConditionalDecorder (model/decoder.py:11-36): blocks + linear_proj (1,128). */
+int dip_engine_set_decoder(dip_engine* e, const dip_block_weights* blocks, int n_layers,
+                           const float* proj_w, const float* proj_b, dip_stream_t stream);
+
+/* The instance every sample of the wave shares: mip (L,128) conditions (one row of the repeated
+ * `conditions` batch of sample.py:151), kpm (L) bytes, pos_of_col (n), CSR + CSC of A (M,n), b (M),
+ * c (n); optional exact-integer twin (csr_val_int, b_int, c_int; nullable).  Pointers are BORROWED:
+ * they must stay valid until the next dip_engine_set_instance / destroy. */
+typedef struct {
+    int L, n, M;
+    int64_t nnz;
+    const float* mip;
+    const uint8_t* kpm;
+    const int32_t* pos_of_col;
+    const int32_t *csr_rowptr, *csr_col; const float* csr_val;
+    const int32_t *csc_colptr, *csc_row; const float* csc_val;
+    const float *b, *c;
+    const int32_t *csr_val_int, *b_int, *c_int;
+} dip_instance;
+int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_t stream);
+
+/* Scratch the caller provides (torch-allocated) for a wave of B samples. */
+size_t dip_engine_workspace_bytes(const dip_engine* e, int B);
+
+/* x-hat0 / eps = NoisePredictV2.apply_model(x, t, mip, kpm)  (model/diffusion.py:153-180).
+ * out: (B, L, 128) contiguous. */
+int dip_engine_denoise(dip_engine* e, float* out, const float* x, int B, float t,
+                       void* workspace, size_t workspace_bytes, dip_stream_t stream);
+/* p_full (B,L) = decoder probabilities (0 at padding), model/decoder.py:38-50.  y_last (nullable):
+ * (B,L,128) copy of the last-L hidden rows (input of linear_proj / select_net, decoder.py:45-52). */
+int dip_engine_decode(dip_engine* e, float* p_full, float* y_last, const float* x, int B,
+                      void* workspace, size_t workspace_bytes, dip_stream_t stream);
+/* grad (B, L, 128) = d loss / d x with loss of model/diffusion.py:623-633 (decoder forward, K2,
+ * decoder input-gradient backward).  viol/obj (B) and p_full (B,L) are side outputs (nullable). */
+int dip_engine_guidance_grad(dip_engine* e, float* grad, float* p_full, float* viol, float* obj,
+                             const float* x, int B, float lam, void* workspace, size_t workspace_bytes,
+                             dip_stream_t stream);
+
+/* Per-step coefficients of the DDIM schedule, computed by the host exactly as the reference does
+ * (model/diffusion.py:601-604,640-643; see oracle/restate.py:ddim_step_coeffs). */
+typedef struct { float t; float sqrt_at, s1m, c_dir, sqrt_aprev, sigma; } dip_ddim_coeffs;
+
+/* One guided DDIM step in place: x <- x_prev  (model/diffusion.py:594-644).  x0_out nullable.
+ * noise nullable (sigma == 0 in every reference script). */
+int dip_engine_guided_ddim_step(dip_engine* e, float* x, float* x0_out, int B, const dip_ddim_coeffs* co,
+                                float gs, float lam, int eps_param, const float* noise,
+                                void* workspace, size_t workspace_bytes, dip_stream_t stream);
+/* One unguided DDIM step in place (model/diffusion.py:674-699). */
+int dip_engine_ddim_step(dip_engine* e, float* x, float* x0_out, int B, const dip_ddim_coeffs* co, int eps_param,
+                         const float* noise, void* workspace, size_t workspace_bytes, dip_stream_t stream);
+
+/* The whole S-step guided loop (model/diffusion.py:582-592), in place on x, steps[0..S-1] in
+ * execution order, followed by the final decode + round + feasibility of sample.py:162-174.
+ * Outputs (device, nullable): xbits (B,n) bytes, penalty (B) fp32, viol_int (B), obj_int (B). */
+int dip_engine_sample_guided_ddim(dip_engine* e, float* x, int B, const dip_ddim_coeffs* steps, int S,
+                                  float gs, float lam, int eps_param,
+                                  uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int,
+                                  void* workspace, size_t workspace_bytes, dip_stream_t stream);
+/* Final decode + round + feasibility only. */
+int dip_engine_final_decode(dip_engine* e, const float* x, int B, float* p_full, uint8_t* xbits, float* penalty,
+                            int64_t* viol_int, int64_t* obj_int, void* workspace, size_t workspace_bytes,
+                            dip_stream_t stream);
+
+/* DDPM guided step (model/diffusion.py:429-454): x <- x_prev.  noise required unless nonzero == 0. */
+typedef struct { float t; float c1, c2, std; float nonzero; float sqrt_recip, sqrt_recipm1; } dip_ddpm_coeffs;
+int dip_engine_guided_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_coeffs* co, float gs, float lam,
+                                int eps_param, const float* noise, void* workspace, size_t workspace_bytes,
+                                dip_stream_t stream);
+int dip_engine_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_coeffs* co, int eps_param,
+                         const float* noise, void* workspace, size_t workspace_bytes, dip_stream_t stream);
+
+/* Number of kernel launches the library has issued since load (bench.py reports the delta). */
+uint64_t dip_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIP_B200_H */

@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Imports the UNMODIFIED reference modules from /root/reference (present only in the build
+container, never on the GPU box) behind the shims of ``oracle/shims.py`` and hands them back
+as a namespace.  The reference's top-level package is called ``model`` -- the same name as
+this repo's drop-in mirror -- so the reference modules are imported, captured and then removed
+from ``sys.modules`` again; both can live in one process.
+
+Used by ``oracle/gen_golden.py`` (fixture generation) and by the CPU tests that validate
+``oracle/restate.py`` against the real reference when it is available.
+"""
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("DIP_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "diffusion.py"))
+
+
+_cache = None
+
+
+def load():
+    """Return a namespace with the reference's classes (DDIMSampler, DDPMSampler, DDPMTrainer,
+    MipConditionalDecorder, CMSP, ...) imported from the unmodified files."""
+    global _cache
+    if _cache is not None:
+        return _cache
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    from . import shims
+    shims.install()
+
+    saved = {k: v for k, v in sys.modules.items() if k == "model" or k.startswith("model.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import importlib
+        diffusion = importlib.import_module("model.diffusion")
+        decoder = importlib.import_module("model.decoder")
+        cmsp = importlib.import_module("model.cmsp")
+        modules = importlib.import_module("model.modules")
+        utils = importlib.import_module("model.utils")
+        encoder = importlib.import_module("model.encoder")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            sys.modules["_dipref_" + k] = sys.modules.pop(k)
+        sys.modules.update(saved)
+
+    ns = types.SimpleNamespace(
+        diffusion=diffusion, decoder=decoder, cmsp=cmsp, modules=modules, utils=utils, encoder=encoder,
+        DDIMSampler=diffusion.DDIMSampler, DDPMSampler=diffusion.DDPMSampler,
+        DDPMTrainer=diffusion.DDPMTrainer, MipConditionalDecorder=decoder.MipConditionalDecorder,
+        CMSP=cmsp.CMSP, root=REFERENCE_ROOT,
+    )
+    _cache = ns
+    return ns

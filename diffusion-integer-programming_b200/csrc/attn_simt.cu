@@ -413,6 +413,7 @@ int dip_attn_fwd(float* o, float* lse, const float* q, const float* k, const flo
     DIP_REQUIRE(B <= 65535, "dip_attn_fwd: B too large for one launch");
     DIP_TRY(set_attrs());
     dim3 grid(cdiv(T, AT), B);
+    DIP_PROF(DIP_PROF_ATTN_FWD, stream);
     attn_fwd_kernel<<<grid, 256, FWD_SMEM, as_stream(stream)>>>(o, lse, q, k, v, ld, key_mask, mask_stride, T);
     DIP_LAUNCHED();
     return 0;
@@ -428,13 +429,22 @@ int dip_attn_bwd(float* dq, float* dk, float* dv, int ld_d, const float* q, cons
     cudaStream_t st = as_stream(stream);
     int64_t rows = (int64_t)B * T;
     int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 8;
-    attn_delta_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(delta_ws, o, d_o, rows);
-    DIP_LAUNCHED();
+    {
+        DIP_PROF(DIP_PROF_OTHER, stream);
+        attn_delta_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(delta_ws, o, d_o, rows);
+        DIP_LAUNCHED();
+    }
     dim3 grid(cdiv(T, AT), B);
-    attn_bwd_dkdv_kernel<<<grid, 256, DKDV_SMEM, st>>>(dk, dv, ld_d, q, k, v, ld, d_o, lse, delta_ws, key_mask, mask_stride, T);
-    DIP_LAUNCHED();
-    attn_bwd_dq_kernel<<<grid, 256, DQ_SMEM, st>>>(dq, ld_d, q, k, v, ld, d_o, lse, delta_ws, key_mask, mask_stride, T);
-    DIP_LAUNCHED();
+    {
+        DIP_PROF(DIP_PROF_ATTN_BWD_DKDV, stream);
+        attn_bwd_dkdv_kernel<<<grid, 256, DKDV_SMEM, st>>>(dk, dv, ld_d, q, k, v, ld, d_o, lse, delta_ws, key_mask, mask_stride, T);
+        DIP_LAUNCHED();
+    }
+    {
+        DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
+        attn_bwd_dq_kernel<<<grid, 256, DQ_SMEM, st>>>(dq, ld_d, q, k, v, ld, d_o, lse, delta_ws, key_mask, mask_stride, T);
+        DIP_LAUNCHED();
+    }
     return 0;
 }
 

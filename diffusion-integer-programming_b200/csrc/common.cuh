@@ -16,6 +16,16 @@ extern std::atomic<uint64_t> g_launches;
 
 inline cudaStream_t as_stream(dip_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// In-library kernel timer (dip_prof_*): when enabled, every launcher brackets its launch with a
+// pair of CUDA events on the launching stream; dip_prof_collect sums them per kernel class.
+struct ProfScope {
+    int slot;
+    cudaStream_t st;
+    ProfScope(int cls, cudaStream_t s);
+    ~ProfScope();
+};
+#define DIP_PROF(cls, stream) dip::ProfScope _prof_scope((cls), dip::as_stream(stream))
+
 #define DIP_FAIL(...)                                  \
     do {                                               \
         dip::set_error(__VA_ARGS__);                   \

@@ -3,6 +3,7 @@
 // sized as a multiple of the SM count.
 #include <stdarg.h>
 #include <math.h>
+#include <vector>
 #include "common.cuh"
 
 namespace dip {
@@ -15,6 +16,27 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- profiler ----------------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int cls; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+
+ProfScope::ProfScope(int cls, cudaStream_t s) : slot(-1), st(s) {
+    if (!g_prof_on) return;
+    if (g_prof_used == g_prof.size()) {
+        ProfRec r;
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        g_prof.push_back(r);
+    }
+    slot = (int)g_prof_used++;
+    g_prof[slot].cls = cls;
+    cudaEventRecord(g_prof[slot].a, st);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
 }
 
 static int g_sm_count = 0;
@@ -263,6 +285,25 @@ int dip_abi_version(void) { return DIP_ABI_VERSION; }
 const char* dip_last_error(void) { return dip::g_err; }
 uint64_t dip_launch_count(void) { return dip::g_launches.load(); }
 
+void dip_prof_enable(int on) {
+    dip::g_prof_on = on != 0;
+    if (on) dip::g_prof_used = 0;
+}
+
+int dip_prof_collect(double* ms_per_class, uint64_t* launches_per_class, int n_classes) {
+    DIP_REQUIRE(ms_per_class && launches_per_class && n_classes > 0, "dip_prof_collect: bad argument");
+    for (int i = 0; i < n_classes; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+    for (size_t i = 0; i < dip::g_prof_used; ++i) {
+        dip::ProfRec& r = dip::g_prof[i];
+        DIP_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        DIP_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cls >= 0 && r.cls < n_classes) { ms_per_class[r.cls] += ms; launches_per_class[r.cls] += 1; }
+    }
+    dip::g_prof_used = 0;
+    return 0;
+}
+
 int dip_check_device(int dev, int* sm, int* major, int* minor) {
     cudaDeviceProp prop;
     DIP_CUDA(cudaGetDeviceProperties(&prop, dev));
@@ -281,6 +322,7 @@ int dip_ddim_step(float* x_prev, float* x0_out, const float* x, const float* mod
     int64_t ps4 = (int64_t)L * D / 4, tot4 = ps4 * B;
     int grid = ew_grid(tot4);
     cudaStream_t st = as_stream(stream);
+    DIP_PROF(DIP_PROF_UPDATE, stream);
     bool g = grad != nullptr, nz = noise != nullptr, x0o = x0_out != nullptr;
     auto xp = reinterpret_cast<float4*>(x_prev);
     auto x0p = reinterpret_cast<float4*>(x0_out);
@@ -303,6 +345,7 @@ int dip_ddpm_mean(float* mean, const float* x, const float* model_out, int64_t o
                   int eps_param, float sqrt_recip, float sqrt_recipm1, dip_stream_t stream) {
     DIP_REQUIRE(mean && x && model_out && B > 0 && L > 0, "dip_ddpm_mean: null/empty argument");
     int64_t ps4 = (int64_t)L * D / 4, tot4 = ps4 * B;
+    DIP_PROF(DIP_PROF_UPDATE, stream);
     ddpm_mean_kernel<<<ew_grid(tot4), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(mean), reinterpret_cast<const float4*>(x),
                                                                    model_out, out_stride, ps4, tot4, c1, c2, eps_param, sqrt_recip, sqrt_recipm1);
     DIP_LAUNCHED();
@@ -313,6 +356,7 @@ int dip_ddpm_update(float* x_prev, const float* mean, const float* grad, int64_t
                     float stdv, float gs, float nonzero, dip_stream_t stream) {
     DIP_REQUIRE(x_prev && mean && B > 0 && L > 0, "dip_ddpm_update: null/empty argument");
     int64_t ps4 = (int64_t)L * D / 4, tot4 = ps4 * B;
+    DIP_PROF(DIP_PROF_UPDATE, stream);
     ddpm_update_kernel<<<ew_grid(tot4), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(x_prev), reinterpret_cast<const float4*>(mean),
                                                                      grad, grad_stride, reinterpret_cast<const float4*>(noise), ps4, tot4, stdv, gs, nonzero);
     DIP_LAUNCHED();
@@ -329,6 +373,7 @@ int dip_randn(float* out, int64_t n, uint64_t seed, uint64_t subseq, dip_stream_
 
 int dip_time_token(float* out, int B, int T, float t, const float* W1, const float* b1, dip_stream_t stream) {
     DIP_REQUIRE(out && W1 && b1 && B > 0 && T > 0, "dip_time_token: null/empty argument");
+    DIP_PROF(DIP_PROF_OTHER, stream);
     time_token_kernel<<<1, 128, 0, as_stream(stream)>>>(out, B, T, t, W1, b1);
     DIP_LAUNCHED();
     return 0;
@@ -337,6 +382,7 @@ int dip_time_token(float* out, int B, int T, float t, const float* W1, const flo
 int dip_decoder_head_fwd(float* p_full, const float* y, int B, int T, int L, const float* w, const float* beta,
                          const uint8_t* kpm, dip_stream_t stream) {
     DIP_REQUIRE(p_full && y && w && beta && kpm && B > 0 && L > 0 && T >= L, "dip_decoder_head_fwd: bad argument");
+    DIP_PROF(DIP_PROF_HEAD, stream);
     head_fwd_kernel<<<ew_grid((int64_t)B * L * 32), 256, 0, as_stream(stream)>>>(p_full, y, B, T, L, w, beta, kpm);
     DIP_LAUNCHED();
     return 0;
@@ -344,6 +390,7 @@ int dip_decoder_head_fwd(float* p_full, const float* y, int B, int T, int L, con
 
 int dip_decoder_head_bwd(float* dy, const float* dz, int B, int T, int L, const float* w, dip_stream_t stream) {
     DIP_REQUIRE(dy && dz && w && B > 0 && L > 0 && T >= L, "dip_decoder_head_bwd: bad argument");
+    DIP_PROF(DIP_PROF_HEAD, stream);
     head_bwd_kernel<<<ew_grid((int64_t)B * T * (D / 4)), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(dy), dz, B, T, L, w);
     DIP_LAUNCHED();
     return 0;

@@ -242,7 +242,9 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     dip_gemm_args g = gemm(x, D, e->w1x, nullptr, w.tmp, D, (int64_t)B * L, D, D, DIP_ACT_QUICKGELU);
     g.rows_in = L; g.rows_out = T1; g.row_off = 1; g.addmat = e->mproj;
     DIP_TRY(dip_gemm_nt(&g, st));
-    g = gemm(w.tmp, D, e->w2, e->b2, w.hd, D, R1, D, D, DIP_ACT_QUICKGELU);
+    // NO activation after linear_2: the reference's OrderedDict names both QuickGELUs "geru", so the
+    // second entry replaces the first and mlp_xt is linear_1 -> QuickGELU -> linear_2 (diffusion.py:145-150)
+    g = gemm(w.tmp, D, e->w2, e->b2, w.hd, D, R1, D, D, DIP_ACT_NONE);
     DIP_TRY(dip_gemm_nt(&g, st));
     for (int l = 0; l < e->n_den; ++l)
         DIP_TRY(block_fwd(e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.ao1, nullptr, nullptr, nullptr, nullptr,

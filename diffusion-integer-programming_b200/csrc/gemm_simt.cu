@@ -151,6 +151,7 @@ int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream) {
     GemmParams P;
     P.a = g;
     dim3 grid(cdiv(g.M, GBM), g.N / GBN);
+    DIP_PROF(DIP_PROF_GEMM, stream);
     gemm_nt_kernel<<<grid, 256, 0, as_stream(stream)>>>(P);
     DIP_LAUNCHED();
     return 0;

@@ -74,6 +74,7 @@ extern "C" {
 int dip_conv_reduce(float* acc, float* deg, const float* PL, const float* PR, const float* we, float s, float a_shift, float a_scale,
                     const int32_t* ptr, const int32_t* nbr, const float* a, int n_target, dip_stream_t stream) {
     DIP_REQUIRE(acc && deg && PL && PR && we && ptr && nbr && a && n_target > 0, "dip_conv_reduce: bad argument");
+    DIP_PROF(DIP_PROF_GNN, stream);
     conv_reduce_kernel<<<warp_grid(n_target), 256, 0, as_stream(stream)>>>(acc, deg, PL, PR, we, s, a_shift, a_scale, ptr, nbr, a, n_target);
     DIP_LAUNCHED();
     return 0;
@@ -82,6 +83,7 @@ int dip_conv_reduce(float* acc, float* deg, const float* PL, const float* PR, co
 int dip_spmm_csr(float* y, const float* X, const float* add, const int32_t* ptr, const int32_t* nbr, const float* val, int n_rows,
                  dip_stream_t stream) {
     DIP_REQUIRE(y && X && ptr && nbr && val && n_rows > 0, "dip_spmm_csr: bad argument");
+    DIP_PROF(DIP_PROF_GNN, stream);
     spmm_csr_kernel<<<warp_grid(n_rows), 256, 0, as_stream(stream)>>>(y, X, add, ptr, nbr, val, n_rows);
     DIP_LAUNCHED();
     return 0;

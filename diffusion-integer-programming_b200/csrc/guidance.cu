@@ -173,6 +173,7 @@ int dip_guidance(float* dz, float* viol, float* obj, float* r_out, float* dp_out
     int Gr = pick_group(nnz, M), Gc = pick_group(nnz, n);
     // (1 - lam) is formed in double like the reference's Python float and rounded once (diffusion.py:633)
     float oml = (float)(1.0 - (double)lam);
+    DIP_PROF(DIP_PROF_GUIDANCE, stream);
     guidance_kernel<<<B, 256, smem, as_stream(stream)>>>(dz, viol, obj, r_out, dp_out, p_full, pos_of_col, csr_rowptr, csr_col, csr_val,
                                                          csc_colptr, csc_row, csc_val, b, c, oml, lam, L, n, M, Gr, Gc);
     DIP_LAUNCHED();
@@ -193,6 +194,7 @@ int dip_round_feasibility(uint8_t* xbits, float* penalty, int64_t* viol_int, int
         DIP_CUDA(cudaFuncSetAttribute(round_feas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = 200 * 1024;
     }
+    DIP_PROF(DIP_PROF_GUIDANCE, stream);
     round_feas_kernel<<<B, 256, smem, as_stream(stream)>>>(xbits, penalty, reinterpret_cast<long long*>(viol_int),
                                                            reinterpret_cast<long long*>(obj_int), p_full, pos_of_col, csr_rowptr, csr_col,
                                                            csr_val, csr_val_int, b, b_int, c_int, L, n, M, pick_group(nnz, M));

@@ -77,6 +77,7 @@ int dip_layernorm_fwd(float* y, float* mean, float* rstd, dip_rows x, const floa
     DIP_REQUIRE(y && x.batch && gamma && beta && rows > 0, "dip_layernorm_fwd: bad argument");
     DIP_REQUIRE((mean == nullptr) == (rstd == nullptr), "dip_layernorm_fwd: mean and rstd go together");
     DIP_REQUIRE(x.split == 0 || (x.shared && x.T > x.split), "dip_layernorm_fwd: bad row source");
+    DIP_PROF(DIP_PROF_LN, stream);
     ln_fwd_kernel<<<ln_grid(rows), 256, 0, as_stream(stream)>>>(y, mean, rstd, x, gamma, beta, rows);
     DIP_LAUNCHED();
     return 0;
@@ -86,6 +87,7 @@ int dip_layernorm_bwd(float* dx, const float* dy, dip_rows x, const float* mean,
                       const float* dres, int64_t rows, int t_min, dip_stream_t stream) {
     DIP_REQUIRE(dx && dy && x.batch && mean && rstd && gamma && rows > 0, "dip_layernorm_bwd: bad argument");
     DIP_REQUIRE(t_min == 0 || x.T > 0, "dip_layernorm_bwd: t_min needs rows.T");
+    DIP_PROF(DIP_PROF_LN, stream);
     ln_bwd_kernel<<<ln_grid(rows), 256, 0, as_stream(stream)>>>(dx, dy, x, mean, rstd, gamma, dres, rows, x.T > 0 ? x.T : 1, t_min);
     DIP_LAUNCHED();
     return 0;

@@ -106,7 +106,11 @@ PROTOTYPES = {
     "dip_engine_guided_ddpm_step": (i32, [vp, vp, i32, C.POINTER(DdpmCoeffs), f32, f32, i32, vp, vp, sz, vp]),
     "dip_engine_ddpm_step": (i32, [vp, vp, i32, C.POINTER(DdpmCoeffs), i32, vp, vp, sz, vp]),
     "dip_launch_count": (u64, []),
+    "dip_prof_enable": (None, [i32]),
+    "dip_prof_collect": (i32, [C.POINTER(C.c_double), C.POINTER(u64), i32]),
 }
+
+PROF_CLASSES = ["gemm", "layernorm", "attn_fwd", "attn_bwd_dkdv", "attn_bwd_dq", "guidance", "update", "head", "gnn", "other"]
 
 _lib = None
 

@@ -299,6 +299,23 @@ int dip_engine_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_coeffs* 
 /* Number of kernel launches the library has issued since load (bench.py reports the delta). */
 uint64_t dip_launch_count(void);
 
+/* Optional in-library kernel timer: while enabled every launcher records a CUDA-event pair around
+ * its launch on the launching stream; dip_prof_collect waits for them and returns the summed
+ * milliseconds and launch counts per kernel class (then resets). */
+#define DIP_PROF_GEMM 0
+#define DIP_PROF_LN 1
+#define DIP_PROF_ATTN_FWD 2
+#define DIP_PROF_ATTN_BWD_DKDV 3
+#define DIP_PROF_ATTN_BWD_DQ 4
+#define DIP_PROF_GUIDANCE 5
+#define DIP_PROF_UPDATE 6
+#define DIP_PROF_HEAD 7
+#define DIP_PROF_GNN 8
+#define DIP_PROF_OTHER 9
+#define DIP_PROF_NCLASSES 10
+void dip_prof_enable(int on);
+int dip_prof_collect(double* ms_per_class, uint64_t* launches_per_class, int n_classes);
+
 #ifdef __cplusplus
 }
 #endif

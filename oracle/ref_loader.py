@@ -37,7 +37,11 @@ def load():
     saved = {k: v for k, v in sys.modules.items() if k == "model" or k.startswith("model.")}
     for k in saved:
         del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
+    # the reference's `model/` has no __init__.py (namespace package) and would lose against any
+    # regular `model` package later on sys.path (this repo's mirror): hide those entries meanwhile
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [p for p in saved_path
+                                      if not os.path.isdir(os.path.join(p or ".", "model")) and p != REFERENCE_ROOT]
     try:
         import importlib
         diffusion = importlib.import_module("model.diffusion")
@@ -47,7 +51,7 @@ def load():
         utils = importlib.import_module("model.utils")
         encoder = importlib.import_module("model.encoder")
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
         for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
             sys.modules["_dipref_" + k] = sys.modules.pop(k)
         sys.modules.update(saved)

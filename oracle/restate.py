@@ -150,8 +150,10 @@ def denoiser_fwd(W, x, t, mip, kpm, prefix="predict_model."):
     g = lambda k: W[prefix + k].to(x.dtype)
     temb = timestep_embedding(t, 2 * D_MODEL).to(x.dtype).unsqueeze(-2)
     z = torch.cat([temb, torch.cat([mip, x], dim=-1)], dim=-2)
+    # mlp_xt is built from an OrderedDict with the key "geru" used twice (diffusion.py:145-150): the second
+    # entry REPLACES the first, so the Sequential is linear_1 -> QuickGELU -> linear_2 with NO final activation.
     z = quick_gelu(z @ g("mlp_xt.linear_1.weight").t() + g("mlp_xt.linear_1.bias"))
-    z = quick_gelu(z @ g("mlp_xt.linear_2.weight").t() + g("mlp_xt.linear_2.bias"))
+    z = z @ g("mlp_xt.linear_2.weight").t() + g("mlp_xt.linear_2.bias")
     mask = torch.cat([torch.zeros((x.shape[0], 1), dtype=torch.bool), kpm], dim=-1)
     for i in range(n_blocks(W, prefix + "resblocks.")):
         z = block_fwd(z, W, prefix + "resblocks.%d." % i, mask)

@@ -1,0 +1,212 @@
+"""GPU parity tests proper: the engine (C-ABI, libdip_b200.so) against the golden vectors produced
+by the unmodified reference and against the CPU oracle on the same seeded inputs.
+
+Protocol: P1 teacher-forced single steps at several schedule positions,
+P2 free-running first steps, P3 decode / round / feasibility bit-exact for identical latents.
+Tolerances: fp32 one-step relative L2 <= 1e-4 on latents/gradients (north_star bar: 1e-3; the
+reference's own fp32-vs-fp64 noise floor is ~2e-7, the kernels' differing summation order ~1e-6);
+0/1 assignments, feasibility flags and integer objectives exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from dip_b200 import synth
+from helpers import golden, tw, rel_l2, case_tensors, coalesced, small_case, small_graph, sc_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def make_engine(cuda, cs, n_den=1, n_dec=2, wseed=1, ints=False):
+    from dip_b200.engine import Engine
+    eng = Engine()
+    eng.set_denoiser(tw(synth.denoiser_weights(n_den, seed=wseed), cuda))
+    eng.set_decoder(tw(synth.decoder_weights(n_dec, seed=wseed + 1), cuda))
+    eng.set_instance(torch.from_numpy(cs.mip).to(cuda), torch.from_numpy(cs.kpm).to(cuda), cs.rows, cs.cols, cs.vals, cs.M, cs.b, cs.c)
+    return eng
+
+
+def coeffs(S, index):
+    from dip_b200.engine import Engine
+    from oracle import restate
+    tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], S)
+    c = restate.ddim_step_coeffs(tab, index)
+    return Engine.ddim_coeffs(S - 1 - index, c["sqrt_at"], c["s1m"], c["c_dir"], c["sqrt_aprev"], c["sigma"])
+
+
+def test_p1_teacher_forced_ddim_x0(cuda):
+    g = golden("ddim_guided_x0")
+    cs = small_case()
+    eng = make_engine(cuda, cs)
+    S, gs, lam = int(g["S"]), float(g["gs"]), float(g["lam"])
+    x_in = torch.from_numpy(cs.x).to(cuda)
+    for index in g["indices"]:
+        index = int(index)
+        x0 = eng.denoise(x_in, S - 1 - index)
+        assert rel_l2(x0, g["tf%d_x0" % index]) < TOL
+        grad, p_full, viol, obj = eng.guidance_grad(x_in, lam)
+        assert rel_l2(p_full[:, :cs.n], g["tf%d_p" % index]) < TOL
+        assert rel_l2(grad, g["tf%d_grad" % index]) < TOL
+        assert float(grad[:, cs.n:].abs().max()) == 0.0          # padded latents get exactly zero gradient
+        x = x_in.clone()
+        x0_out = torch.empty_like(x)
+        eng.guided_ddim_step(x, coeffs(S, index), gs, lam, x0_out=x0_out)
+        assert rel_l2(x, g["tf%d_xprev" % index]) < TOL
+        assert torch.equal(x0_out, x0)
+
+
+def test_p2_free_running_and_p3_final_decode(cuda):
+    g = golden("ddim_guided_x0")
+    cs = small_case()
+    eng = make_engine(cuda, cs)
+    S, gs, lam = int(g["S"]), float(g["gs"]), float(g["lam"])
+    x = torch.from_numpy(cs.x).to(cuda).clone()
+    for k in range(3):
+        eng.guided_ddim_step(x, coeffs(S, k), gs, lam)
+        assert rel_l2(x, g["free%d_x" % k]) < 1e-3 * (k + 1)
+    # P3: identical latents in -> bit-identical assignment / feasibility out
+    fd = eng.final_decode(torch.from_numpy(g["free2_x"]).to(cuda))
+    assert rel_l2(fd["p_full"][:, :cs.n], g["final_p"]) < TOL
+    assert np.array_equal(fd["xbits"].cpu().numpy().astype(np.float32), g["final_x"])
+    assert np.allclose(fd["penalty"].cpu().numpy(), g["final_penalty"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(fd["penalty"].cpu().numpy() <= 1e-5, g["final_penalty"] <= 1e-5)
+    margin = float((torch.from_numpy(g["final_p"]) - 0.5).abs().min())
+    assert margin > 1e-4, "fixture decode margin too small for a meaningful bit-exact check"
+    # unguided step
+    xu = torch.from_numpy(cs.x).to(cuda).clone()
+    eng.ddim_step(xu, coeffs(S, 0))
+    assert rel_l2(xu, g["unguided_xprev"]) < TOL
+
+
+def test_eps_parameterisation(cuda):
+    g = golden("ddim_guided_eps")
+    cs = small_case()
+    eng = make_engine(cuda, cs)
+    S, gs, lam = int(g["S"]), float(g["gs"]), float(g["lam"])
+    for index in g["indices"]:
+        index = int(index)
+        x = torch.from_numpy(cs.x).to(cuda).clone()
+        x0 = torch.empty_like(x)
+        eng.guided_ddim_step(x, coeffs(S, index), gs, lam, eps_param=True, x0_out=x0)
+        assert rel_l2(x0, g["tf%d_x0" % index]) < TOL
+        assert rel_l2(x, g["tf%d_xprev" % index]) < TOL
+
+
+def test_ddpm_steps(cuda):
+    from dip_b200 import _lib
+    from oracle import restate
+    g = golden("ddpm_guided_x0")
+    cs = small_case(seed=1)
+    eng = make_engine(cuda, cs)
+    buf = restate.trainer_buffers()
+    tabs = restate.ddpm_tables(buf)
+    for ti in g["ts"]:
+        ti = int(ti)
+        std = float((0.5 * tabs["posterior_log_variance_clipped"][ti]).exp())
+        co = _lib.DdpmCoeffs(float(ti), float(tabs["posterior_mean_coef1"][ti]), float(tabs["posterior_mean_coef2"][ti]), std,
+                             0.0 if ti == 0 else 1.0, float(buf["sqrt_recip_alphas_cumprod"][ti]), float(buf["sqrt_recipm1_alphas_cumprod"][ti]))
+        x = torch.from_numpy(cs.x).to(cuda).clone()
+        eng.guided_ddpm_step(x, co, float(g["gs"]), float(g["lam"]), noise=torch.from_numpy(g["t%d_noise" % ti]).to(cuda))
+        assert rel_l2(x, g["t%d_xprev" % ti]) < TOL
+        xu = torch.from_numpy(cs.x).to(cuda).clone()
+        eng.ddpm_step(xu, co, noise=torch.from_numpy(g["t%d_unoise" % ti]).to(cuda))
+        assert rel_l2(xu, g["t%d_unguided" % ti]) < TOL
+
+
+def test_encoder_vs_golden(cuda):
+    from dip_b200 import encoder, ops
+    g = golden("encoder_small")
+    gr = small_graph()
+    W = tw(synth.encoder_weights(seed=3), cuda)
+    w = {k[len("mip_encoder.gnn_model."):]: v for k, v in W.items()}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    v = encoder.gnn_forward(w, T(gr.cons), T(gr.edge_index), T(gr.edge_attr), T(gr.var))
+    assert rel_l2(v, g["var_features"]) < TOL
+    mip = ops.gather_pad(v, T(gr.int_indices), 24)
+    assert rel_l2(mip, g["mip_features"][0]) < TOL
+    assert float(mip[len(gr.int_indices):].abs().max()) == 0.0
+
+
+def test_one_call_sampler_equals_stepwise_and_is_deterministic(cuda):
+    cs = small_case()
+    eng = make_engine(cuda, cs)
+    S = 5
+    steps = [coeffs(S, k) for k in range(S)]
+    x1 = torch.from_numpy(cs.x).to(cuda).clone()
+    out = eng.sample_guided_ddim(x1, steps, 1e5, 0.9)
+    x2 = torch.from_numpy(cs.x).to(cuda).clone()
+    for co in steps:
+        eng.guided_ddim_step(x2, co, 1e5, 0.9)
+    fd = eng.final_decode(x2)
+    assert torch.equal(x1, x2) and torch.equal(out["xbits"], fd["xbits"]) and torch.equal(out["penalty"], fd["penalty"])
+    x3 = torch.from_numpy(cs.x).to(cuda).clone()
+    out3 = eng.sample_guided_ddim(x3, steps, 1e5, 0.9)
+    assert torch.equal(x1, x3) and torch.equal(out["xbits"], out3["xbits"])        # run-to-run bitwise
+
+
+def test_batch_invariance(cuda):
+    """A sample's trajectory must not depend on which wave it is in (sharding invariance)."""
+    cs = small_case(B=4)
+    eng = make_engine(cuda, cs)
+    S = 3
+    steps = [coeffs(S, k) for k in range(S)]
+    xa = torch.from_numpy(cs.x).to(cuda).clone()
+    eng.sample_guided_ddim(xa, steps, 1e5, 0.9)
+    for b in (0, 3):
+        xb = torch.from_numpy(cs.x[b:b + 1]).to(cuda).clone()
+        eng.sample_guided_ddim(xb, steps, 1e5, 0.9)
+        assert torch.equal(xa[b:b + 1], xb)
+
+
+def test_engine_errors(cuda):
+    from dip_b200 import _lib
+    from dip_b200.engine import Engine
+    eng = Engine()
+    with pytest.raises(_lib.DipError):
+        eng.workspace(2)                                     # no instance yet
+    cs = small_case()
+    eng.set_conditions(torch.from_numpy(cs.mip).to(cuda), torch.from_numpy(cs.kpm).to(cuda))
+    with pytest.raises(_lib.DipError, match="set_denoiser"):
+        eng.denoise(torch.from_numpy(cs.x).to(cuda), 3)
+    with pytest.raises(_lib.DipError):
+        eng._x(torch.from_numpy(cs.x))                       # CPU latent: no CPU path
+    with pytest.raises(_lib.DipError, match="objective vector"):
+        eng.set_instance(torch.from_numpy(cs.mip).to(cuda), torch.from_numpy(cs.kpm).to(cuda), cs.rows, cs.cols, cs.vals, cs.M, cs.b,
+                         np.zeros(cs.n + 1, np.float32))
+
+
+def test_full_size_set_cover_step_vs_oracle(cuda):
+    """BASELINE config shapes (L = n = 2000, M = 1000, nnz = 1e5, D = 128, n_d = 1, n_e = 2): one guided
+    step of 2 samples against the CPU oracle (a few seconds on the host)."""
+    from dip_b200.engine import Engine
+    from oracle import restate
+    inst, mip, kpm, x = sc_case(B=2)
+    Wd, Wdec = synth.denoiser_weights(1, seed=1), synth.decoder_weights(2, seed=2)
+    eng = Engine()
+    eng.set_denoiser(tw(Wd, cuda)); eng.set_decoder(tw(Wdec, cuda))
+    eng.set_instance(torch.from_numpy(mip).to(cuda), torch.from_numpy(kpm).to(cuda), inst.rows, inst.cols, inst.a_val, inst.M, inst.b, inst.c,
+                     a_int=inst.a_int, b_int=inst.b_int, c_int=inst.c_int)
+    S, gs, lam = 100, 1e5, 0.9
+    tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], S)
+    A = (torch.from_numpy(inst.rows), torch.from_numpy(inst.cols), torch.from_numpy(inst.a_val), inst.M)
+    mipB, kpmB = torch.from_numpy(mip)[None].repeat(2, 1, 1), torch.from_numpy(kpm)[None].repeat(2, 1)
+    ref = restate.guided_ddim_step(tw(Wd), tw(Wdec), torch.from_numpy(x), S - 1, restate.ddim_step_coeffs(tab, 0), mipB, kpmB, A,
+                                   torch.from_numpy(inst.b), torch.from_numpy(inst.c), gs, lam)
+    xg = torch.from_numpy(x).to(cuda).clone()
+    x0 = torch.empty_like(xg)
+    grad, p_full, viol, obj = eng.guidance_grad(xg, lam)
+    assert rel_l2(p_full, ref["p_full"]) < TOL
+    assert rel_l2(grad, ref["grad"]) < TOL
+    eng.guided_ddim_step(xg, coeffs(S, 0), gs, lam, x0_out=x0)
+    assert rel_l2(x0, ref["x0"]) < TOL
+    assert rel_l2(xg, ref["x_prev"]) < TOL
+    # P3 at full size: decode the oracle's latent on both sides
+    fd = eng.final_decode(ref["x_prev"].to(cuda))
+    ofd = restate.final_decode(tw(Wdec), mipB, ref["x_prev"], kpmB, A, torch.from_numpy(inst.b))
+    margin = (ofd["p"] - 0.5).abs()
+    safe = margin > 1e-4
+    assert np.array_equal(fd["xbits"].cpu().numpy()[safe.numpy()], ofd["x_int"].numpy().astype(np.uint8)[safe.numpy()])
+    feas, objv, violv = restate.feasibility_int(fd["xbits"].cpu().numpy(), inst.rows, inst.cols, inst.a_int, inst.M, inst.b_int, inst.c_int)
+    assert np.array_equal(fd["viol_int"].cpu().numpy(), violv) and np.array_equal(fd["obj_int"].cpu().numpy(), objv)
+    assert np.array_equal(fd["penalty"].cpu().numpy() <= 1e-5, feas)

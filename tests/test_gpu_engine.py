@@ -149,7 +149,7 @@ def test_batch_invariance(cuda):
     """A sample's trajectory must not depend on which wave it is in (sharding invariance)."""
     cs = small_case(B=4)
     eng = make_engine(cuda, cs)
-    S = 3
+    S = 4            # S = 3 would index alpha-bar[1000] (SURVEY section 7 quirk 10)
     steps = [coeffs(S, k) for k in range(S)]
     xa = torch.from_numpy(cs.x).to(cuda).clone()
     eng.sample_guided_ddim(xa, steps, 1e5, 0.9)

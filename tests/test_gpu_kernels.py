@@ -165,7 +165,8 @@ def test_time_token(cuda):
         emb = restate.timestep_embedding(torch.tensor([t]), 2 * D)
         ref = restate.quick_gelu(emb.double() @ W1.double().t() + b1.double())[0]
         out = ops.time_token(2, 5, t, W1.to(cuda), b1.to(cuda))
-        assert rel_l2(out[0, 0], ref) < 5e-6 and torch.equal(out[0, 0], out[1, 0]) and float(out[:, 1:].abs().max()) == 0.0
+        # t * f_k in fp32 amplifies a 1-ulp difference of expf (GPU vs host libm) by t: 999 * 6e-8 ~ 6e-5 rad
+        assert rel_l2(out[0, 0], ref) < (5e-6 if t < 100 else 5e-5) and torch.equal(out[0, 0], out[1, 0]) and float(out[:, 1:].abs().max()) == 0.0
 
 
 def test_decoder_head(cuda):
@@ -236,7 +237,9 @@ def test_round_feasibility_vs_oracle(cuda):
     assert feas[0] and not feas[1]
     r, c_, v, _ = (torch.from_numpy(inst.rows), torch.from_numpy(inst.cols), torch.from_numpy(inst.a_val), None)
     pen = torch.clamp(restate.spmv_rows(r, c_, v, inst.M, torch.from_numpy(xb).float()) - torch.from_numpy(inst.b), min=0).sum(-1)
-    assert torch.equal(out["penalty"].cpu(), pen)                          # integer-valued A: exact in fp32
+    # every row term max((Ax)_i - b_i, 0) is exact for integer-valued A; only the order of the row sum differs
+    assert torch.allclose(out["penalty"].cpu(), pen, rtol=1e-6, atol=0)
+    assert np.array_equal(out["penalty"].cpu().numpy() == 0, pen.numpy() == 0)
     assert np.array_equal((out["penalty"].cpu().numpy() <= 1e-5), feas)
 
 

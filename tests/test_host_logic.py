@@ -101,9 +101,13 @@ dist.destroy_process_group()
 def test_all_gather_world2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731")
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29731", str(script)], capture_output=True, text=True, env=env, timeout=300)
+                        "--master-port", port, str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = sorted(l for l in r.stdout.splitlines() if l.startswith("RANK"))
     assert len(lines) == 2 and lines[0].split(" ", 2)[2] == lines[1].split(" ", 2)[2]       # both ranks hold the same merged result

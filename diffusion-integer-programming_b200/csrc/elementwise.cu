@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <vector>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace dip {
@@ -255,6 +256,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(float4* __restrict__ dy, 
     }
 }
 
+__global__ void __launch_bounds__(256) split_bf16_kernel(uint2* __restrict__ hi, uint2* __restrict__ lo, const float4* __restrict__ x, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        float vs[4] = {v.x, v.y, v.z, v.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 hb = __float2bfloat16_rn(vs[e]);
+            __nv_bfloat16 lb = __float2bfloat16_rn(vs[e] - __bfloat162float(hb));
+            h[e] = __bfloat16_as_ushort(hb);
+            l[e] = __bfloat16_as_ushort(lb);
+        }
+        hi[i] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        lo[i] = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+    }
+}
+
 __global__ void __launch_bounds__(256) gather_pad_kernel(float4* __restrict__ out, const float* __restrict__ src,
                                                          const int64_t* __restrict__ idx, int n, int L) {
     int64_t total4 = (int64_t)L * (D / 4);
@@ -392,6 +410,15 @@ int dip_decoder_head_bwd(float* dy, const float* dz, int B, int T, int L, const 
     DIP_REQUIRE(dy && dz && w && B > 0 && L > 0 && T >= L, "dip_decoder_head_bwd: bad argument");
     DIP_PROF(DIP_PROF_HEAD, stream);
     head_bwd_kernel<<<ew_grid((int64_t)B * T * (D / 4)), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(dy), dz, B, T, L, w);
+    DIP_LAUNCHED();
+    return 0;
+}
+
+int dip_split_bf16(void* hi, void* lo, const float* x, int64_t n, dip_stream_t stream) {
+    DIP_REQUIRE(hi && lo && x && n > 0 && n % 4 == 0, "dip_split_bf16: bad argument");
+    DIP_PROF(DIP_PROF_OTHER, stream);
+    split_bf16_kernel<<<ew_grid(n / 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo),
+                                                                     reinterpret_cast<const float4*>(x), n / 4);
     DIP_LAUNCHED();
     return 0;
 }

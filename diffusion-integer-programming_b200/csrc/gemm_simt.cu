@@ -2,6 +2,7 @@
 // This is the exact-fp32 path of the Linear layers (model/modules.py:293-296, model/diffusion.py:160).
 // CTA tile 128x128x16, 256 threads, 8x8 outputs per thread held in registers; operand tiles are
 // transposed into shared memory so the inner product reads are conflict-free float4 broadcasts.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace dip {
@@ -109,6 +110,21 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmParams P) {
                 v[2] = apply_act(v[2], g.act, ax.z); v[3] = apply_act(v[3], g.act, ax.w);
             }
             *reinterpret_cast<float4*>(g.C + out_row * g.ldc + c) = make_float4(v[0], v[1], v[2], v[3]);
+            if (g.split_hi) {
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    h[e] = __float2bfloat16_rn(v[e]);
+                    l[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+                }
+                uint2 hv, lv;
+                hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+                hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+                lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+                lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_hi) + out_row * g.ldc + c) = hv;
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_lo) + out_row * g.ldc + c) = lv;
+            }
         }
     }
 }
@@ -147,6 +163,7 @@ int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream) {
     DIP_REQUIRE(g.lda % 4 == 0 && g.ldc % 4 == 0, "dip_gemm_nt: lda/ldc must be multiples of 4");
     DIP_REQUIRE(g.res.batch == nullptr || g.N == D, "dip_gemm_nt: residual needs N == 128");
     DIP_REQUIRE(g.act != DIP_ACT_MUL_QUICKGELU_GRAD || g.aux, "dip_gemm_nt: aux missing");
+    DIP_REQUIRE((g.split_hi == nullptr) == (g.split_lo == nullptr), "dip_gemm_nt: split_hi and split_lo go together");
     DIP_REQUIRE(g.rows_in == 0 || (g.rows_out >= g.rows_in + g.row_off), "dip_gemm_nt: bad row remap");
     GemmParams P;
     P.a = g;

@@ -36,6 +36,8 @@ class GemmArgs(C.Structure):
         ("row_bias_scale", vp),
         ("preact", vp),
         ("aux", vp),
+        ("split_hi", vp),
+        ("split_lo", vp),
     ]
 
 
@@ -81,6 +83,8 @@ PROTOTYPES = {
     "dip_layernorm_bwd": (i32, [vp, vp, Rows, vp, vp, vp, vp, i64, i32, vp]),
     "dip_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp]),
     "dip_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp, i32, i32, vp]),
+    "dip_split_bf16": (i32, [vp, vp, vp, i64, vp]),
+    "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dip_time_token": (i32, [vp, i32, i32, f32, vp, vp, vp]),
     "dip_decoder_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "dip_decoder_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp]),

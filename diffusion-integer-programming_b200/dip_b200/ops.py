@@ -100,6 +100,25 @@ def attn_bwd(qkv, o, d_o, lse, B, T, key_mask=None, mask_stride=None):
     return dqkv
 
 
+def split_bf16(x):
+    lib = _lib.load()
+    x = _f32(x)
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.dip_split_bf16(ptr(hi), ptr(lo), ptr(x), x.numel(), _stream()))
+    return hi, lo
+
+
+def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None):
+    """tcgen05 attention forward on the bf16 (hi, lo) planes of the packed (B*T, 384) qkv."""
+    lib = _lib.load()
+    o = torch.empty((B * T, D), dtype=torch.float32, device=qkv_hi.device)
+    lse = torch.empty(B * T, dtype=torch.float32, device=qkv_hi.device)
+    km, ms = _mask(key_mask, B, T, mask_stride)
+    check(lib.dip_attn_fwd_tc(ptr(o), ptr(lse), ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, _stream()))
+    return o, lse
+
+
 def _mask(key_mask, B, T, mask_stride):
     if key_mask is None:
         return None, 0

@@ -123,6 +123,10 @@ typedef struct {
     const float* row_bias_scale;
     float* preact;
     const float* aux;
+    /* optional bf16 (hi, lo) planes of the result, x = hi + lo to ~16 mantissa bits, same row/column
+     * indexing as C (row stride ldc elements): the operand format of the tensor-core kernels below */
+    void* split_hi;
+    void* split_lo;
 } dip_gemm_args;
 int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream);
 
@@ -149,6 +153,15 @@ int dip_attn_fwd(float* o, float* lse, const float* q, const float* k, const flo
 int dip_attn_bwd(float* dq, float* dk, float* dv, int ld_d, const float* q, const float* k, const float* v, int ld,
                  const float* o, const float* d_o, const float* lse, const uint8_t* key_mask, int64_t mask_stride,
                  float* delta_ws, int B, int T, dip_stream_t stream);
+
+/* ---- tensor-core (tcgen05 / TMEM / TMA) path, "bf16x2 split" numerics ------------------------- */
+/* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0). */
+int dip_split_bf16(void* hi, void* lo, const float* x, int64_t n, dip_stream_t stream);
+/* Same contract as dip_attn_fwd, operands given as the bf16 (hi, lo) planes of the packed (B*T, 384)
+ * in_proj output [q | k | v].  Every product is evaluated as hi.hi + hi.lo + lo.hi with fp32
+ * accumulation in tensor memory. */
+int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo, const uint8_t* key_mask,
+                    int64_t mask_stride, int B, int T, dip_stream_t stream);
 
 /* Row 0 of every sample of the denoiser's first hidden layer: QuickGELU(W1 . temb(t) + b1) with
  * temb the 256-wide sinusoidal embedding of model/diffusion.py:39-74.  out: (B, T, 128), row 0. */

@@ -119,6 +119,19 @@ def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None):
     return o, lse
 
 
+def attn_bwd_tc(qkv_hi, qkv_lo, o, d_o, lse, B, T, key_mask=None, mask_stride=None):
+    lib = _lib.load()
+    o, d_o = _f32(o), _f32(d_o)
+    do_hi, do_lo = split_bf16(d_o)
+    dqkv = torch.empty((B * T, 3 * D), dtype=torch.float32, device=o.device)
+    delta = torch.empty(B * T, dtype=torch.float32, device=o.device)
+    km, ms = _mask(key_mask, B, T, mask_stride)
+    dbase = dqkv.data_ptr()
+    check(lib.dip_attn_bwd_tc(dbase, dbase + 4 * D, dbase + 8 * D, 3 * D, ptr(qkv_hi), ptr(qkv_lo), ptr(do_hi), ptr(do_lo), ptr(o), ptr(d_o),
+                              ptr(lse), ptr(km), ms, ptr(delta), B, T, _stream()))
+    return dqkv
+
+
 def _mask(key_mask, B, T, mask_stride):
     if key_mask is None:
         return None, 0

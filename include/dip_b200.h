@@ -163,6 +163,12 @@ int dip_split_bf16(void* hi, void* lo, const float* x, int64_t n, dip_stream_t s
 int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo, const uint8_t* key_mask,
                     int64_t mask_stride, int B, int T, dip_stream_t stream);
 
+/* Same contract as dip_attn_bwd on split planes; do_hi/do_lo: planes of d_o (B*T,128).  Two tcgen05
+ * kernels (key-stationary dK/dV, query-stationary dQ); deterministic. */
+int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo,
+                    const void* do_hi, const void* do_lo, const float* o, const float* d_o, const float* lse,
+                    const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T, dip_stream_t stream);
+
 /* Row 0 of every sample of the denoiser's first hidden layer: QuickGELU(W1 . temb(t) + b1) with
  * temb the 256-wide sinusoidal embedding of model/diffusion.py:39-74.  out: (B, T, 128), row 0. */
 int dip_time_token(float* out, int B, int T, float t, const float* W1, const float* b1, dip_stream_t stream);

@@ -63,3 +63,43 @@ def test_attention_fwd_tc_full_size(cuda):
     o, lse = ops.attn_fwd_tc(hi, lo, B, T)
     o_ref, lse_ref = ops.attn_fwd(qkv, B, T)
     assert rel_l2(o, o_ref) < TC_TOL and rel_l2(lse, lse_ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,masked", [(1, 128, False), (2, 100, True), (1, 193, False), (2, 257, True), (1, 1000, True)])
+def test_attention_bwd_tc(cuda, B, T, masked):
+    from dip_b200 import ops
+    qkv = rnd((B * T, 3 * D), T + 1, 1.5)
+    mask = None
+    if masked:
+        mask = torch.zeros((B, T), dtype=torch.bool)
+        for b in range(B):
+            mask[b, T - 5 - 3 * b:] = True
+            mask[b, 7 + b] = True
+    ref_in = qkv.double().requires_grad_(True)
+    ref = _attn_ref(ref_in, B, T, mask)
+    d_o = rnd((B * T, D), 99)
+    ref.backward(d_o.double())
+    km = None if mask is None else mask.to(cuda)
+    hi, lo = ops.split_bf16(qkv.to(cuda))
+    o, lse = ops.attn_fwd_tc(hi, lo, B, T, km)
+    dqkv = ops.attn_bwd_tc(hi, lo, o, d_o.to(cuda), lse, B, T, km)
+    dq, dk, dv = dqkv.split(D, dim=-1)
+    rq, rk, rv = ref_in.grad.split(D, dim=-1)
+    assert rel_l2(dv, rv) < TC_TOL, ("dv", rel_l2(dv, rv))
+    assert rel_l2(dk, rk) < TC_TOL, ("dk", rel_l2(dk, rk))
+    assert rel_l2(dq, rq) < TC_TOL, ("dq", rel_l2(dq, rq))
+    assert torch.equal(dqkv, ops.attn_bwd_tc(hi, lo, o, d_o.to(cuda), lse, B, T, km))
+
+
+def test_attention_bwd_tc_full_size(cuda):
+    from dip_b200 import ops
+    B, T = 2, 4000
+    qkv = rnd((B * T, 3 * D), 5, 1.0).to(cuda)
+    d_o = rnd((B * T, D), 6).to(cuda)
+    hi, lo = ops.split_bf16(qkv)
+    o, lse = ops.attn_fwd_tc(hi, lo, B, T)
+    dqkv = ops.attn_bwd_tc(hi, lo, o, d_o, lse, B, T)
+    o_ref, lse_ref = ops.attn_fwd(qkv, B, T)
+    ref = ops.attn_bwd(qkv, o_ref, d_o, lse_ref, B, T)
+    for name, a, r in zip("qkv", dqkv.split(D, dim=-1), ref.split(D, dim=-1)):
+        assert rel_l2(a, r) < TC_TOL, (name, rel_l2(a, r))

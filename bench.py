@@ -317,13 +317,13 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "wave": B, "ddim_steps": S, "instance_per_rank": True,
                        "l2": "working set per wave (%.1f GB) exceeds the 126 MB L2; no flush needed" % (eng.workspace(B)[1] / 1e9),
-                       "precision_mode": "fp32 SIMT (exact); tensor-core path not enabled in this build"},
+                       "precision_mode": "attention on tcgen05 tensor cores, bf16x2-split operands (3 MMA passes, fp32 accumulate); linears fp32 SIMT"},
             "feasible_per_s": float(cnt[0]) / (ms / 1e3), "feasible_ratio": float(cnt[0]) / total_samples,
             "tflops_effective": (den + dec_f + dec_b) * S * total_samples / (ms / 1e3) / 1e12,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * L * D * 4,
                     "d2h_bytes_per_step": B * inst.n + B * 4 + B * 16, "feasible_ratio": float(cnt[1]) / total_samples},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "attn_bwd_dkdv_kernel (decoder attention backward, dK/dV/dP)", "bound": "tensor", "achieved": achieved,
+            "roofline": {"kernel": "attn_bwd_tc_kernel<key-stationary> (decoder attention backward: dP, dV, dK; tcgen05)", "bound": "tensor", "achieved": achieved,
                          "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
                          "peak_source": pk["src"] + ", sustained bf16", "launch_ms": avg_ms,
                          "share_of_step": dk["ms"] / total_prof_ms if total_prof_ms > 0 else None},

@@ -53,6 +53,7 @@ struct dip_engine {
     float* mproj = nullptr;
     uint8_t *mask_den = nullptr, *mask_dec = nullptr;
     int inst_cap_L = 0;
+    int mode = DIP_PRECISION_TC_SPLIT;
 };
 
 namespace dip {
@@ -100,11 +101,13 @@ struct Carver {
 
 struct LayerSave {
     float *mean1, *rstd1, *qkv, *ao, *lse, *xmid, *mean2, *rstd2, *u, *xout;
+    void *qkv_hi, *qkv_lo;   // bf16 planes of qkv (tensor-core mode)
 };
 
 struct Workspace {
     // denoiser
     float *hd, *tmp, *tmp2, *qkv1, *ao1;
+    void *qkv1_hi, *qkv1_lo, *do_hi, *do_lo;
     // decoder
     LayerSave ls[MAX_LAYERS];
     float *h, *h2;
@@ -123,6 +126,8 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
     w.tmp2 = c.take<float>(R1 * D);
     w.qkv1 = c.take<float>(R1 * 3 * D);
     w.ao1 = c.take<float>(R1 * D);
+    w.qkv1_hi = c.take<uint16_t>(R1 * 3 * D);
+    w.qkv1_lo = c.take<uint16_t>(R1 * 3 * D);
     for (int l = 0; l < e->n_dec; ++l) {
         LayerSave& s = w.ls[l];
         s.mean1 = c.take<float>(R2); s.rstd1 = c.take<float>(R2);
@@ -133,6 +138,8 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
         s.mean2 = c.take<float>(R2); s.rstd2 = c.take<float>(R2);
         s.u = c.take<float>(R2 * D);
         s.xout = c.take<float>(R2 * D);
+        s.qkv_hi = c.take<uint16_t>(R2 * 3 * D);
+        s.qkv_lo = c.take<uint16_t>(R2 * 3 * D);
     }
     w.h = c.take<float>(R2 * D);
     w.h2 = c.take<float>(R2 * D);
@@ -144,6 +151,8 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
     w.dao = c.take<float>(R2 * D);
     w.dqkv = c.take<float>(R2 * 3 * D);
     w.delta = c.take<float>(R2);
+    w.do_hi = c.take<uint16_t>(R2 * D);
+    w.do_lo = c.take<uint16_t>(R2 * D);
     w.p_full = c.take<float>((size_t)B * L);
     w.dz = c.take<float>((size_t)B * L);
     w.viol = c.take<float>(B);
@@ -169,14 +178,17 @@ static dip_rows plain_rows(const float* p, int T) {
 
 // One ResidualAttentionBlock forward (model/modules.py:293-296).  xin -> xmid -> xout; h, h2 are
 // transients.  Statistics / lse / u are saved when non-null.
-static int block_fwd(const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, float* qkv, float* ao, float* lse,
-                     float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask, int B, int T, dip_stream_t st) {
+static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, float* qkv, void* qkv_hi,
+                     void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
+                     int B, int T, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     DIP_REQUIRE(R < (1ll << 31), "wave too large: B*T = %lld rows", (long long)R);
     DIP_TRY(dip_layernorm_fwd(h, mean1, rstd1, xin, w.ln1_w, w.ln1_b, R, st));
     dip_gemm_args g = gemm(h, D, w.in_w, w.in_b, qkv, 3 * D, R, 3 * D, D, DIP_ACT_NONE);
+    if (mode == DIP_PRECISION_TC_SPLIT) { g.split_hi = qkv_hi; g.split_lo = qkv_lo; }
     DIP_TRY(dip_gemm_nt(&g, st));
-    DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
+    if (mode == DIP_PRECISION_TC_SPLIT) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, st));
+    else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
     g = gemm(ao, D, w.out_w, w.out_b, xmid, D, R, D, D, DIP_ACT_NONE);
     g.res = xin;
     DIP_TRY(dip_gemm_nt(&g, st));
@@ -191,8 +203,9 @@ static int block_fwd(const BlockW& w, dip_rows xin, float* xmid, float* xout, fl
 }
 
 // Input-gradient backward of one block.  dxout -> dxin (rows with t >= t_min only).
-static int block_bwd(const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int B, int T, float* dt1,
-                     float* dt2, float* dxm, float* dao, float* dqkv, float* delta, float* dxin, int t_min, dip_stream_t st) {
+static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int B, int T, float* dt1,
+                     float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, float* dxin, int t_min,
+                     dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     // dU = (dxout . W_proj) * gelu'(u)
     dip_gemm_args g = gemm(dxout, D, w.proj_wT, nullptr, dt1, D, R, D, D, DIP_ACT_MUL_QUICKGELU_GRAD);
@@ -205,8 +218,12 @@ static int block_bwd(const BlockW& w, const float* dxout, dip_rows xin, const La
     DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, 0, st));
     // dAO = dxmid . W_out
     g = gemm(dxm, D, w.out_wT, nullptr, dao, D, R, D, D, DIP_ACT_NONE);
+    if (mode == DIP_PRECISION_TC_SPLIT) { g.split_hi = do_hi; g.split_lo = do_lo; }
     DIP_TRY(dip_gemm_nt(&g, st));
-    DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
+    if (mode == DIP_PRECISION_TC_SPLIT)
+        DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
+    else
+        DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
     // dH1 = dQKV . W_in
     g = gemm(dqkv, 3 * D, w.in_wT, nullptr, dt1, D, R, D, 3 * D, DIP_ACT_NONE);
     DIP_TRY(dip_gemm_nt(&g, st));
@@ -247,8 +264,8 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     g = gemm(w.tmp, D, e->w2, e->b2, w.hd, D, R1, D, D, DIP_ACT_NONE);
     DIP_TRY(dip_gemm_nt(&g, st));
     for (int l = 0; l < e->n_den; ++l)
-        DIP_TRY(block_fwd(e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.ao1, nullptr, nullptr, nullptr, nullptr,
-                          nullptr, nullptr, e->mask_den, B, T1, st));
+        DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, e->mask_den, B, T1, st));
     return 0;
 }
 
@@ -260,8 +277,8 @@ static int decode(dip_engine* e, const Workspace& w, const float* x, int B, dip_
         if (l == 0) { xin.shared = e->inst.mip; xin.batch = x; xin.T = T2; xin.split = L; }
         else xin = plain_rows(w.ls[l - 1].xout, T2);
         const LayerSave& s = w.ls[l];
-        DIP_TRY(block_fwd(e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, s.qkv, s.ao, s.lse, s.mean1, s.rstd1, s.mean2, s.rstd2, s.u,
-                          e->mask_dec, B, T2, st));
+        DIP_TRY(block_fwd(e->mode, e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, s.qkv, s.qkv_hi, s.qkv_lo, s.ao, s.lse, s.mean1, s.rstd1, s.mean2,
+                          s.rstd2, s.u, e->mask_dec, B, T2, st));
     }
     DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, e->inst.kpm, st));
     return 0;
@@ -283,8 +300,8 @@ static int guidance_grad(dip_engine* e, const Workspace& w, const float* x, int 
         if (l == 0) { xin.shared = in.mip; xin.batch = x; xin.T = T2; xin.split = L; }
         else xin = plain_rows(w.ls[l - 1].xout, T2);
         // the gradient w.r.t. the (constant) mip tokens of layer 0 is never used: skip those rows
-        DIP_TRY(block_bwd(e->dec[l], dcur, xin, w.ls[l], e->mask_dec, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.dqkv, w.delta, dnext,
-                          l == 0 ? L : 0, st));
+        DIP_TRY(block_bwd(e->mode, e->dec[l], dcur, xin, w.ls[l], e->mask_dec, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.do_hi, w.do_lo, w.dqkv, w.delta,
+                          dnext, l == 0 ? L : 0, st));
         float* t = dcur; dcur = dnext; dnext = t;
     }
     *grad = dcur + (int64_t)L * D;
@@ -398,6 +415,13 @@ int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_
     DIP_CUDA(cudaMemcpyAsync(e->mask_dec + inst->L, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
     e->has_inst = true;
     e->mproj_valid = false;
+    return 0;
+}
+
+int dip_engine_set_precision(dip_engine* e, int mode) {
+    DIP_REQUIRE(e, "null engine");
+    DIP_REQUIRE(mode == DIP_PRECISION_FP32_SIMT || mode == DIP_PRECISION_TC_SPLIT, "unknown precision mode %d", mode);
+    e->mode = mode;
     return 0;
 }
 

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "dip_engine_set_denoiser": (i32, [vp, vp, vp, vp, vp, C.POINTER(BlockWeights), i32, vp]),
     "dip_engine_set_decoder": (i32, [vp, C.POINTER(BlockWeights), i32, vp, vp, vp]),
     "dip_engine_set_instance": (i32, [vp, C.POINTER(Instance), vp]),
+    "dip_engine_set_precision": (i32, [vp, i32]),
     "dip_engine_workspace_bytes": (sz, [vp, i32]),
     "dip_engine_denoise": (i32, [vp, vp, vp, i32, f32, vp, sz, vp]),
     "dip_engine_decode": (i32, [vp, vp, vp, vp, i32, vp, sz, vp]),

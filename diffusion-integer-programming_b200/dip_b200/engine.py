@@ -77,6 +77,7 @@ class Engine:
         self._ws = None
         self.inst = None
         self.n_den = self.n_dec = 0
+        self.precision = "tc"
 
     def __del__(self):
         try:
@@ -85,6 +86,12 @@ class Engine:
                 self.h = None
         except Exception:
             pass
+
+    def set_precision(self, mode):
+        """'tc' (default: tcgen05 tensor cores, bf16x2-split operands) or 'fp32' (exact SIMT kernels)."""
+        code = {"tc": 1, "fp32": 0, 1: 1, 0: 0}[mode]
+        check(self.lib.dip_engine_set_precision(self.h, code))
+        self.precision = "tc" if code == 1 else "fp32"
 
     # ---- weights -------------------------------------------------------------------------------
     def _blocks(self, sd, prefix, n_layers, keep):

@@ -265,6 +265,14 @@ typedef struct {
 } dip_instance;
 int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_t stream);
 
+/* Arithmetic of the attention kernels (the >95 % of the FLOPs):
+ *   DIP_PRECISION_TC_SPLIT  (default) tcgen05 tensor cores, every fp32 operand carried as bf16 hi + lo planes,
+ *                           products hi.hi + hi.lo + lo.hi accumulated in fp32 (one-step error ~1e-5, bar 1e-3);
+ *   DIP_PRECISION_FP32_SIMT exact fp32 FFMA kernels (one-step error ~1e-7) -- the on-GPU checker of the former. */
+#define DIP_PRECISION_FP32_SIMT 0
+#define DIP_PRECISION_TC_SPLIT 1
+int dip_engine_set_precision(dip_engine* e, int mode);
+
 /* Scratch the caller provides (torch-allocated) for a wave of B samples. */
 size_t dip_engine_workspace_bytes(const dip_engine* e, int B);
 

@@ -15,12 +15,16 @@ from dip_b200 import synth
 from helpers import golden, tw, rel_l2, case_tensors, coalesced, small_case, small_graph, sc_case
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4
+# one-step relative-L2 tolerance per precision mode: exact fp32 SIMT kernels, and the tcgen05 "bf16x2 split"
+# mode whose bar is north_star's 1e-3 (observed ~1e-5)
+TOLS = {"fp32": 1e-4, "tc": 1e-3}
+MODES = ["fp32", "tc"]
 
 
-def make_engine(cuda, cs, n_den=1, n_dec=2, wseed=1, ints=False):
+def make_engine(cuda, cs, n_den=1, n_dec=2, wseed=1, ints=False, precision="fp32"):
     from dip_b200.engine import Engine
     eng = Engine()
+    eng.set_precision(precision)
     eng.set_denoiser(tw(synth.denoiser_weights(n_den, seed=wseed), cuda))
     eng.set_decoder(tw(synth.decoder_weights(n_dec, seed=wseed + 1), cuda))
     eng.set_instance(torch.from_numpy(cs.mip).to(cuda), torch.from_numpy(cs.kpm).to(cuda), cs.rows, cs.cols, cs.vals, cs.M, cs.b, cs.c)
@@ -35,10 +39,12 @@ def coeffs(S, index):
     return Engine.ddim_coeffs(S - 1 - index, c["sqrt_at"], c["s1m"], c["c_dir"], c["sqrt_aprev"], c["sigma"])
 
 
-def test_p1_teacher_forced_ddim_x0(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_p1_teacher_forced_ddim_x0(cuda, mode):
+    TOL = TOLS[mode]
     g = golden("ddim_guided_x0")
     cs = small_case()
-    eng = make_engine(cuda, cs)
+    eng = make_engine(cuda, cs, precision=mode)
     S, gs, lam = int(g["S"]), float(g["gs"]), float(g["lam"])
     x_in = torch.from_numpy(cs.x).to(cuda)
     for index in g["indices"]:
@@ -56,15 +62,17 @@ def test_p1_teacher_forced_ddim_x0(cuda):
         assert torch.equal(x0_out, x0)
 
 
-def test_p2_free_running_and_p3_final_decode(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_p2_free_running_and_p3_final_decode(cuda, mode):
+    TOL = TOLS[mode]
     g = golden("ddim_guided_x0")
     cs = small_case()
-    eng = make_engine(cuda, cs)
+    eng = make_engine(cuda, cs, precision=mode)
     S, gs, lam = int(g["S"]), float(g["gs"]), float(g["lam"])
     x = torch.from_numpy(cs.x).to(cuda).clone()
     for k in range(3):
         eng.guided_ddim_step(x, coeffs(S, k), gs, lam)
-        assert rel_l2(x, g["free%d_x" % k]) < 1e-3 * (k + 1)
+        assert rel_l2(x, g["free%d_x" % k]) < 10 * TOL * (k + 1)
     # P3: identical latents in -> bit-identical assignment / feasibility out
     fd = eng.final_decode(torch.from_numpy(g["free2_x"]).to(cuda))
     assert rel_l2(fd["p_full"][:, :cs.n], g["final_p"]) < TOL
@@ -79,10 +87,12 @@ def test_p2_free_running_and_p3_final_decode(cuda):
     assert rel_l2(xu, g["unguided_xprev"]) < TOL
 
 
-def test_eps_parameterisation(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_eps_parameterisation(cuda, mode):
+    TOL = TOLS[mode]
     g = golden("ddim_guided_eps")
     cs = small_case()
-    eng = make_engine(cuda, cs)
+    eng = make_engine(cuda, cs, precision=mode)
     S, gs, lam = int(g["S"]), float(g["gs"]), float(g["lam"])
     for index in g["indices"]:
         index = int(index)
@@ -93,12 +103,14 @@ def test_eps_parameterisation(cuda):
         assert rel_l2(x, g["tf%d_xprev" % index]) < TOL
 
 
-def test_ddpm_steps(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_ddpm_steps(cuda, mode):
+    TOL = TOLS[mode]
     from dip_b200 import _lib
     from oracle import restate
     g = golden("ddpm_guided_x0")
     cs = small_case(seed=1)
-    eng = make_engine(cuda, cs)
+    eng = make_engine(cuda, cs, precision=mode)
     buf = restate.trainer_buffers()
     tabs = restate.ddpm_tables(buf)
     for ti in g["ts"]:
@@ -115,6 +127,7 @@ def test_ddpm_steps(cuda):
 
 
 def test_encoder_vs_golden(cuda):
+    TOL = 1e-4
     from dip_b200 import encoder, ops
     g = golden("encoder_small")
     gr = small_graph()
@@ -128,9 +141,11 @@ def test_encoder_vs_golden(cuda):
     assert float(mip[len(gr.int_indices):].abs().max()) == 0.0
 
 
-def test_one_call_sampler_equals_stepwise_and_is_deterministic(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_one_call_sampler_equals_stepwise_and_is_deterministic(cuda, mode):
+    TOL = TOLS[mode]
     cs = small_case()
-    eng = make_engine(cuda, cs)
+    eng = make_engine(cuda, cs, precision=mode)
     S = 5
     steps = [coeffs(S, k) for k in range(S)]
     x1 = torch.from_numpy(cs.x).to(cuda).clone()
@@ -145,10 +160,12 @@ def test_one_call_sampler_equals_stepwise_and_is_deterministic(cuda):
     assert torch.equal(x1, x3) and torch.equal(out["xbits"], out3["xbits"])        # run-to-run bitwise
 
 
-def test_batch_invariance(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_batch_invariance(cuda, mode):
+    TOL = TOLS[mode]
     """A sample's trajectory must not depend on which wave it is in (sharding invariance)."""
     cs = small_case(B=4)
-    eng = make_engine(cuda, cs)
+    eng = make_engine(cuda, cs, precision=mode)
     S = 4            # S = 3 would index alpha-bar[1000] (SURVEY section 7 quirk 10)
     steps = [coeffs(S, k) for k in range(S)]
     xa = torch.from_numpy(cs.x).to(cuda).clone()
@@ -176,7 +193,9 @@ def test_engine_errors(cuda):
                          np.zeros(cs.n + 1, np.float32))
 
 
-def test_full_size_set_cover_step_vs_oracle(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_full_size_set_cover_step_vs_oracle(cuda, mode):
+    TOL = TOLS[mode]
     """BASELINE config shapes (L = n = 2000, M = 1000, nnz = 1e5, D = 128, n_d = 1, n_e = 2): one guided
     step of 2 samples against the CPU oracle (a few seconds on the host)."""
     from dip_b200.engine import Engine
@@ -184,6 +203,7 @@ def test_full_size_set_cover_step_vs_oracle(cuda):
     inst, mip, kpm, x = sc_case(B=2)
     Wd, Wdec = synth.denoiser_weights(1, seed=1), synth.decoder_weights(2, seed=2)
     eng = Engine()
+    eng.set_precision(mode)
     eng.set_denoiser(tw(Wd, cuda)); eng.set_decoder(tw(Wdec, cuda))
     eng.set_instance(torch.from_numpy(mip).to(cuda), torch.from_numpy(kpm).to(cuda), inst.rows, inst.cols, inst.a_val, inst.M, inst.b, inst.c,
                      a_int=inst.a_int, b_int=inst.b_int, c_int=inst.c_int)

@@ -43,6 +43,40 @@ def gemm_nt(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=
     return out
 
 
+def gemm_tc(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=0, addmat=None, res=None, res_shared=None, res_T=0,
+            res_split=0, row_bias_scale=None, preact=None, aux=None, out_rows=None, a_shared=None, a_T=0, a_split=0, ln=None,
+            want_stats=False, want_split=False, want_c=True, M=None):
+    """tcgen05 version of gemm_nt.  ln = (gamma, beta) fuses LayerNorm into the A load; a_shared/a_T/a_split
+    give a two-source A (then A is the per-sample part and M the total row count)."""
+    lib = _lib.load()
+    A, W = _f32(A, "A"), _f32(W, "W")
+    N, K = W.shape
+    if M is None:
+        M = A.numel() // K
+    w_hi, w_lo = split_bf16(W)
+    n_out = out_rows if out_rows is not None else M
+    dev = A.device
+    if out is None and want_c:
+        out = torch.empty((n_out, N), dtype=torch.float32, device=dev)
+    hi = torch.empty((n_out, N), dtype=torch.bfloat16, device=dev) if want_split else None
+    lo = torch.empty((n_out, N), dtype=torch.bfloat16, device=dev) if want_split else None
+    mean = torch.empty(M, dtype=torch.float32, device=dev) if want_stats else None
+    rstd = torch.empty(M, dtype=torch.float32, device=dev) if want_stats else None
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.bias, g.C, g.ldc = ptr(A), K, None, ptr(bias), ptr(out), N
+    g.M, g.N, g.K, g.act = M, N, K, ACT[act]
+    g.rows_in, g.rows_out, g.row_off = rows_in, rows_out, row_off
+    g.addmat = ptr(addmat)
+    g.res = Rows(ptr(res_shared), ptr(res), int(res_T), int(res_split))
+    g.row_bias_scale, g.preact, g.aux = ptr(row_bias_scale), ptr(preact), ptr(aux)
+    g.split_hi, g.split_lo = ptr(hi), ptr(lo)
+    ar = Rows(ptr(a_shared), ptr(A), int(a_T), int(a_split)) if a_shared is not None else None
+    check(lib.dip_gemm_tc(C.byref(g), ptr(w_hi), ptr(w_lo), C.byref(ar) if ar is not None else None, ptr(ln[0]) if ln else None,
+                          ptr(ln[1]) if ln else None, ptr(mean), ptr(rstd), _stream()))
+    res_ = {"C": out, "hi": hi, "lo": lo, "mean": mean, "rstd": rstd}
+    return res_
+
+
 def linear_smallk(x, W, bias=None, shift=None, scale=None, act=None):
     lib = _lib.load()
     x, W = _f32(x), _f32(W)

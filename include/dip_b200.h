@@ -169,6 +169,15 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
                     const void* do_hi, const void* do_lo, const float* o, const float* d_o, const float* lse,
                     const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T, dip_stream_t stream);
 
+/* dip_gemm_nt on tcgen05 (bf16x2-split operands): w_hi / w_lo are the bf16 planes of the (N,K) weight
+ * (dip_split_bf16 of the nn.Linear weight).  K must be 128 or 384.  Extras over dip_gemm_nt:
+ *   a_rows   (nullable) two-source A rows (K == 128), replaces args->A;
+ *   ln_gamma/ln_beta (nullable) LayerNorm(128, eps 1e-5) applied to every A row on load (model/modules.py:280,288
+ *            fused into the following Linear); ln_mean/ln_rstd (nullable) receive the row statistics;
+ *   args->C may be NULL when only the split planes / preact are wanted. */
+int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, const dip_rows* a_rows,
+                const float* ln_gamma, const float* ln_beta, float* ln_mean, float* ln_rstd, dip_stream_t stream);
+
 /* Row 0 of every sample of the denoiser's first hidden layer: QuickGELU(W1 . temb(t) + b1) with
  * temb the 256-wide sinusoidal embedding of model/diffusion.py:39-74.  out: (B, T, 128), row 0. */
 int dip_time_token(float* out, int B, int T, float t, const float* W1, const float* b1, dip_stream_t stream);

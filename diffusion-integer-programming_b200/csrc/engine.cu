@@ -10,9 +10,17 @@ namespace dip {
 
 constexpr int MAX_LAYERS = 8;
 
+// a weight in the three forms the kernels consume: fp32 (SIMT GEMM) and bf16 hi / lo planes (tcgen05 GEMM)
+struct WRef {
+    float* w = nullptr;
+    void* hi = nullptr;
+    void* lo = nullptr;
+};
+
 struct BlockW {
-    float *ln1_w, *ln1_b, *in_w, *in_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
-    float *in_wT, *out_wT, *fc_wT, *proj_wT;   // transposed copies for the input-gradient GEMMs
+    float *ln1_w, *ln1_b, *in_b, *out_b, *ln2_w, *ln2_b, *fc_b, *proj_b;
+    WRef in_w, out_w, fc_w, proj_w;
+    WRef in_wT, out_wT, fc_wT, proj_wT;   // transposed copies for the input-gradient GEMMs
 };
 
 __global__ void transpose_kernel(float* __restrict__ out, const float* __restrict__ in, int rows, int cols) {
@@ -45,7 +53,8 @@ using namespace dip;
 struct dip_engine {
     int n_den = 0, n_dec = 0;
     BlockW den[MAX_LAYERS], dec[MAX_LAYERS];
-    float *w1 = nullptr, *w1m = nullptr, *w1x = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    float *w1 = nullptr, *w1m = nullptr, *b1 = nullptr, *b2 = nullptr;
+    WRef w1x, w2;
     float *proj_w = nullptr, *proj_b = nullptr;
     Pool den_pool, dec_pool, inst_pool;
     bool has_den = false, has_dec = false, has_inst = false, mproj_valid = false;
@@ -58,30 +67,48 @@ struct dip_engine {
 
 namespace dip {
 
+// allocate the bf16 planes of an (n-element) fp32 weight already on the device
+static int make_planes(Pool& pool, WRef& w, size_t n, cudaStream_t st) {
+    float *h = nullptr, *l = nullptr;
+    DIP_TRY(pool.alloc(&h, (n + 1) / 2));
+    DIP_TRY(pool.alloc(&l, (n + 1) / 2));
+    w.hi = h; w.lo = l;
+    return dip_split_bf16(w.hi, w.lo, w.w, (int64_t)n, st);
+}
+
+static int copy_weight(Pool& pool, WRef& w, const float* src, size_t n, cudaStream_t st) {
+    DIP_REQUIRE(src, "weights: null pointer");
+    DIP_TRY(pool.alloc(&w.w, n));
+    DIP_CUDA(cudaMemcpyAsync(w.w, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return make_planes(pool, w, n, st);
+}
+
+static int transposed_weight(Pool& pool, WRef& wT, const WRef& w, int rows, int cols, cudaStream_t st) {
+    DIP_TRY(pool.alloc(&wT.w, (size_t)rows * cols));
+    transpose_kernel<<<64, 256, 0, st>>>(wT.w, w.w, rows, cols);
+    DIP_LAUNCHED();
+    return make_planes(pool, wT, (size_t)rows * cols, st);
+}
+
 static int copy_block(Pool& pool, BlockW& w, const dip_block_weights& s, cudaStream_t st) {
     struct Item { float** dst; const float* src; size_t n; };
     Item items[] = {
-        {&w.ln1_w, s.ln1_w, D}, {&w.ln1_b, s.ln1_b, D}, {&w.in_w, s.in_proj_w, 3 * D * D}, {&w.in_b, s.in_proj_b, 3 * D},
-        {&w.out_w, s.out_proj_w, D * D}, {&w.out_b, s.out_proj_b, D}, {&w.ln2_w, s.ln2_w, D}, {&w.ln2_b, s.ln2_b, D},
-        {&w.fc_w, s.fc_w, D * D}, {&w.fc_b, s.fc_b, D}, {&w.proj_w, s.proj_w, D * D}, {&w.proj_b, s.proj_b, D},
+        {&w.ln1_w, s.ln1_w, D}, {&w.ln1_b, s.ln1_b, D}, {&w.in_b, s.in_proj_b, 3 * D}, {&w.out_b, s.out_proj_b, D},
+        {&w.ln2_w, s.ln2_w, D}, {&w.ln2_b, s.ln2_b, D}, {&w.fc_b, s.fc_b, D}, {&w.proj_b, s.proj_b, D},
     };
     for (auto& it : items) {
         DIP_REQUIRE(it.src, "block weights: null pointer");
         DIP_TRY(pool.alloc(it.dst, it.n));
         DIP_CUDA(cudaMemcpyAsync(*it.dst, it.src, it.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    DIP_TRY(pool.alloc(&w.in_wT, 3 * D * D));
-    DIP_TRY(pool.alloc(&w.out_wT, D * D));
-    DIP_TRY(pool.alloc(&w.fc_wT, D * D));
-    DIP_TRY(pool.alloc(&w.proj_wT, D * D));
-    transpose_kernel<<<64, 256, 0, st>>>(w.in_wT, w.in_w, 3 * D, D);
-    DIP_LAUNCHED();
-    transpose_kernel<<<32, 256, 0, st>>>(w.out_wT, w.out_w, D, D);
-    DIP_LAUNCHED();
-    transpose_kernel<<<32, 256, 0, st>>>(w.fc_wT, w.fc_w, D, D);
-    DIP_LAUNCHED();
-    transpose_kernel<<<32, 256, 0, st>>>(w.proj_wT, w.proj_w, D, D);
-    DIP_LAUNCHED();
+    DIP_TRY(copy_weight(pool, w.in_w, s.in_proj_w, 3 * D * D, st));
+    DIP_TRY(copy_weight(pool, w.out_w, s.out_proj_w, D * D, st));
+    DIP_TRY(copy_weight(pool, w.fc_w, s.fc_w, D * D, st));
+    DIP_TRY(copy_weight(pool, w.proj_w, s.proj_w, D * D, st));
+    DIP_TRY(transposed_weight(pool, w.in_wT, w.in_w, 3 * D, D, st));
+    DIP_TRY(transposed_weight(pool, w.out_wT, w.out_w, D, D, st));
+    DIP_TRY(transposed_weight(pool, w.fc_wT, w.fc_w, D, D, st));
+    DIP_TRY(transposed_weight(pool, w.proj_wT, w.proj_w, D, D, st));
     return 0;
 }
 
@@ -162,10 +189,10 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
     return w;
 }
 
-static dip_gemm_args gemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int64_t M, int N, int K, int act) {
+static dip_gemm_args gemm(const float* A, int lda, float* C, int ldc, int64_t M, int N, int K, const float* bias, int act) {
     dip_gemm_args g;
     memset(&g, 0, sizeof(g));
-    g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
+    g.A = A; g.lda = lda; g.bias = bias; g.C = C; g.ldc = ldc;
     g.M = (int)M; g.N = N; g.K = K; g.act = act;
     return g;
 }
@@ -176,29 +203,52 @@ static dip_rows plain_rows(const float* p, int T) {
     return r;
 }
 
+// One Linear, optionally preceded by LayerNorm of its input rows `a_rows` (then g.A is ignored):
+//   tensor-core mode: one tcgen05 GEMM launch, LayerNorm fused into the operand load;
+//   fp32 mode       : LayerNorm kernel into `ln_tmp`, then the SIMT GEMM.
+static int linear(int mode, dip_gemm_args g, const WRef& w, const dip_rows* a_rows, const float* ln_g, const float* ln_b, float* mean, float* rstd,
+                  float* ln_tmp, dip_stream_t st) {
+    if (mode == DIP_PRECISION_TC_SPLIT) return dip_gemm_tc(&g, w.hi, w.lo, a_rows, ln_g, ln_b, mean, rstd, st);
+    if (a_rows) {
+        DIP_REQUIRE(ln_g && ln_tmp, "linear: row-source inputs go through LayerNorm");
+        DIP_TRY(dip_layernorm_fwd(ln_tmp, mean, rstd, *a_rows, ln_g, ln_b, g.M, st));
+        g.A = ln_tmp; g.lda = D;
+    }
+    g.W = w.w;
+    if (g.C == nullptr) {
+        // the SIMT GEMM always writes fp32 C; callers in fp32 mode pass one
+        DIP_FAIL("linear: fp32 mode needs an fp32 output");
+    }
+    return dip_gemm_nt(&g, st);
+}
+
 // One ResidualAttentionBlock forward (model/modules.py:293-296).  xin -> xmid -> xout; h, h2 are
 // transients.  Statistics / lse / u are saved when non-null.
 static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, float* qkv, void* qkv_hi,
                      void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
                      int B, int T, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
+    const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     DIP_REQUIRE(R < (1ll << 31), "wave too large: B*T = %lld rows", (long long)R);
-    DIP_TRY(dip_layernorm_fwd(h, mean1, rstd1, xin, w.ln1_w, w.ln1_b, R, st));
-    dip_gemm_args g = gemm(h, D, w.in_w, w.in_b, qkv, 3 * D, R, 3 * D, D, DIP_ACT_NONE);
-    if (mode == DIP_PRECISION_TC_SPLIT) { g.split_hi = qkv_hi; g.split_lo = qkv_lo; }
-    DIP_TRY(dip_gemm_nt(&g, st));
-    if (mode == DIP_PRECISION_TC_SPLIT) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, st));
+    // q|k|v = LN1(x) . W_in^T + b_in   (tensor-core mode: only the bf16 planes are written)
+    dip_gemm_args g = gemm(nullptr, D, tc ? nullptr : qkv, 3 * D, R, 3 * D, D, w.in_b, DIP_ACT_NONE);
+    if (tc) { g.split_hi = qkv_hi; g.split_lo = qkv_lo; }
+    DIP_TRY(linear(mode, g, w.in_w, &xin, w.ln1_w, w.ln1_b, mean1, rstd1, h, st));
+    if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, st));
     else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
-    g = gemm(ao, D, w.out_w, w.out_b, xmid, D, R, D, D, DIP_ACT_NONE);
+    // x_mid = x + attn . W_out^T + b_out
+    g = gemm(ao, D, xmid, D, R, D, D, w.out_b, DIP_ACT_NONE);
     g.res = xin;
-    DIP_TRY(dip_gemm_nt(&g, st));
-    DIP_TRY(dip_layernorm_fwd(h, mean2, rstd2, plain_rows(xmid, T), w.ln2_w, w.ln2_b, R, st));
-    g = gemm(h, D, w.fc_w, w.fc_b, h2, D, R, D, D, DIP_ACT_QUICKGELU);
+    DIP_TRY(linear(mode, g, w.out_w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    // g = QuickGELU(LN2(x_mid) . W_fc^T + b_fc)   (pre-activation saved for the backward pass)
+    dip_rows xm = plain_rows(xmid, T);
+    g = gemm(nullptr, D, h2, D, R, D, D, w.fc_b, DIP_ACT_QUICKGELU);
     g.preact = u;
-    DIP_TRY(dip_gemm_nt(&g, st));
-    g = gemm(h2, D, w.proj_w, w.proj_b, xout, D, R, D, D, DIP_ACT_NONE);
-    g.res = plain_rows(xmid, T);
-    DIP_TRY(dip_gemm_nt(&g, st));
+    DIP_TRY(linear(mode, g, w.fc_w, &xm, w.ln2_w, w.ln2_b, mean2, rstd2, h, st));
+    // x_out = x_mid + g . W_proj^T + b_proj
+    g = gemm(h2, D, xout, D, R, D, D, w.proj_b, DIP_ACT_NONE);
+    g.res = xm;
+    DIP_TRY(linear(mode, g, w.proj_w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     return 0;
 }
 
@@ -207,26 +257,27 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
                      float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, float* dxin, int t_min,
                      dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
+    const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     // dU = (dxout . W_proj) * gelu'(u)
-    dip_gemm_args g = gemm(dxout, D, w.proj_wT, nullptr, dt1, D, R, D, D, DIP_ACT_MUL_QUICKGELU_GRAD);
+    dip_gemm_args g = gemm(dxout, D, dt1, D, R, D, D, nullptr, DIP_ACT_MUL_QUICKGELU_GRAD);
     g.aux = s.u;
-    DIP_TRY(dip_gemm_nt(&g, st));
+    DIP_TRY(linear(mode, g, w.proj_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dH2 = dU . W_fc
-    g = gemm(dt1, D, w.fc_wT, nullptr, dt2, D, R, D, D, DIP_ACT_NONE);
-    DIP_TRY(dip_gemm_nt(&g, st));
+    g = gemm(dt1, D, dt2, D, R, D, D, nullptr, DIP_ACT_NONE);
+    DIP_TRY(linear(mode, g, w.fc_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dxmid = dxout + LN2'(dH2)
     DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, 0, st));
-    // dAO = dxmid . W_out
-    g = gemm(dxm, D, w.out_wT, nullptr, dao, D, R, D, D, DIP_ACT_NONE);
-    if (mode == DIP_PRECISION_TC_SPLIT) { g.split_hi = do_hi; g.split_lo = do_lo; }
-    DIP_TRY(dip_gemm_nt(&g, st));
-    if (mode == DIP_PRECISION_TC_SPLIT)
+    // dAO = dxmid . W_out   (+ bf16 planes for the tensor-core attention backward)
+    g = gemm(dxm, D, dao, D, R, D, D, nullptr, DIP_ACT_NONE);
+    if (tc) { g.split_hi = do_hi; g.split_lo = do_lo; }
+    DIP_TRY(linear(mode, g, w.out_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    if (tc)
         DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
     else
         DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
     // dH1 = dQKV . W_in
-    g = gemm(dqkv, 3 * D, w.in_wT, nullptr, dt1, D, R, D, 3 * D, DIP_ACT_NONE);
-    DIP_TRY(dip_gemm_nt(&g, st));
+    g = gemm(dqkv, 3 * D, dt1, D, R, D, 3 * D, nullptr, DIP_ACT_NONE);
+    DIP_TRY(linear(mode, g, w.in_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dxin = dxmid + LN1'(dH1)
     DIP_TRY(dip_layernorm_bwd(dxin, dt1, xin, s.mean1, s.rstd1, w.ln1_w, dxm, R, t_min, st));
     return 0;
@@ -251,18 +302,19 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     const int64_t R1 = (int64_t)B * T1;
     if (!e->mproj_valid) {
         // mip . W1[:, :128]^T + b1 -- constant over samples and steps, hoisted out of the loop
-        dip_gemm_args g = gemm(e->inst.mip, D, e->w1m, e->b1, e->mproj, D, L, D, D, DIP_ACT_NONE);
+        dip_gemm_args g = gemm(e->inst.mip, D, e->mproj, D, L, D, D, e->b1, DIP_ACT_NONE);
+        g.W = e->w1m;
         DIP_TRY(dip_gemm_nt(&g, st));
         e->mproj_valid = true;
     }
     DIP_TRY(dip_time_token(w.tmp, B, T1, t, e->w1, e->b1, st));
-    dip_gemm_args g = gemm(x, D, e->w1x, nullptr, w.tmp, D, (int64_t)B * L, D, D, DIP_ACT_QUICKGELU);
+    dip_gemm_args g = gemm(x, D, w.tmp, D, (int64_t)B * L, D, D, nullptr, DIP_ACT_QUICKGELU);
     g.rows_in = L; g.rows_out = T1; g.row_off = 1; g.addmat = e->mproj;
-    DIP_TRY(dip_gemm_nt(&g, st));
+    DIP_TRY(linear(e->mode, g, e->w1x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // NO activation after linear_2: the reference's OrderedDict names both QuickGELUs "geru", so the
     // second entry replaces the first and mlp_xt is linear_1 -> QuickGELU -> linear_2 (diffusion.py:145-150)
-    g = gemm(w.tmp, D, e->w2, e->b2, w.hd, D, R1, D, D, DIP_ACT_NONE);
-    DIP_TRY(dip_gemm_nt(&g, st));
+    g = gemm(w.tmp, D, w.hd, D, R1, D, D, e->b2, DIP_ACT_NONE);
+    DIP_TRY(linear(e->mode, g, e->w2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     for (int l = 0; l < e->n_den; ++l)
         DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
                           nullptr, nullptr, nullptr, nullptr, e->mask_den, B, T1, st));
@@ -353,16 +405,16 @@ int dip_engine_set_denoiser(dip_engine* e, const float* w1, const float* b1, con
     e->mproj_valid = false;
     DIP_TRY(e->den_pool.alloc(&e->w1, 2 * D * D));
     DIP_TRY(e->den_pool.alloc(&e->w1m, D * D));
-    DIP_TRY(e->den_pool.alloc(&e->w1x, D * D));
+    DIP_TRY(e->den_pool.alloc(&e->w1x.w, D * D));
     DIP_TRY(e->den_pool.alloc(&e->b1, D));
-    DIP_TRY(e->den_pool.alloc(&e->w2, D * D));
     DIP_TRY(e->den_pool.alloc(&e->b2, D));
     DIP_CUDA(cudaMemcpyAsync(e->w1, w1, 2 * D * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     // split linear_1 (128, 256) into its mip half [:, :128] and its x half [:, 128:] (diffusion.py:156)
     DIP_CUDA(cudaMemcpy2DAsync(e->w1m, D * sizeof(float), w1, 2 * D * sizeof(float), D * sizeof(float), D, cudaMemcpyDeviceToDevice, st));
-    DIP_CUDA(cudaMemcpy2DAsync(e->w1x, D * sizeof(float), w1 + D, 2 * D * sizeof(float), D * sizeof(float), D, cudaMemcpyDeviceToDevice, st));
+    DIP_CUDA(cudaMemcpy2DAsync(e->w1x.w, D * sizeof(float), w1 + D, 2 * D * sizeof(float), D * sizeof(float), D, cudaMemcpyDeviceToDevice, st));
+    DIP_TRY(make_planes(e->den_pool, e->w1x, D * D, st));
     DIP_CUDA(cudaMemcpyAsync(e->b1, b1, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    DIP_CUDA(cudaMemcpyAsync(e->w2, w2, D * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DIP_TRY(copy_weight(e->den_pool, e->w2, w2, D * D, st));
     DIP_CUDA(cudaMemcpyAsync(e->b2, b2, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     for (int l = 0; l < n_layers; ++l) DIP_TRY(copy_block(e->den_pool, e->den[l], blocks[l], st));
     e->n_den = n_layers;

@@ -1,18 +1,27 @@
 // Flash attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), one head of width 128,
-// key-padding mask, "bf16x2 split" numerics (see tc_common.cuh): forward here, backward below.
+// key-padding mask, "bf16x2 split" numerics (see tc_common.cuh): forward and input-gradient backward.
 //
 // Operands are the bf16 (hi, lo) planes of the packed in_proj output, shape (B*T, 384) each, written
 // by the producing GEMM's epilogue.  Every tile is moved by TMA (SWIZZLE_128B boxes of 64 columns)
 // straight into the layout tcgen05.mma consumes; the same [rows x 128] tile serves as a K-major
 // operand (Q, K in S = Q K^T) or as an MN-major B operand (V in P V) by descriptor only.
 //
-// Forward CTA = 128 queries (one TMEM lane / one softmax thread per query), key tiles of 64:
-//   warp 4 : TMA producer (Q once, then a 2-stage K/V ring)
-//   warp 5 : one thread issues tcgen05.mma:  S_j = Q K_j^T (3 passes) into a double-buffered TMEM
-//            tile, PV_j = P_j V_j (3 passes) into a second TMEM tile; S_{j+1} is queued before PV_j so the
-//            tensor pipe works while the softmax warps turn S_j into P_j
-//   warps 0-3 : online softmax in registers (exp2 domain), P_j written as bf16 hi/lo into swizzled
-//            shared memory, running output kept in registers and folded with each PV_j tile.
+// Two measured facts of tcgen05.mma on B200 shape these kernels (tools/mma_bench.cu, tools/mma_ts_test.cu):
+//  (1) with M = 128 every instruction costs max(~66, N/2) cycles when A is read from shared memory -- small-N
+//      MMAs waste the pipe.  The score GEMMs therefore stack the hi and lo planes of the streamed operand
+//      along N: one B operand [X_hi ; X_lo] of 2 x rows, issued once with A_hi and once with A_lo into the
+//      SAME accumulator.  Column block 0 then holds A.X_hi, block 1 holds A.X_lo; their sum -- formed by the
+//      row threads -- is the exact four-term product, for 2 MMAs per k-step instead of 3.
+//  (2) the A operand may live in tensor memory (lane = row, 32-bit column = bf16 pair).  P and dS are
+//      written there by the row threads (tcgen05.st) and never touch shared memory; the space pays for a
+//      third pipeline stage.
+//
+// All kernels: 320 threads = 8 "row" warps + 1 producer warp + 1 MMA warp.
+//   warps 0-7 : two warps per TMEM lane quarter; thread (row r, half h) owns row r of the 128-row tile
+//               and half of its columns.
+//   warp 8    : TMA producer; its 32 lanes also ballot the key-padding mask of every streamed tile into a
+//               bit word, so the row warps never touch global memory inside the loop.
+//   warp 9    : one thread issues tcgen05.mma / tcgen05.commit.
 #include <math.h>
 #include "tc_common.cuh"
 
@@ -21,33 +30,56 @@ namespace tcattn {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 64;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float SM_SCALE = 0.08838834764831845f;
+constexpr float SC2 = SM_SCALE * LOG2E;         // scores are exponentiated in base 2
+constexpr int NTHREADS = 320, ROW_THREADS = 256, W_PRODUCER = 8, W_MMA = 9;
+constexpr uint32_t SMEM_LIMIT = 232448;
 
-constexpr uint32_t Q_BYTES = 65536;        // hi [2][128][64] + lo [2][128][64] bf16
-constexpr uint32_t KV_STAGE = 65536;       // K hi, K lo, V hi, V lo: [2][64][64] bf16 each
-constexpr uint32_t P_BYTES = 32768;        // hi [128][64] + lo [128][64]
-constexpr uint32_t OFF_KV = Q_BYTES, OFF_P = Q_BYTES + 2 * KV_STAGE, OFF_BAR = OFF_P + P_BYTES;
-constexpr uint32_t FWD_SMEM = OFF_BAR + 256 + 1024;   // + barriers + alignment slack
+__device__ __forceinline__ void require_aligned_smem(const void* p) {
+    if ((smem_u32(p) & 1023u) != 0u) {
+        if (threadIdx.x == 0) printf("dip: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+}
 
-constexpr uint32_t IDESC_S = instr_desc(128, BN, 0, 0);     // Q (K-major) x K (K-major) -> 128 x 64
-constexpr uint32_t IDESC_PV = instr_desc(128, 128, 0, 1);   // P (K-major) x V (MN-major) -> 128 x 128
+// =============================================================================================
+// forward: CTA = 128 queries, key tiles of 64
+// =============================================================================================
+// shared memory: Q hi/lo resident (64 KB) | K ring, 3 stages x 32 KB, each [kb][hi,lo][64 keys][64 d]
+//                (k-block kb: 128 stacked rows = B operand of the score MMA) | V ring, 2 stages x 32 KB,
+//                each [hi,lo][d-half][64 keys][64 d] (MN-major B operand of P.V)
+// tensor memory: [0,256) two score buffers of 128 columns (Q.K_hi | Q.K_lo), [256,384) P.V,
+//                [384,512) two P buffers of (32 hi + 32 lo) packed columns
+constexpr int BM = 128, BN = 64;
+constexpr uint32_t Q_BYTES = 65536, K_STAGE = 32768, V_STAGE = 32768;
+constexpr int K_STAGES = 3, V_STAGES = 2;
+constexpr uint32_t OFF_K = Q_BYTES, OFF_V = OFF_K + K_STAGES * K_STAGE, OFF_BAR = OFF_V + V_STAGES * V_STAGE;
+constexpr uint32_t OFF_BITS = OFF_BAR + 192, OFF_XM = OFF_BAR + 256;      // mask-bit ring (8 x u64), row-max exchange [2][2][128] f32
+constexpr uint32_t FWD_SMEM = OFF_XM + 2048;
+static_assert(OFF_BAR == 229376 && FWD_SMEM <= SMEM_LIMIT, "forward kernel shared memory");
+constexpr uint32_t TM_S = 0, TM_PV = 256, TM_P = 384;
 
-enum { B_QFULL = 0, B_KVFULL = 1, B_KVEMPTY = 3, B_SFULL = 5, B_SFREE = 7, B_PFULL = 9, B_PVFULL = 10, B_COUNT = 11 };
+constexpr uint32_t IDESC_S = instr_desc(128, 128, 0, 0);    // Q (K-major) x [K_hi;K_lo] (K-major) -> 128 x 128
+constexpr uint32_t IDESC_PV = instr_desc(128, 128, 0, 1);   // P (tensor memory) x V (MN-major) -> 128 x 128
+constexpr float RESCALE_THRESHOLD = 8.0f;                   // log2 units: P stays below 2^8 between rescales
 
-__global__ void __launch_bounds__(192, 1)
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17, B_PVFREE = 18 };
+
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_constant__ CUtensorMap tm_lo128,
                    const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64, float* __restrict__ o,
                    float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t sm[];
+    require_aligned_smem(sm);
     uint8_t* sQ = sm;
-    uint8_t* sKV = sm + OFF_KV;
-    uint8_t* sP = sm + OFF_P;
+    uint8_t* sK = sm + OFF_K;
+    uint8_t* sV = sm + OFF_V;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    volatile uint64_t* bits_ring = reinterpret_cast<volatile uint64_t*>(sm + OFF_BITS);
+    volatile float* xm = reinterpret_cast<volatile float*>(sm + OFF_XM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * BM;
@@ -56,24 +88,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[B_QFULL], 1);
+        for (int s = 0; s < K_STAGES; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[B_KVFULL + s], 1);
-            mbar_init(&bars[B_KVEMPTY + s], 1);
+            mbar_init(&bars[B_VFULL + s], 1);
+            mbar_init(&bars[B_VEMPTY + s], 1);
             mbar_init(&bars[B_SFULL + s], 1);
-            mbar_init(&bars[B_SFREE + s], 128);
+            mbar_init(&bars[B_SFREE + s], ROW_THREADS);
+            mbar_init(&bars[B_PFULL + s], ROW_THREADS);
         }
-        mbar_init(&bars[B_PFULL], 128);
         mbar_init(&bars[B_PVFULL], 1);
+        mbar_init(&bars[B_PVFREE], ROW_THREADS);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;      // columns [0,64) S buf 0, [64,128) S buf 1, [128,256) PV
+    const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp == W_PRODUCER) {
+        // ------------------------------------------------------------------ TMA producer + mask ballots
+        const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
+        auto load_K = [&](int j) {      // all lanes: ballot the mask of tile j; lane 0: wait for the stage, issue the 4 boxes
+            const int s = j % K_STAGES;
+            const int k0 = j * BN + lane, k1 = k0 + 32;
+            const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
+            const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
+            if (lane == 0) {
+                if (j >= K_STAGES) mbar_wait(&bars[B_KEMPTY + s], ((j / K_STAGES) - 1) & 1);
+                bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
+                mbar_expect_tx(&bars[B_KFULL + s], K_STAGE);
+                uint8_t* dst = sK + s * K_STAGE;
+                const int krow = row_base + j * BN;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_2d(dst + kb * 16384, &tm_hi64, &bars[B_KFULL + s], 128 + kb * 64, krow);           // rows 0-63 of the stacked operand
+                    tma_load_2d(dst + kb * 16384 + 8192, &tm_lo64, &bars[B_KFULL + s], 128 + kb * 64, krow);    // rows 64-127
+                }
+            }
+            __syncwarp();
+        };
         if (lane == 0) {
             tma_prefetch_desc(&tm_hi128); tma_prefetch_desc(&tm_lo128); tma_prefetch_desc(&tm_hi64); tma_prefetch_desc(&tm_lo64);
             mbar_expect_tx(&bars[B_QFULL], Q_BYTES);
@@ -81,66 +135,70 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 tma_load_2d(sQ + kb * 16384, &tm_hi128, &bars[B_QFULL], kb * 64, row_base + q0);
                 tma_load_2d(sQ + 32768 + kb * 16384, &tm_lo128, &bars[B_QFULL], kb * 64, row_base + q0);
             }
-            for (int j = 0; j < n_tiles; ++j) {
+        }
+        load_K(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) load_K(j + 1);          // K runs one tile ahead of V: it is released after S_j, long before P_j.V_j
+            if (lane == 0) {
                 const int s = j & 1;
-                if (j >= 2) mbar_wait(&bars[B_KVEMPTY + s], ((j >> 1) - 1) & 1);
-                mbar_expect_tx(&bars[B_KVFULL + s], KV_STAGE);
-                uint8_t* dst = sKV + s * KV_STAGE;
+                if (j >= 2) mbar_wait(&bars[B_VEMPTY + s], ((j >> 1) - 1) & 1);
+                mbar_expect_tx(&bars[B_VFULL + s], V_STAGE);
+                uint8_t* dst = sV + s * V_STAGE;
                 const int krow = row_base + j * BN;
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_2d(dst + kb * 8192, &tm_hi64, &bars[B_KVFULL + s], 128 + kb * 64, krow);            // K hi
-                    tma_load_2d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_KVFULL + s], 128 + kb * 64, krow);    // K lo
-                    tma_load_2d(dst + 32768 + kb * 8192, &tm_hi64, &bars[B_KVFULL + s], 256 + kb * 64, krow);    // V hi
-                    tma_load_2d(dst + 49152 + kb * 8192, &tm_lo64, &bars[B_KVFULL + s], 256 + kb * 64, krow);    // V lo
+                    tma_load_2d(dst + kb * 8192, &tm_hi64, &bars[B_VFULL + s], 256 + kb * 64, krow);            // V hi, d-half kb
+                    tma_load_2d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_VFULL + s], 256 + kb * 64, krow);    // V lo
                 }
             }
+            __syncwarp();
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV), aP = smem_u32(sP);
+            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
             mbar_wait(&bars[B_QFULL], 0);
             auto issue_S = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(&bars[B_KVFULL + s], (j >> 1) & 1);
-                if (j >= 2) mbar_wait(&bars[B_SFREE + s], ((j >> 1) - 1) & 1);
+                const int s = j % K_STAGES, sb = j & 1;
+                mbar_wait(&bars[B_KFULL + s], (j / K_STAGES) & 1);
+                if (j >= 2) mbar_wait(&bars[B_SFREE + sb], ((j >> 1) - 1) & 1);
                 tc_fence_after();
-                const uint32_t kbase = aKV + s * KV_STAGE;
+                const uint32_t kbase = aK + s * K_STAGE;
                 uint32_t acc = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t qa = aQ + (pass == 2 ? 32768 : 0);            // hi, hi, lo
-                    const uint32_t ka = kbase + (pass == 1 ? 16384 : 0);        // hi, lo, hi
+                for (int pl = 0; pl < 2; ++pl)                     // A = Q_hi, then Q_lo, into the same 128 columns
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            tc_mma(tmem + s * BN, smem_desc(qa + kb * 16384 + ks * 32, 16, 1024), smem_desc(ka + kb * 8192 + ks * 32, 16, 1024),
-                                   IDESC_S, acc);
+                            tc_mma(tmem + TM_S + sb * 128, smem_desc(aQ + pl * 32768 + kb * 16384 + ks * 32, 16, 1024),
+                                   smem_desc(kbase + kb * 16384 + ks * 32, 16, 1024), IDESC_S, acc);
                             acc = 1;
                         }
-                }
-                tc_commit(&bars[B_SFULL + s]);
+                tc_commit(&bars[B_SFULL + sb]);
+                tc_commit(&bars[B_KEMPTY + s]);
             };
             auto issue_PV = [&](int j) {
                 const int s = j & 1;
-                mbar_wait(&bars[B_PFULL], j & 1);
+                mbar_wait(&bars[B_VFULL + s], (j >> 1) & 1);
+                mbar_wait(&bars[B_PFULL + s], (j >> 1) & 1);
+                if (j > 0) mbar_wait(&bars[B_PVFREE], (j - 1) & 1);          // the row warps have folded the previous P.V tile
                 tc_fence_after();
-                const uint32_t vbase = aKV + s * KV_STAGE + 32768;
+                const uint32_t vbase = aV + s * V_STAGE;
+                const uint32_t pbase = tmem + TM_P + s * 64;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t pa = aP + (pass == 2 ? 16384 : 0);           // hi, hi, lo
-                    const uint32_t va = vbase + (pass == 1 ? 16384 : 0);        // hi, lo, hi
+                    const uint32_t pa = pbase + (pass == 2 ? 32 : 0);           // P hi, hi, lo
+                    const uint32_t va = vbase + (pass == 1 ? 16384 : 0);        // V hi, lo, hi
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         // V tile: two [64 keys x 64 d] blocks 8192 bytes apart (MN blocks), 16 keys per k-step = 2048 bytes
-                        tc_mma(tmem + 128, smem_desc(pa + ks * 32, 16, 1024), smem_desc(va + ks * 2048, 8192, 1024), IDESC_PV, acc);
+                        tc_mma_ts(tmem + TM_PV, pa + ks * 8, smem_desc(va + ks * 2048, 8192, 1024), IDESC_PV, acc);
                         acc = 1;
                     }
                 }
                 tc_commit(&bars[B_PVFULL]);
-                tc_commit(&bars[B_KVEMPTY + s]);
+                tc_commit(&bars[B_VEMPTY + s]);
             };
             issue_S(0);
             for (int j = 0; j < n_tiles; ++j) {
@@ -149,154 +207,157 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax: thread = query row
-        const int row = threadIdx.x;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
-        float oacc[128];
+        // ------------------------------------------------------------------ row warps: thread = (query row, key half)
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        float oacc[64];
 #pragma unroll
-        for (int i = 0; i < 128; ++i) oacc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        for (int i = 0; i < 64; ++i) oacc[i] = 0.f;
+        float m_used = -INFINITY, l_part = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
             mbar_wait(&bars[B_SFULL + s], (j >> 1) & 1);
             tc_fence_after();
-            float sv[64];
+            float sv[32];
             {
-                float t0[32], t1[32];
-                tmem_ld32(lane_addr + s * BN, t0);
-                tmem_ld32(lane_addr + s * BN + 32, t1);
+                float s_lo[32];
+                tmem_ld32(lane_addr + TM_S + s * 128 + h * 32, sv);           // Q . K_hi
+                tmem_ld32(lane_addr + TM_S + s * 128 + 64 + h * 32, s_lo);    // Q . K_lo
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { sv[i] = t0[i]; sv[32 + i] = t1[i]; }
+                for (int c = 0; c < 32; ++c) sv[c] += s_lo[c];
             }
             tc_fence_before();
             mbar_arrive(&bars[B_SFREE + s]);
+            const uint32_t mb = (uint32_t)(bits_ring[j & 7] >> (32 * h));
             float mx = -INFINITY;
+            if (mb == 0u) {
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                const int key = j * BN + c;
-                const bool masked = (key >= T) || (mrow && mrow[key]);
-                sv[c] = masked ? -INFINITY : sv[c] * (SM_SCALE * LOG2E);
-                mx = fmaxf(mx, sv[c]);
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, sv[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if ((mb >> c) & 1u) sv[c] = -INFINITY;
+                    mx = fmaxf(mx, sv[c]);
+                }
             }
-            const float m_new = fmaxf(m_run, mx);
-            const bool dead = (m_new == -INFINITY);
-            const float alpha = dead ? 1.0f : exp2f(m_run - m_new);
+            // the two key halves of a row agree on the tile maximum through shared memory
+            xm[(s * 2 + h) * 128 + row] = mx;
+            named_bar_sync(1, ROW_THREADS);
+            const float m_tile = fmaxf(mx, xm[(s * 2 + (h ^ 1)) * 128 + row]) * SC2;
+            // lazy rescaling: the exponent base only moves when the row maximum grew by more than 2^8
+            const bool need = m_tile > m_used + RESCALE_THRESHOLD;
+            const float m_new = need ? m_tile : m_used;
+            const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+            const bool any_need = __any_sync(0xffffffffu, need);
+            const float neg_m = (m_new == -INFINITY) ? 0.f : -m_new;
             float rowsum = 0.f;
+            uint32_t phi[16], plo[16];
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                const float p = dead ? 0.f : exp2f(sv[c] - m_new);
-                sv[c] = p;
-                rowsum += p;
+            for (int c = 0; c < 16; ++c) {
+                const float p0 = ex2_approx(fmaf(sv[2 * c], SC2, neg_m));
+                const float p1 = ex2_approx(fmaf(sv[2 * c + 1], SC2, neg_m));
+                rowsum += p0 + p1;
+                split2(p0, p1, phi[c], plo[c]);
             }
-            l_run = l_run * alpha + rowsum;
-            m_run = m_new;
-            // previous tile's P.V must be complete before P is overwritten; fold it into the running output
+            l_part = l_part * alpha + rowsum;
+            m_used = m_new;
+            // P_j -> tensor memory (A operand of P.V): this half's 32 keys = 16 packed columns per plane.
+            // Buffer s was last read by P_{j-2}.V_{j-2}, whose completion this thread observed one iteration ago.
+            tmem_st16(lane_addr + TM_P + s * 64 + h * 16, phi);
+            tmem_st16(lane_addr + TM_P + s * 64 + 32 + h * 16, plo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[B_PFULL + s]);
             if (j > 0) {
                 mbar_wait(&bars[B_PVFULL], (j - 1) & 1);
                 tc_fence_after();
-            }
-            // P_j -> shared memory (bf16 hi / lo, K-major SWIZZLE_128B: row = query, 8 chunks of 8 keys)
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(sv[c8 * 8 + 2 * e], h0, l0);
-                    split_bf16(sv[c8 * 8 + 2 * e + 1], h1, l1);
-                    hw[e] = pack2(h0, h1);
-                    lw[e] = pack2(l0, l1);
-                }
-                const uint32_t off = sw128_off(row, c8);
-                *reinterpret_cast<uint4*>(sP + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(sP + 16384 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-            if (j > 0) {
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < 2; ++ch) {
                     float t[32];
-                    tmem_ld32(lane_addr + 128 + ch * 32, t);
+                    tmem_ld32(lane_addr + TM_PV + h * 64 + ch * 32, t);
+                    if (any_need) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) oacc[ch * 32 + i] = (oacc[ch * 32 + i] + t[i]) * alpha;
+                        for (int i = 0; i < 32; ++i) oacc[ch * 32 + i] = (oacc[ch * 32 + i] + t[i]) * alpha;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) oacc[ch * 32 + i] += t[i];
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(&bars[B_PVFREE]);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&bars[B_PFULL]);
         }
         mbar_wait(&bars[B_PVFULL], (n_tiles - 1) & 1);
         tc_fence_after();
+        // total row sum = the two halves' partial sums
+        named_bar_sync(1, ROW_THREADS);
+        xm[h * 128 + row] = l_part;
+        named_bar_sync(1, ROW_THREADS);
+        const float l_run = l_part + xm[(h ^ 1) * 128 + row];
         const float inv = 1.0f / l_run;
         const int t_q = q0 + row;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
             float t[32];
-            tmem_ld32(lane_addr + 128 + ch * 32, t);
+            tmem_ld32(lane_addr + TM_PV + h * 64 + ch * 32, t);
             if (t_q < T) {
-                float* orow = o + ((int64_t)row_base + t_q) * D + ch * 32;
+                float* orow = o + ((int64_t)row_base + t_q) * D + h * 64 + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                     *reinterpret_cast<float4*>(orow + i) = make_float4((oacc[ch * 32 + i] + t[i]) * inv, (oacc[ch * 32 + i + 1] + t[i + 1]) * inv,
                                                                        (oacc[ch * 32 + i + 2] + t[i + 2]) * inv, (oacc[ch * 32 + i + 3] + t[i + 3]) * inv);
             }
         }
-        if (lse && t_q < T) lse[(int64_t)row_base + t_q] = m_run * LN2 + logf(l_run);
+        if (lse && h == 0 && t_q < T) lse[(int64_t)row_base + t_q] = m_used * LN2 + logf(l_run);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
-
 
 // =============================================================================================
 // backward (input gradients only, deterministic: no atomics)
 // =============================================================================================
 // Two launches of one templated kernel, both with a 128-row stationary operand pair in shared memory
-// and 32-row streamed tiles (2-stage TMA ring):
+// and 32-row streamed tiles (3-stage TMA ring):
 //   KS = true  (key-stationary)   rows = keys   : X = K, Y = V stationary; U = Q, W = dO streamed
 //        G1 = K Q^T (= S^T), G2 = V dO^T (= dP^T);  dV += P^T dO,  dK += dS^T Q
 //   KS = false (query-stationary) rows = queries: X = Q, Y = dO stationary; U = K, W = V streamed
 //        G1 = Q K^T (= S),   G2 = dO V^T (= dP);    dQ += dS K
-// P = exp(S/sqrt(d) - lse[query]) and dS = P (dP - delta[query]) / sqrt(d) are formed by the 128 row
-// threads from TMEM and written back to shared memory as bf16 hi/lo in the un-swizzled ("interleaved")
-// K-major core-matrix layout; the streamed tiles double as MN-major B operands of the accumulating GEMMs.
-constexpr int BT = 32;                         // streamed tile rows
+// P = exp(S/sqrt(d) - lse[query]) and dS = P (dP - delta[query]) / sqrt(d) are formed by the row warps and
+// written to tensor memory as the A operands of the accumulating GEMMs; the streamed tiles double as
+// their MN-major B operands.
+// shared memory: X hi/lo, Y hi/lo (128 KB) | ring of 3 stages x 32 KB, each U then W as [d-half][hi,lo][32 rows][64 d]
+//                (d-half kb: 64 stacked rows = B operand of a score MMA; plane p: two d-halves 8192 bytes apart = MN-major B)
+// tensor memory: [0,64) G1 (X.U_hi | X.U_lo), [64,128) G2, [128,256) acc1 (dV), [256,384) acc2 (dK / dQ),
+//                [384,512) two P/dS buffers of 64 columns: P hi, P lo, dS hi, dS lo (16 packed columns each)
+constexpr int BT = 32, TL_STAGES = 3;
 constexpr uint32_t ST_PLANE = 32768;           // stationary plane: [2][128][64] bf16
-constexpr uint32_t TL_PLANE = 8192;            // streamed plane:   [2][32][64] bf16
-constexpr uint32_t TL_STAGE = 4 * TL_PLANE;    // U hi, U lo, W hi, W lo
-constexpr uint32_t PD_PLANE = 8192;            // [128][32] bf16 interleaved
-constexpr uint32_t BOFF_X = 0, BOFF_Y = 2 * ST_PLANE, BOFF_TL = 4 * ST_PLANE, BOFF_PD = BOFF_TL + 2 * TL_STAGE,
-                   BOFF_BAR = BOFF_PD + 4 * PD_PLANE;
-constexpr uint32_t BWD_SMEM = BOFF_BAR + 256 + 1024;
-constexpr uint32_t IDESC_G = instr_desc(128, BT, 0, 0);       // X (K-major) x U (K-major) -> 128 x 32
-constexpr uint32_t IDESC_ACC = instr_desc(128, 128, 0, 1);    // P/dS (K-major) x U/W (MN-major) -> 128 x 128
+constexpr uint32_t TL_HALF = 16384;            // U or W of one stage
+constexpr uint32_t TL_STAGE = 2 * TL_HALF;
+constexpr uint32_t BOFF_X = 0, BOFF_Y = 2 * ST_PLANE, BOFF_TL = 4 * ST_PLANE, BOFF_BAR = BOFF_TL + TL_STAGES * TL_STAGE, BOFF_BITS = BOFF_BAR + 192;
+constexpr uint32_t BWD_SMEM = BOFF_BAR + 256;
+static_assert(BOFF_BAR == 229376 && BWD_SMEM <= SMEM_LIMIT, "backward kernel shared memory");
+constexpr uint32_t TM_G1 = 0, TM_G2 = 64, TM_ACC1 = 128, TM_ACC2 = 256, TM_PD = 384;
+constexpr uint32_t IDESC_G = instr_desc(128, 2 * BT, 0, 0);   // X (K-major) x [U_hi;U_lo] (K-major) -> 128 x 64
+constexpr uint32_t IDESC_ACC = instr_desc(128, 128, 0, 1);    // P/dS (tensor memory) x U/W (MN-major) -> 128 x 128
 
-enum { C_XFULL = 0, C_TLFULL = 1, C_TLEMPTY = 3, C_GFULL = 5, C_GFREE = 7, C_PDFULL = 9, C_PDFREE = 10, C_DONE = 11 };
-
-// un-swizzled K-major descriptor for the [128 x 32] P / dS tiles: core matrix = 8 rows x 16 bytes,
-// K-adjacent core matrices 128 bytes apart (LBO), 8-row groups 512 bytes apart (SBO)
-__device__ __forceinline__ uint64_t nosw_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(128u >> 4) << 16;
-    d |= (uint64_t)(512u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
+enum { C_XFULL = 0, C_TLFULL = 1, C_TLEMPTY = 4, C_GFULL = 7, C_GFREE = 8, C_PDFULL = 9, C_PDFREE = 11, C_DONE = 13 };
 
 template <bool KS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
                    const __grid_constant__ CUtensorMap tm_qkv_hi32, const __grid_constant__ CUtensorMap tm_qkv_lo32,
                    const __grid_constant__ CUtensorMap tm_do_hi128, const __grid_constant__ CUtensorMap tm_do_lo128,
                    const __grid_constant__ CUtensorMap tm_do_hi32, const __grid_constant__ CUtensorMap tm_do_lo32,
                    float* __restrict__ out1, float* __restrict__ out2, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
                    const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t sm[];
+    require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BOFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    volatile uint32_t* bits_ring = reinterpret_cast<volatile uint32_t*>(sm + BOFF_BITS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, r0 = blockIdx.x * 128;      // first stationary row (key for KS, query otherwise)
@@ -305,14 +366,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[C_XFULL], 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[C_TLFULL + s], 1);
-            mbar_init(&bars[C_TLEMPTY + s], 1);
-            mbar_init(&bars[C_GFULL + s], 1);
-            mbar_init(&bars[C_GFREE + s], 128);
-        }
-        mbar_init(&bars[C_PDFULL], 128);
-        mbar_init(&bars[C_PDFREE], 1);
+        for (int s = 0; s < TL_STAGES; ++s) { mbar_init(&bars[C_TLFULL + s], 1); mbar_init(&bars[C_TLEMPTY + s], 1); }
+        mbar_init(&bars[C_GFULL], 1);
+        mbar_init(&bars[C_GFREE], ROW_THREADS);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[C_PDFULL + s], ROW_THREADS); mbar_init(&bars[C_PDFREE + s], 1); }
         mbar_init(&bars[C_DONE], 1);
         mbar_fence_init();
     }
@@ -320,13 +377,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;     // [0,64) G1 x2, [64,128) G2 x2, [128,256) acc1 (dV), [256,384) acc2 (dK / dQ)
+    const uint32_t tmem = *tmem_slot;
 
     // column of the packed (q|k|v) planes each operand lives in
     constexpr int COL_X = KS ? 128 : 0;      // K : Q
     constexpr int COL_U = KS ? 0 : 128;      // Q : K
+    const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
 
-    if (warp == 4) {
+    if (warp == W_PRODUCER) {
+        const CUtensorMap* whi = KS ? &tm_do_hi32 : &tm_qkv_hi32;
+        const CUtensorMap* wlo = KS ? &tm_do_lo32 : &tm_qkv_lo32;
+        const int col_w = KS ? 0 : 256;  // dO : V
         if (lane == 0) {
             const CUtensorMap* yhi = KS ? &tm_qkv_hi128 : &tm_do_hi128;
             const CUtensorMap* ylo = KS ? &tm_qkv_lo128 : &tm_do_lo128;
@@ -338,77 +399,79 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 tma_load_2d(sm + BOFF_Y + kb * 16384, yhi, &bars[C_XFULL], col_y + kb * 64, row_base + r0);
                 tma_load_2d(sm + BOFF_Y + ST_PLANE + kb * 16384, ylo, &bars[C_XFULL], col_y + kb * 64, row_base + r0);
             }
-            const CUtensorMap* whi = KS ? &tm_do_hi32 : &tm_qkv_hi32;
-            const CUtensorMap* wlo = KS ? &tm_do_lo32 : &tm_qkv_lo32;
-            const int col_w = KS ? 0 : 256;  // dO : V
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                if (j >= 2) mbar_wait(&bars[C_TLEMPTY + s], ((j >> 1) - 1) & 1);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j % TL_STAGES;
+            // invalid streamed rows of this tile: beyond T, or (query-stationary: streamed rows are keys) masked keys
+            const int c = j * BT + lane;
+            const bool bad = (c >= T) || (!KS && mrow && mrow[c]);
+            const uint32_t bits = __ballot_sync(0xffffffffu, bad);
+            if (lane == 0) {
+                if (j >= TL_STAGES) mbar_wait(&bars[C_TLEMPTY + s], ((j / TL_STAGES) - 1) & 1);
+                bits_ring[j & 7] = bits;
                 mbar_expect_tx(&bars[C_TLFULL + s], TL_STAGE);
                 uint8_t* dst = sm + BOFF_TL + s * TL_STAGE;
                 const int trow = row_base + j * BT;
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_2d(dst + kb * 4096, &tm_qkv_hi32, &bars[C_TLFULL + s], COL_U + kb * 64, trow);
-                    tma_load_2d(dst + TL_PLANE + kb * 4096, &tm_qkv_lo32, &bars[C_TLFULL + s], COL_U + kb * 64, trow);
-                    tma_load_2d(dst + 2 * TL_PLANE + kb * 4096, whi, &bars[C_TLFULL + s], col_w + kb * 64, trow);
-                    tma_load_2d(dst + 3 * TL_PLANE + kb * 4096, wlo, &bars[C_TLFULL + s], col_w + kb * 64, trow);
+                    tma_load_2d(dst + kb * 8192, &tm_qkv_hi32, &bars[C_TLFULL + s], COL_U + kb * 64, trow);                // U hi, d-half kb
+                    tma_load_2d(dst + kb * 8192 + 4096, &tm_qkv_lo32, &bars[C_TLFULL + s], COL_U + kb * 64, trow);         // U lo
+                    tma_load_2d(dst + TL_HALF + kb * 8192, whi, &bars[C_TLFULL + s], col_w + kb * 64, trow);               // W hi
+                    tma_load_2d(dst + TL_HALF + kb * 8192 + 4096, wlo, &bars[C_TLFULL + s], col_w + kb * 64, trow);        // W lo
                 }
             }
+            __syncwarp();
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         if (lane == 0) {
-            const uint32_t aX = smem_u32(sm + BOFF_X), aY = smem_u32(sm + BOFF_Y), aTL = smem_u32(sm + BOFF_TL), aPD = smem_u32(sm + BOFF_PD);
+            const uint32_t aX = smem_u32(sm + BOFF_X), aY = smem_u32(sm + BOFF_Y), aTL = smem_u32(sm + BOFF_TL);
             mbar_wait(&bars[C_XFULL], 0);
             auto issue_G = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(&bars[C_TLFULL + s], (j >> 1) & 1);
-                if (j >= 2) mbar_wait(&bars[C_GFREE + s], ((j >> 1) - 1) & 1);
+                const int s = j % TL_STAGES;
+                mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);
+                if (j >= 1) mbar_wait(&bars[C_GFREE], (j - 1) & 1);
                 tc_fence_after();
                 const uint32_t tl = aTL + s * TL_STAGE;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {                       // g = 0: X.U^T, g = 1: Y.W^T
+                for (int g = 0; g < 2; ++g) {                       // g = 0: X.[U_hi;U_lo]^T, g = 1: Y.[W_hi;W_lo]^T
                     const uint32_t st = g == 0 ? aX : aY;
-                    const uint32_t tp = tl + g * 2 * TL_PLANE;
+                    const uint32_t tp = tl + g * TL_HALF;
                     uint32_t acc = 0;
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a = st + (pass == 2 ? ST_PLANE : 0);          // hi, hi, lo
-                        const uint32_t bb = tp + (pass == 1 ? TL_PLANE : 0);         // hi, lo, hi
+                    for (int pl = 0; pl < 2; ++pl)                  // A = stationary hi, then lo, into the same 64 columns
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                tc_mma(tmem + g * 64 + s * BT, smem_desc(a + kb * 16384 + ks * 32, 16, 1024),
-                                       smem_desc(bb + kb * 4096 + ks * 32, 16, 1024), IDESC_G, acc);
+                                tc_mma(tmem + (g == 0 ? TM_G1 : TM_G2), smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024),
+                                       smem_desc(tp + kb * 8192 + ks * 32, 16, 1024), IDESC_G, acc);
                                 acc = 1;
                             }
-                    }
                 }
-                tc_commit(&bars[C_GFULL + s]);
+                tc_commit(&bars[C_GFULL]);
             };
             auto issue_acc = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(&bars[C_PDFULL], j & 1);
+                const int s = j % TL_STAGES, pb = j & 1;
+                mbar_wait(&bars[C_PDFULL + pb], (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t tl = aTL + s * TL_STAGE;
+                const uint32_t pd = tmem + TM_PD + pb * 64;
 #pragma unroll
                 for (int g = (KS ? 0 : 1); g < 2; ++g) {            // g = 0: acc1 += P.W (dV), g = 1: acc2 += dS.U (dK / dQ)
-                    const uint32_t pd = aPD + g * 2 * PD_PLANE;
-                    const uint32_t tp = tl + (g == 0 ? 2 * TL_PLANE : 0);
+                    const uint32_t tp = tl + (g == 0 ? TL_HALF : 0);
                     uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a = pd + (pass == 2 ? PD_PLANE : 0);
-                        const uint32_t bb = tp + (pass == 1 ? TL_PLANE : 0);
+                        const uint32_t a = pd + g * 32 + (pass == 2 ? 16 : 0);        // A hi, hi, lo (16 packed columns per plane)
+                        const uint32_t bb = tp + (pass == 1 ? 4096 : 0);              // B hi, lo, hi
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
-                            // streamed tile as MN-major B: d-halves 4096 bytes apart, 16 rows per k-step = 2048 bytes
-                            tc_mma(tmem + 128 + g * 128, nosw_desc(a + ks * 256), smem_desc(bb + ks * 2048, 4096, 1024), IDESC_ACC, acc);
+                            // streamed tile as MN-major B: d-halves 8192 bytes apart, 16 rows per k-step = 2048 bytes
+                            tc_mma_ts(tmem + (g == 0 ? TM_ACC1 : TM_ACC2), a + ks * 8, smem_desc(bb + ks * 2048, 8192, 1024), IDESC_ACC, acc);
                             acc = 1;
                         }
                     }
                 }
-                tc_commit(&bars[C_PDFREE]);
+                tc_commit(&bars[C_PDFREE + pb]);
                 tc_commit(&bars[C_TLEMPTY + s]);
             };
             issue_G(0);
@@ -419,9 +482,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             tc_commit(&bars[C_DONE]);
         }
     } else {
-        const int row = threadIdx.x;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
+        // ------------------------------------------------------------------ row warps: thread = (stationary row, 16 of the 32 tile columns)
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         const int r_idx = r0 + row;
         bool row_ok = r_idx < T;
         float row_lse2 = 0.f, row_delta = 0.f;
@@ -431,70 +495,70 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             row_lse2 = lse[(int64_t)row_base + r_idx] * LOG2E;
             row_delta = delta[(int64_t)row_base + r_idx];
         }
-        uint8_t* sPD = sm + BOFF_PD;
-        const uint32_t wr_off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 16u;
         for (int j = 0; j < n_tiles; ++j) {
-            const int s = j & 1;
-            mbar_wait(&bars[C_GFULL + s], (j >> 1) & 1);
+            const int pb = j & 1;
+            // key-stationary: lanes 0-15 fetch lse, lanes 16-31 delta of this thread's 16 queries; broadcast by shuffle below
+            float qstat = 0.f;
+            if (KS) {
+                const int cq = j * BT + h * 16 + (lane & 15);
+                if (cq < T) qstat = (lane < 16) ? __ldg(lse + (int64_t)row_base + cq) * LOG2E : __ldg(delta + (int64_t)row_base + cq);
+            }
+            mbar_wait(&bars[C_GFULL], j & 1);
             tc_fence_after();
-            float g1[32], g2[32];
-            tmem_ld32(lane_addr + s * BT, g1);
-            tmem_ld32(lane_addr + 64 + s * BT, g2);
-            tc_fence_before();
-            mbar_arrive(&bars[C_GFREE + s]);
+            float g1[16], g2[16];
+            {
+                float t1[16], t2[16];
+                tmem_ld16(lane_addr + TM_G1 + h * 16, g1);
+                tmem_ld16(lane_addr + TM_G1 + 32 + h * 16, t1);
+                tmem_ld16(lane_addr + TM_G2 + h * 16, g2);
+                tmem_ld16(lane_addr + TM_G2 + 32 + h * 16, t2);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int cidx = j * BT + c;
-                bool ok = row_ok && cidx < T;
+                for (int c = 0; c < 16; ++c) { g1[c] += t1[c]; g2[c] += t2[c]; }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars[C_GFREE]);
+            const uint32_t bad = (bits_ring[j & 7] >> (16 * h)) & 0xffffu;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
                 float l2 = row_lse2, dl = row_delta;
                 if (KS) {
-                    if (ok) {
-                        l2 = __ldg(lse + (int64_t)row_base + cidx) * LOG2E;
-                        dl = __ldg(delta + (int64_t)row_base + cidx);
-                    }
-                } else {
-                    if (ok && mrow && mrow[cidx]) ok = false;
+                    l2 = __shfl_sync(0xffffffffu, qstat, c);
+                    dl = __shfl_sync(0xffffffffu, qstat, 16 + c);
                 }
-                const float p = ok ? exp2f(g1[c] * (SM_SCALE * LOG2E) - l2) : 0.f;
+                const bool ok = row_ok && !((bad >> c) & 1u);
+                const float p = ok ? ex2_approx(fmaf(g1[c], SC2, -l2)) : 0.f;
                 g1[c] = p;
                 g2[c] = p * (g2[c] - dl) * SM_SCALE;
             }
-            if (j > 0) mbar_wait(&bars[C_PDFREE], (j - 1) & 1);     // previous accumulating MMAs are done with the P / dS tiles
+            uint32_t ph[8], pl[8], dh[8], dlw[8];
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                uint32_t ph[4], pl[4], dh[4], dlw[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(g1[kc * 8 + 2 * e], h0, l0);
-                    split_bf16(g1[kc * 8 + 2 * e + 1], h1, l1);
-                    ph[e] = pack2(h0, h1); pl[e] = pack2(l0, l1);
-                    split_bf16(g2[kc * 8 + 2 * e], h0, l0);
-                    split_bf16(g2[kc * 8 + 2 * e + 1], h1, l1);
-                    dh[e] = pack2(h0, h1); dlw[e] = pack2(l0, l1);
-                }
-                const uint32_t off = wr_off + kc * 128;
-                if (KS) {
-                    *reinterpret_cast<uint4*>(sPD + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                    *reinterpret_cast<uint4*>(sPD + PD_PLANE + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                }
-                *reinterpret_cast<uint4*>(sPD + 2 * PD_PLANE + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
-                *reinterpret_cast<uint4*>(sPD + 3 * PD_PLANE + off) = make_uint4(dlw[0], dlw[1], dlw[2], dlw[3]);
+            for (int c = 0; c < 8; ++c) {
+                split2(g1[2 * c], g1[2 * c + 1], ph[c], pl[c]);
+                split2(g2[2 * c], g2[2 * c + 1], dh[c], dlw[c]);
             }
-            fence_proxy_async();
+            if (j >= 2) mbar_wait(&bars[C_PDFREE + pb], ((j >> 1) - 1) & 1);     // the accumulating MMAs of tile j-2 are done with this buffer
+            tc_fence_after();
+            const uint32_t pd = lane_addr + TM_PD + pb * 64 + h * 8;
+            if (KS) {
+                tmem_st8(pd, ph);
+                tmem_st8(pd + 16, pl);
+            }
+            tmem_st8(pd + 32, dh);
+            tmem_st8(pd + 48, dlw);
+            tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars[C_PDFULL]);
+            mbar_arrive(&bars[C_PDFULL + pb]);
         }
         mbar_wait(&bars[C_DONE], 0);
         tc_fence_after();
         const bool store_ok = r_idx < T;
 #pragma unroll
         for (int g = (KS ? 0 : 1); g < 2; ++g) {
-            float* dst = (g == 0 ? out1 : out2) + ((int64_t)row_base + r_idx) * ld_d;
+            float* dst = (g == 0 ? out1 : out2) + ((int64_t)row_base + r_idx) * ld_d + h * 64;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 float t[32];
-                tmem_ld32(lane_addr + 128 + g * 128 + ch * 32, t);
+                tmem_ld32(lane_addr + (g == 0 ? TM_ACC1 : TM_ACC2) + h * 64 + ch * 32, t);
                 if (store_ok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
@@ -576,11 +640,10 @@ int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo
     DIP_TRY(make_tmap_bf16_2d(&lo64, qkv_lo, R, 3 * D, 3 * D, 64, 64));
     dim3 grid(cdiv(T, tcattn::BM), B);
     DIP_PROF(DIP_PROF_ATTN_FWD, stream);
-    tcattn::attn_fwd_tc_kernel<<<grid, 192, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T);
+    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T);
     DIP_LAUNCHED();
     return 0;
 }
-
 
 int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo, const void* do_hi, const void* do_lo,
                     const float* o, const float* d_o, const float* lse, const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T,
@@ -614,14 +677,14 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     dim3 grid(cdiv(T, 128), B);
     {
         DIP_PROF(DIP_PROF_ATTN_BWD_DKDV, stream);
-        tcattn::attn_bwd_tc_kernel<true><<<grid, 192, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32, d_lo32, dv, dk,
-                                                                              ld_d, lse, delta_ws, key_mask, mask_stride, T);
+        tcattn::attn_bwd_tc_kernel<true><<<grid, tcattn::NTHREADS, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32,
+                                                                                           d_lo32, dv, dk, ld_d, lse, delta_ws, key_mask, mask_stride, T);
         DIP_LAUNCHED();
     }
     {
         DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
-        tcattn::attn_bwd_tc_kernel<false><<<grid, 192, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32, d_lo32, nullptr,
-                                                                               dq, ld_d, lse, delta_ws, key_mask, mask_stride, T);
+        tcattn::attn_bwd_tc_kernel<false><<<grid, tcattn::NTHREADS, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32,
+                                                                                            d_lo32, nullptr, dq, ld_d, lse, delta_ws, key_mask, mask_stride, T);
         DIP_LAUNCHED();
     }
     return 0;

@@ -22,7 +22,7 @@ constexpr uint32_t A_STAGE = 2 * A_PLANE;           // hi + lo
 constexpr uint32_t OFF_W = 2 * A_STAGE;             // after the 2-stage A ring (128 KB)
 constexpr uint32_t W_BYTES = 98304;                 // up to 96 KB of weight planes
 constexpr uint32_t OFF_BAR = OFF_W + W_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
 
 enum { G_WFULL = 0, G_AFULL = 1, G_AEMPTY = 3, G_CFULL = 5, G_CEMPTY = 7 };
 
@@ -46,11 +46,53 @@ __device__ __forceinline__ float act_apply(float v, int act, float aux) {
     }
 }
 
+// one float4 of one output row through the whole epilogue (bias, addmat, residual, preact, activation, stores)
+__device__ __forceinline__ void emit4(const dip_gemm_args& g, int64_t row, int c, float (&x)[4]) {
+    int64_t out_row = row;
+    int t_in = 0;
+    if (g.rows_in > 0) {
+        const int64_t bb = row / g.rows_in;
+        t_in = (int)(row - bb * g.rows_in);
+        out_row = bb * g.rows_out + g.row_off + t_in;
+    }
+    if (g.bias) {
+        const float rbs = g.row_bias_scale ? g.row_bias_scale[row] : 1.0f;
+        const float4 bv = *reinterpret_cast<const float4*>(g.bias + c);
+        x[0] += bv.x * rbs; x[1] += bv.y * rbs; x[2] += bv.z * rbs; x[3] += bv.w * rbs;
+    }
+    if (g.addmat) {
+        const float4 am = *reinterpret_cast<const float4*>(g.addmat + (int64_t)t_in * g.N + c);
+        x[0] += am.x; x[1] += am.y; x[2] += am.z; x[3] += am.w;
+    }
+    if (g.res.batch) {
+        const float4 rr = *reinterpret_cast<const float4*>(row_ptr(g.res, out_row) + c);
+        x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+    }
+    if (g.preact) *reinterpret_cast<float4*>(g.preact + out_row * g.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (g.act != DIP_ACT_NONE) {
+        float4 ax = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.act == DIP_ACT_MUL_QUICKGELU_GRAD) ax = *reinterpret_cast<const float4*>(g.aux + out_row * g.ldc + c);
+        x[0] = act_apply(x[0], g.act, ax.x); x[1] = act_apply(x[1], g.act, ax.y);
+        x[2] = act_apply(x[2], g.act, ax.z); x[3] = act_apply(x[3], g.act, ax.w);
+    }
+    if (g.C) *reinterpret_cast<float4*>(g.C + out_row * g.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (g.split_hi) {
+        uint32_t h0, l0, h1, l1;
+        split2(x[0], x[1], h0, l0);
+        split2(x[2], x[3], h1, l1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_hi) + out_row * g.ldc + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_lo) + out_row * g.ldc + c) = make_uint2(l0, l1);
+    }
+}
+
+constexpr int STG_LD = 36;                          // staging row stride in floats (conflict-free float4 access)
+constexpr uint32_t STG_WARP = 32 * STG_LD * 4;      // per epilogue warp
+
 template <int KCH, int BN>
 __global__ void __launch_bounds__(288, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Params P) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t sm[];
+    if ((smem_u32(sm) & 1023u) != 0u) __trap();
     uint8_t* sW = sm + OFF_W;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -58,6 +100,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     constexpr uint32_t W_BLOCK = BN * 128;                 // one 64-column k-block of BN weight rows
     constexpr uint32_t W_PLANE = 2 * KCH * W_BLOCK;
     constexpr uint32_t IDESC = instr_desc(128, BN, 0, 0);
+    // K = 128: the weights take 64 KB of the 96 KB region; the rest stages the output tile for coalesced stores
+    constexpr bool STAGED = (2 * W_PLANE + 4 * STG_WARP <= W_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -94,31 +138,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 const int s = it & 1;
                 if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);
                 uint8_t* dst = sm + s * A_STAGE;
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int r = warp * 32 + rr;
-                    const int64_t row = (int64_t)tile * 128 + r;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < g.M) {
-                        const float* src = P.a_rows.batch ? row_ptr(P.a_rows, row) : g.A + row * (int64_t)g.lda + kc * 128;
-                        v = reinterpret_cast<const float4*>(src)[lane];
-                        if (ln) {
-                            const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);
-                            const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+#pragma unroll 1
+                for (int rr0 = 0; rr0 < 32; rr0 += 8) {
+                    float4 v[8];
+                    // 8 independent 512-byte row loads in flight per warp before any is consumed
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t row = (int64_t)tile * 128 + warp * 32 + rr0 + u;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < g.M) {
+                            const float* src = P.a_rows.batch ? row_ptr(P.a_rows, row) : g.A + row * (int64_t)g.lda + kc * 128;
+                            v[u] = reinterpret_cast<const float4*>(src)[lane];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = warp * 32 + rr0 + u;
+                        const int64_t row = (int64_t)tile * 128 + r;
+                        float4 x = v[u];
+                        if (ln && row < g.M) {
+                            const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.0f / D);
+                            const float dx = x.x - mu, dy = x.y - mu, dz = x.z - mu, dw = x.w - mu;
                             const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
                             float rs = rsqrtf(var + 1e-5f);
                             rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
-                            v = make_float4(dx * rs * gam.x + bet.x, dy * rs * gam.y + bet.y, dz * rs * gam.z + bet.z, dw * rs * gam.w + bet.w);
+                            x = make_float4(dx * rs * gam.x + bet.x, dy * rs * gam.y + bet.y, dz * rs * gam.z + bet.z, dw * rs * gam.w + bet.w);
                             if (P.ln_mean && blockIdx.y == 0 && lane == 0) {
                                 P.ln_mean[row] = mu;
                                 P.ln_rstd[row] = rs;
                             }
                         }
+                        uint32_t h0, l0, h1, l1;
+                        split2(x.x, x.y, h0, l0);
+                        split2(x.z, x.w, h1, l1);
+                        const uint32_t off = kb * 16384 + sw128_off(r, chunk) + half * 8;
+                        *reinterpret_cast<uint2*>(dst + off) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(dst + A_PLANE + off) = make_uint2(l0, l1);
                     }
-                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-                    const uint32_t off = kb * 16384 + sw128_off(r, chunk) + half * 8;
-                    *reinterpret_cast<uint2*>(dst + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
-                    *reinterpret_cast<uint2*>(dst + A_PLANE + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
                 }
                 fence_proxy_async();
                 mbar_arrive(&bars[G_AFULL + s]);
@@ -162,28 +218,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = row
-        const int ew = warp - 5;                     // TMEM lane quarter = warp % 4
+        // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp % 4
         const int q = warp & 3;
-        const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        (void)ew;
+        float* stg = reinterpret_cast<float*>(sW + 2 * W_PLANE + (warp - 5) * STG_WARP);
         int ti = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
             const int cb = ti & 1;
             mbar_wait(&bars[G_CFULL + cb], (ti >> 1) & 1);
             tc_fence_after();
-            const int64_t row = (int64_t)tile * 128 + r;
-            const bool row_ok = row < g.M;
-            int64_t out_row = row;
-            int t_in = 0;
-            if (g.rows_in > 0 && row_ok) {
-                const int64_t bb = row / g.rows_in;
-                t_in = (int)(row - bb * g.rows_in);
-                out_row = bb * g.rows_out + g.row_off + t_in;
-            }
-            const float rbs = (g.row_bias_scale && row_ok) ? g.row_bias_scale[row] : 1.0f;
-            const float* resp = (g.res.batch && row_ok) ? row_ptr(g.res, out_row) : nullptr;
+            const int64_t row0 = (int64_t)tile * 128 + q * 32;
 #pragma unroll
             for (int ch = 0; ch < BN / 32; ++ch) {
                 float v[32];
@@ -192,38 +236,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(&bars[G_CEMPTY + cb]);           // accumulator drained: the MMA warp may reuse it
                 }
-                if (!row_ok) continue;
                 const int c0 = n0 + ch * 32;
+                if (STAGED) {
+                    // transpose through shared memory: afterwards every warp instruction touches 8 rows x 128 contiguous bytes
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float x[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
-                    const int c = c0 + i;
-                    if (g.bias) {
-                        const float4 bv = *reinterpret_cast<const float4*>(g.bias + c);
-                        x[0] += bv.x * rbs; x[1] += bv.y * rbs; x[2] += bv.z * rbs; x[3] += bv.w * rbs;
-                    }
-                    if (g.addmat) {
-                        const float4 am = *reinterpret_cast<const float4*>(g.addmat + (int64_t)t_in * g.N + c);
-                        x[0] += am.x; x[1] += am.y; x[2] += am.z; x[3] += am.w;
-                    }
-                    if (resp) {
-                        const float4 rr = *reinterpret_cast<const float4*>(resp + c);
-                        x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-                    }
-                    if (g.preact) *reinterpret_cast<float4*>(g.preact + out_row * g.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
-                    if (g.act != DIP_ACT_NONE) {
-                        float4 ax = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (g.act == DIP_ACT_MUL_QUICKGELU_GRAD) ax = *reinterpret_cast<const float4*>(g.aux + out_row * g.ldc + c);
-                        x[0] = act_apply(x[0], g.act, ax.x); x[1] = act_apply(x[1], g.act, ax.y);
-                        x[2] = act_apply(x[2], g.act, ax.z); x[3] = act_apply(x[3], g.act, ax.w);
-                    }
-                    if (g.C) *reinterpret_cast<float4*>(g.C + out_row * g.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
-                    if (g.split_hi) {
-                        __nv_bfloat16 h[4], l[4];
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    __syncwarp();
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) split_bf16(x[e], h[e], l[e]);
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_hi) + out_row * g.ldc + c) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_lo) + out_row * g.ldc + c) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+                    for (int rr0 = 0; rr0 < 32; rr0 += 4) {
+                        const int rr = rr0 + (lane >> 3), cc = (lane & 7) * 4;
+                        const float4 t = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
+                        float x[4] = {t.x, t.y, t.z, t.w};
+                        if (row0 + rr < g.M) emit4(g, row0 + rr, c0 + cc, x);
+                    }
+                    __syncwarp();
+                } else {
+                    const int64_t row = row0 + lane;
+                    if (row < g.M) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float x[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+                            emit4(g, row, c0 + i, x);
+                        }
                     }
                 }
             }

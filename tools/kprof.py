@@ -15,3 +15,10 @@ for _ in range(3):
     dqkv = ops.attn_bwd_tc(hi, lo, o, d_o, lse, B, T, mask)
 torch.cuda.synchronize()
 print("ok", float(o.abs().mean()), float(dqkv.abs().mean()))
+# GEMMs: fp32 SIMT vs tcgen05 on the decoder-sized activation
+x = torch.randn(B * T, D, device=dev); W = torch.randn(D, D, device=dev) * 0.1; bias = torch.randn(D, device=dev)
+for _ in range(3):
+    a = ops.gemm_nt(x, W, bias)
+    c = ops.gemm_tc(x, W, bias)["C"]
+torch.cuda.synchronize()
+print("gemm ok", float((a - c).abs().max()))

@@ -1,0 +1,70 @@
+// Development micro-benchmark: cycles per tcgen05.mma for the shapes / operand layouts the kernels use.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I diffusion-integer-programming_b200/csrc tools/mma_bench.cu -o tools/mma_bench
+#include <cstdio>
+#include <cstdlib>
+#include "tc_common.cuh"
+namespace dip { void set_error(const char*, ...) {} std::atomic<uint64_t> g_launches{0}; int sm_count() { return 148; } }
+using namespace dip::tc;
+
+// mode 0: A K-major SW128, B K-major SW128 (N rows);  mode 1: B MN-major SW128;  mode 2: A un-swizzled K-major, B MN-major
+template <int N, int MODE>
+__global__ void __launch_bounds__(128, 1) bench(long long* out, int n_mma, int same_acc) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 196608 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm) + 65536;
+        const uint32_t idesc = dip::tc::instr_desc(128, N, 0, MODE >= 1 ? 1 : 0);
+        long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) {
+            const int ks = i & 3, kb = (i >> 2) & 1;
+            uint64_t da, db;
+            if (MODE == 2) { da = 0; da |= (uint64_t)(((a0 + (i & 1) * 256) & 0x3FFFF) >> 4); da |= (uint64_t)(128 >> 4) << 16; da |= (uint64_t)(512 >> 4) << 32; da |= (uint64_t)1 << 46; }
+            else da = smem_desc(a0 + kb * 16384 + ks * 32, 16, 1024);
+            if (MODE == 0) db = smem_desc(b0 + kb * (N * 128) + ks * 32, 16, 1024);
+            else db = smem_desc(b0 + (i & 1) * 2048, 8192, 1024);
+            tc_mma(tmem + (same_acc ? 0 : (i & 1) * N), da, db, idesc, i > 1);
+        }
+        long long t1 = clock64();
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int MODE>
+void run(const char* name, long long* d, int same_acc) {
+    cudaFuncSetAttribute(bench<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704);
+    const int n = 2048;
+    for (int grid : {1, 148}) {
+        bench<N, MODE><<<grid, 128, 200704>>>(d, n, same_acc);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[2];
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("%-34s N=%3d same_acc=%d grid=%3d : issue %.1f cyc/mma, complete %.1f cyc/mma (ideal %d) %s\n", name, N, same_acc, grid, (double)h[0] / n,
+               (double)h[1] / n, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
+}
+
+int main() {
+    long long* d; cudaMalloc(&d, 64);
+    run<32, 0>("K-major A x K-major B", d, 1);
+    run<64, 0>("K-major A x K-major B", d, 1);
+    run<64, 0>("K-major A x K-major B", d, 0);
+    run<128, 0>("K-major A x K-major B", d, 1);
+    run<256, 0>("K-major A x K-major B", d, 1);
+    run<128, 1>("K-major A x MN-major B", d, 1);
+    run<128, 1>("K-major A x MN-major B", d, 0);
+    run<128, 2>("nosw A x MN-major B", d, 1);
+    return 0;
+}

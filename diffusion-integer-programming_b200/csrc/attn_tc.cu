@@ -16,12 +16,14 @@
 //      written there by the row threads (tcgen05.st) and never touch shared memory; the space pays for a
 //      third pipeline stage.
 //
-// All kernels: 320 threads = 8 "row" warps + 1 producer warp + 1 MMA warp.
+// All kernels: 352 threads = 8 "row" warps + 1 producer warp + 2 MMA warps.
 //   warps 0-7 : two warps per TMEM lane quarter; thread (row r, half h) owns row r of the 128-row tile
 //               and half of its columns.
 //   warp 8    : TMA producer; its 32 lanes also ballot the key-padding mask of every streamed tile into a
 //               bit word, so the row warps never touch global memory inside the loop.
-//   warp 9    : one thread issues tcgen05.mma / tcgen05.commit.
+//   warps 9,10: one thread each issues tcgen05.mma / tcgen05.commit -- warp 9 the score GEMMs, warp 10 the
+//               accumulating GEMMs.  Issue is throttled to the tensor pipe's rate and every mbarrier wait costs
+//               ~250 cycles (measured, tools/ktrace.py); two issuers hide each other's waits.
 #include <math.h>
 #include "tc_common.cuh"
 
@@ -34,8 +36,23 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float SM_SCALE = 0.08838834764831845f;
 constexpr float SC2 = SM_SCALE * LOG2E;         // scores are exponentiated in base 2
-constexpr int NTHREADS = 320, ROW_THREADS = 256, W_PRODUCER = 8, W_MMA = 9;
+constexpr int NTHREADS = 352, ROW_THREADS = 256, W_PRODUCER = 8, W_MMA = 9, W_MMA2 = 10;
 constexpr uint32_t SMEM_LIMIT = 232448;
+
+#ifdef DIP_TRACE
+// Development aid (compile with -DDIP_TRACE): CTA (0,0) logs (event << 48 | tile << 32 | SM clock low bits) from its
+// producer lane, MMA lane and row thread 0 into three regions of a global buffer; plain stores, no atomics.
+__device__ unsigned long long* g_trace = nullptr;
+struct Tracer {
+    unsigned long long* p; int n;
+    __device__ Tracer(int region) : p(nullptr), n(0) { if (g_trace && blockIdx.x == 0 && blockIdx.y == 0 && region >= 0) p = g_trace + region * 16384; }
+    __device__ __forceinline__ void ev(int e, int tile) { if (p && n < 16384) p[n++] = ((unsigned long long)e << 48) | ((unsigned long long)tile << 32) | (unsigned long long)(unsigned int)clock64(); }
+};
+#define TR(e, t) tracer.ev((e), (t))
+#else
+struct Tracer { __device__ Tracer(int) {} };
+#define TR(e, t)
+#endif
 
 __device__ __forceinline__ void require_aligned_smem(const void* p) {
     if ((smem_u32(p) & 1023u) != 0u) {
@@ -65,7 +82,7 @@ constexpr uint32_t IDESC_S = instr_desc(128, 128, 0, 0);    // Q (K-major) x [K_
 constexpr uint32_t IDESC_PV = instr_desc(128, 128, 0, 1);   // P (tensor memory) x V (MN-major) -> 128 x 128
 constexpr float RESCALE_THRESHOLD = 8.0f;                   // log2 units: P stays below 2^8 between rescales
 
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17, B_PVFREE = 18 };
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_constant__ CUtensorMap tm_lo128,
@@ -85,6 +102,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     const int b = blockIdx.y, q0 = blockIdx.x * BM;
     const int row_base = b * T;
     const int n_tiles = (T + BN - 1) / BN;
+    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : -1);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[B_QFULL], 1);
@@ -97,7 +115,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             mbar_init(&bars[B_PFULL + s], ROW_THREADS);
         }
         mbar_init(&bars[B_PVFULL], 1);
-        mbar_init(&bars[B_PVFREE], ROW_THREADS);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -152,15 +169,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             }
             __syncwarp();
         }
-    } else if (warp == W_MMA) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
+    } else if (warp == W_MMA || warp == W_MMA2) {
+        // ------------------------------------------------------------------ MMA issuers (one thread each)
         if (lane == 0) {
             const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-            mbar_wait(&bars[B_QFULL], 0);
+            if (warp == W_MMA) mbar_wait(&bars[B_QFULL], 0);
             auto issue_S = [&](int j) {
                 const int s = j % K_STAGES, sb = j & 1;
+                TR(20, j);
                 mbar_wait(&bars[B_KFULL + s], (j / K_STAGES) & 1);
+                TR(21, j);
                 if (j >= 2) mbar_wait(&bars[B_SFREE + sb], ((j >> 1) - 1) & 1);
+                TR(22, j);
                 tc_fence_after();
                 const uint32_t kbase = aK + s * K_STAGE;
                 uint32_t acc = 0;
@@ -176,12 +196,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                         }
                 tc_commit(&bars[B_SFULL + sb]);
                 tc_commit(&bars[B_KEMPTY + s]);
+                TR(23, j);
             };
             auto issue_PV = [&](int j) {
                 const int s = j & 1;
+                TR(24, j);
                 mbar_wait(&bars[B_VFULL + s], (j >> 1) & 1);
-                mbar_wait(&bars[B_PFULL + s], (j >> 1) & 1);
-                if (j > 0) mbar_wait(&bars[B_PVFREE], (j - 1) & 1);          // the row warps have folded the previous P.V tile
+                TR(25, j);
+                mbar_wait(&bars[B_PFULL + s], (j >> 1) & 1);       // P_j stored AND the previous P.V tile folded by the row warps
+                TR(26, j);
                 tc_fence_after();
                 const uint32_t vbase = aV + s * V_STAGE;
                 const uint32_t pbase = tmem + TM_P + s * 64;
@@ -199,11 +222,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 }
                 tc_commit(&bars[B_PVFULL]);
                 tc_commit(&bars[B_VEMPTY + s]);
+                TR(28, j);
             };
-            issue_S(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_S(j + 1);
-                issue_PV(j);
+            if (warp == W_MMA) {
+                for (int j = 0; j < n_tiles; ++j) issue_S(j);
+            } else {
+                for (int j = 0; j < n_tiles; ++j) issue_PV(j);
             }
         }
     } else {
@@ -217,7 +241,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
         float m_used = -INFINITY, l_part = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
+            TR(30, j);
             mbar_wait(&bars[B_SFULL + s], (j >> 1) & 1);
+            TR(31, j);
             tc_fence_after();
             float sv[32];
             {
@@ -229,6 +255,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             }
             tc_fence_before();
             mbar_arrive(&bars[B_SFREE + s]);
+            TR(32, j);
             const uint32_t mb = (uint32_t)(bits_ring[j & 7] >> (32 * h));
             float mx = -INFINITY;
             if (mb == 0u) {
@@ -244,6 +271,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             // the two key halves of a row agree on the tile maximum through shared memory
             xm[(s * 2 + h) * 128 + row] = mx;
             named_bar_sync(1, ROW_THREADS);
+            TR(33, j);
             const float m_tile = fmaxf(mx, xm[(s * 2 + (h ^ 1)) * 128 + row]) * SC2;
             // lazy rescaling: the exponent base only moves when the row maximum grew by more than 2^8
             const bool need = m_tile > m_used + RESCALE_THRESHOLD;
@@ -264,13 +292,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             m_used = m_new;
             // P_j -> tensor memory (A operand of P.V): this half's 32 keys = 16 packed columns per plane.
             // Buffer s was last read by P_{j-2}.V_{j-2}, whose completion this thread observed one iteration ago.
+            TR(34, j);
             tmem_st16(lane_addr + TM_P + s * 64 + h * 16, phi);
             tmem_st16(lane_addr + TM_P + s * 64 + 32 + h * 16, plo);
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[B_PFULL + s]);
+            TR(35, j);
             if (j > 0) {
                 mbar_wait(&bars[B_PVFULL], (j - 1) & 1);
+                TR(36, j);
                 tc_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
@@ -284,9 +313,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                         for (int i = 0; i < 32; ++i) oacc[ch * 32 + i] += t[i];
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&bars[B_PVFREE]);
+                TR(37, j);
             }
+            // one arrival publishes both facts the accumulate issuer needs: P_j is in tensor memory and the P.V tile is free again
+            tc_fence_before();
+            mbar_arrive(&bars[B_PFULL + s]);
         }
         mbar_wait(&bars[B_PVFULL], (n_tiles - 1) & 1);
         tc_fence_after();
@@ -421,10 +452,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             }
             __syncwarp();
         }
-    } else if (warp == W_MMA) {
+    } else if (warp == W_MMA || warp == W_MMA2) {
         if (lane == 0) {
             const uint32_t aX = smem_u32(sm + BOFF_X), aY = smem_u32(sm + BOFF_Y), aTL = smem_u32(sm + BOFF_TL);
-            mbar_wait(&bars[C_XFULL], 0);
+            if (warp == W_MMA) mbar_wait(&bars[C_XFULL], 0);
             auto issue_G = [&](int j) {
                 const int s = j % TL_STAGES;
                 mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);
@@ -451,6 +482,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             };
             auto issue_acc = [&](int j) {
                 const int s = j % TL_STAGES, pb = j & 1;
+                mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);     // this issuer observes the TMA completion itself
                 mbar_wait(&bars[C_PDFULL + pb], (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t tl = aTL + s * TL_STAGE;
@@ -474,12 +506,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 tc_commit(&bars[C_PDFREE + pb]);
                 tc_commit(&bars[C_TLEMPTY + s]);
             };
-            issue_G(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_G(j + 1);
-                issue_acc(j);
+            if (warp == W_MMA) {
+                for (int j = 0; j < n_tiles; ++j) issue_G(j);
+            } else {
+                for (int j = 0; j < n_tiles; ++j) issue_acc(j);
+                tc_commit(&bars[C_DONE]);
             }
-            tc_commit(&bars[C_DONE]);
         }
     } else {
         // ------------------------------------------------------------------ row warps: thread = (stationary row, 16 of the 32 tile columns)
@@ -644,6 +676,13 @@ int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo
     DIP_LAUNCHED();
     return 0;
 }
+
+#ifdef DIP_TRACE
+int dip_debug_set_trace(unsigned long long* device_buffer) {
+    DIP_CUDA(cudaMemcpyToSymbol(tcattn::g_trace, &device_buffer, sizeof(device_buffer)));
+    return 0;
+}
+#endif
 
 int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo, const void* do_hi, const void* do_lo,
                     const float* o, const float* d_o, const float* lse, const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T,

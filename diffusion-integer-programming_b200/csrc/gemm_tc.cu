@@ -3,13 +3,20 @@
 // into the operand load (every CTA tile holds complete 128-feature rows, so the statistics are
 // row-local).  These GEMMs have only 32 FLOP per HBM byte: the kernel is built to stream --
 // persistent CTAs, warp-specialised:
-//   warps 0-3  loaders : coalesced fp32 row loads (one warp per row, float4 per lane), optional LN by warp
-//                        shuffles, split into bf16 hi/lo, swizzled K-major stores into a 2-stage ring
+//   warps 0-3  loaders : coalesced fp32 row loads (one warp per row, float4 per lane, 8 rows in flight per
+//                        warp), optional LN by warp shuffles, split into bf16 hi/lo, swizzled K-major stores
+//                        into a 2-stage ring
 //   warp  4    MMA     : one thread issues 3 passes x K/16 tcgen05.mma per stage into a double-buffered
 //                        TMEM accumulator; weights (bf16 hi/lo planes, TMA, SWIZZLE_128B) stay resident
-//   warps 5-8  epilogue: thread = row; TMEM -> registers -> bias / residual / activation -> global
+//   warps 5-8  epilogue: TMEM -> registers -> (K = 128: transposed through shared memory so that every
+//                        global access is 4 rows x 128 contiguous bytes) -> bias / residual / activation -> global
 //                        (fp32 and/or bf16 hi/lo planes for the attention kernels)
+// The kernel body is written branch-free on purpose: an earlier version skipped unused epilogue features with
+// branches over large blocks in a ~100 KB kernel and spent most of its time in instruction fetch (measured:
+// ~2000 cycles for ~300 executed instructions).  Here unused operands read a zero block with stride 0, unused
+// outputs are predicated stores, and only the activation is skipped as one small uniform block.
 // Supported shapes: K = 128 (BN = 128 columns per CTA column-block) and K = 384 (BN = 64), N % BN == 0.
+#include <string.h>
 #include "tc_common.cuh"
 
 namespace dip {
@@ -20,75 +27,82 @@ using namespace tc;
 constexpr uint32_t A_PLANE = 32768;                 // [2 kb][128 rows][64] bf16
 constexpr uint32_t A_STAGE = 2 * A_PLANE;           // hi + lo
 constexpr uint32_t OFF_W = 2 * A_STAGE;             // after the 2-stage A ring (128 KB)
-constexpr uint32_t W_BYTES = 98304;                 // up to 96 KB of weight planes
+constexpr uint32_t W_BYTES = 98304;                 // up to 96 KB of weight planes (K = 128: 64 KB + output staging)
 constexpr uint32_t OFF_BAR = OFF_W + W_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
+constexpr int STG_LD = 36;                          // staging row stride in floats (conflict-free float4 access)
+constexpr uint32_t STG_WARP = 32 * STG_LD * 4;      // per epilogue warp
+constexpr uint32_t BIG = 1u << 30;
 
 enum { G_WFULL = 0, G_AFULL = 1, G_AEMPTY = 3, G_CFULL = 5, G_CEMPTY = 7 };
 
+__device__ float g_zeros[4 * 128];                  // what absent operands read (stride 0)
+
+// Every optional feature is expressed as data: absent inputs point at g_zeros with stride 0, absent outputs are null.
 struct Params {
-    dip_gemm_args g;
-    dip_rows a_rows;          // A source (two-source rows allowed when K == 128); a_rows.batch == NULL -> g.A / g.lda
-    const float* ln_gamma;    // LayerNorm prologue (K == 128 only), NULL = off
-    const float* ln_beta;
-    float* ln_mean;           // optional statistics output (written by column-block 0)
-    float* ln_rstd;
-    int n_tiles;
+    int M, N, n_tiles, act;
+    // A: K = 128 -> row r = (b, t) with b = r / a_T, t = r % a_T: t < a_split ? a_shared + t*128 : a_batch + (b*(a_T-a_split) + t-a_split)*128
+    //    K = 384 -> a_batch + r*lda + kc*128
+    const float *a_shared, *a_batch;
+    uint32_t a_T, a_split;
+    int lda;
+    const float *ln_gamma, *ln_beta;
+    float *ln_mean, *ln_rstd;
+    // epilogue
+    uint32_t rows_in, rows_out, row_off;            // output row = (r / rows_in) * rows_out + row_off + r % rows_in
+    const float* bias;                              // N entries (or zeros)
+    const float* row_bias_scale;                    // M entries or null (-> 1)
+    const float* addmat; uint32_t add_ld;           // row t_in, stride add_ld (0 when absent)
+    const float *res_shared, *res_batch; uint32_t res_T, res_split, res_mul;   // residual rows like A; res_mul = 0 when absent
+    const float* aux; uint32_t aux_ld;              // operand of the QuickGELU-gradient epilogue (stride 0 when absent)
+    float *C, *preact; void *split_hi, *split_lo;
+    int ldc;
 };
 
-__device__ __forceinline__ float act_apply(float v, int act, float aux) {
-    switch (act) {
-        case DIP_ACT_QUICKGELU: return quick_gelu(v);
-        case DIP_ACT_RELU: return fmaxf(v, 0.f);
-        case DIP_ACT_SIGMOID: return sigmoidf_(v);
-        case DIP_ACT_MUL_QUICKGELU_GRAD: return v * quick_gelu_grad(aux);
-        default: return v;
-    }
+__device__ __forceinline__ const float* src_row(const float* shared, const float* batch, uint32_t T, uint32_t split, uint32_t r) {
+    const uint32_t b = r / T, t = r - b * T;
+    const bool sh = t < split;
+    const float* base = sh ? shared : batch;
+    const uint32_t idx = sh ? t : b * (T - split) + (t - split);
+    return base + (size_t)idx * D;
 }
 
-// one float4 of one output row through the whole epilogue (bias, addmat, residual, preact, activation, stores)
-__device__ __forceinline__ void emit4(const dip_gemm_args& g, int64_t row, int c, float (&x)[4]) {
-    int64_t out_row = row;
-    int t_in = 0;
-    if (g.rows_in > 0) {
-        const int64_t bb = row / g.rows_in;
-        t_in = (int)(row - bb * g.rows_in);
-        out_row = bb * g.rows_out + g.row_off + t_in;
+// sigmoid by MUFU.EX2 + MUFU.RCP: the slow paths of expf / IEEE division would triple the epilogue's size
+__device__ __forceinline__ float fast_sigmoid(float z) { return __frcp_rn(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+__device__ __forceinline__ float act_apply(float v, int act, float aux) {
+    const float z = act == DIP_ACT_MUL_QUICKGELU_GRAD ? aux : v;
+    const float sg = fast_sigmoid((act == DIP_ACT_SIGMOID ? 1.0f : 1.702f) * z);
+    const float gelu = v * sg, grad = v * (sg + 1.702f * z * sg * (1.0f - sg));
+    return act == DIP_ACT_RELU ? fmaxf(v, 0.f) : act == DIP_ACT_QUICKGELU ? gelu : act == DIP_ACT_SIGMOID ? sg : grad;
+}
+
+// the whole epilogue of one float4 of output row `row`, columns c..c+3 (a4 = accumulator)
+__device__ __forceinline__ void epilogue4(const Params& P, uint32_t row, int c, float4 a4) {
+    const uint32_t b = row / P.rows_in, t_in = row - b * P.rows_in;
+    const size_t out_row = (size_t)b * P.rows_out + P.row_off + t_in;
+    float rbs = 1.0f;
+    if (P.row_bias_scale) rbs = P.row_bias_scale[row];
+    const float4 bv = *reinterpret_cast<const float4*>(P.bias + c);
+    const float4 am = *reinterpret_cast<const float4*>(P.addmat + (size_t)t_in * P.add_ld + c);
+    const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, (uint32_t)out_row * P.res_mul) + c);
+    const float4 ax = *reinterpret_cast<const float4*>(P.aux + out_row * P.aux_ld + c);
+    float x[4] = {a4.x + bv.x * rbs + am.x + rv.x, a4.y + bv.y * rbs + am.y + rv.y, a4.z + bv.z * rbs + am.z + rv.z, a4.w + bv.w * rbs + am.w + rv.w};
+    if (P.preact) *reinterpret_cast<float4*>(P.preact + out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (P.act != DIP_ACT_NONE) {
+        x[0] = act_apply(x[0], P.act, ax.x); x[1] = act_apply(x[1], P.act, ax.y);
+        x[2] = act_apply(x[2], P.act, ax.z); x[3] = act_apply(x[3], P.act, ax.w);
     }
-    if (g.bias) {
-        const float rbs = g.row_bias_scale ? g.row_bias_scale[row] : 1.0f;
-        const float4 bv = *reinterpret_cast<const float4*>(g.bias + c);
-        x[0] += bv.x * rbs; x[1] += bv.y * rbs; x[2] += bv.z * rbs; x[3] += bv.w * rbs;
-    }
-    if (g.addmat) {
-        const float4 am = *reinterpret_cast<const float4*>(g.addmat + (int64_t)t_in * g.N + c);
-        x[0] += am.x; x[1] += am.y; x[2] += am.z; x[3] += am.w;
-    }
-    if (g.res.batch) {
-        const float4 rr = *reinterpret_cast<const float4*>(row_ptr(g.res, out_row) + c);
-        x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-    }
-    if (g.preact) *reinterpret_cast<float4*>(g.preact + out_row * g.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
-    if (g.act != DIP_ACT_NONE) {
-        float4 ax = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.act == DIP_ACT_MUL_QUICKGELU_GRAD) ax = *reinterpret_cast<const float4*>(g.aux + out_row * g.ldc + c);
-        x[0] = act_apply(x[0], g.act, ax.x); x[1] = act_apply(x[1], g.act, ax.y);
-        x[2] = act_apply(x[2], g.act, ax.z); x[3] = act_apply(x[3], g.act, ax.w);
-    }
-    if (g.C) *reinterpret_cast<float4*>(g.C + out_row * g.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
-    if (g.split_hi) {
+    if (P.C) *reinterpret_cast<float4*>(P.C + out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (P.split_hi) {
         uint32_t h0, l0, h1, l1;
         split2(x[0], x[1], h0, l0);
         split2(x[2], x[3], h1, l1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_hi) + out_row * g.ldc + c) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.split_lo) + out_row * g.ldc + c) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_hi) + out_row * P.ldc + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_lo) + out_row * P.ldc + c) = make_uint2(l0, l1);
     }
 }
 
-constexpr int STG_LD = 36;                          // staging row stride in floats (conflict-free float4 access)
-constexpr uint32_t STG_WARP = 32 * STG_LD * 4;      // per epilogue warp
-
-template <int KCH, int BN>
+template <int KCH, int BN, bool LN>
 __global__ void __launch_bounds__(288, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Params P) {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -96,11 +110,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     uint8_t* sW = sm + OFF_W;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    const dip_gemm_args& g = P.g;
     constexpr uint32_t W_BLOCK = BN * 128;                 // one 64-column k-block of BN weight rows
     constexpr uint32_t W_PLANE = 2 * KCH * W_BLOCK;
     constexpr uint32_t IDESC = instr_desc(128, BN, 0, 0);
-    // K = 128: the weights take 64 KB of the 96 KB region; the rest stages the output tile for coalesced stores
     constexpr bool STAGED = (2 * W_PLANE + 4 * STG_WARP <= W_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,45 +137,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (warp < 4) {
         // ------------------------------------------------------------------ loaders
         float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool ln = P.ln_gamma != nullptr;
-        if (ln) {
+        if (LN) {
             gam = reinterpret_cast<const float4*>(P.ln_gamma)[lane];
             bet = reinterpret_cast<const float4*>(P.ln_beta)[lane];
         }
         // lane l holds columns 4l..4l+3 of its row: k-block l/16, 16-byte chunk (l%16)/2, half l%2
-        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;
+        const uint32_t lane_off = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
+        const int chunk = (lane & 15) >> 1;
+        const bool stats = LN && P.ln_mean != nullptr && blockIdx.y == 0 && lane == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+#pragma unroll 1
             for (int kc = 0; kc < KCH; ++kc, ++it) {
                 const int s = it & 1;
                 if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);
-                uint8_t* dst = sm + s * A_STAGE;
+                uint8_t* dst = sm + s * A_STAGE + lane_off;
 #pragma unroll 1
                 for (int rr0 = 0; rr0 < 32; rr0 += 8) {
                     float4 v[8];
-                    // 8 independent 512-byte row loads in flight per warp before any is consumed
+                    // 8 independent 512-byte row loads in flight per warp before any is consumed; rows past M re-read row M-1
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int64_t row = (int64_t)tile * 128 + warp * 32 + rr0 + u;
-                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row < g.M) {
-                            const float* src = P.a_rows.batch ? row_ptr(P.a_rows, row) : g.A + row * (int64_t)g.lda + kc * 128;
-                            v[u] = reinterpret_cast<const float4*>(src)[lane];
-                        }
+                        const uint32_t row = min((uint32_t)tile * 128u + warp * 32 + rr0 + u, (uint32_t)P.M - 1u);
+                        const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
+                        v[u] = reinterpret_cast<const float4*>(src)[lane];
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int r = warp * 32 + rr0 + u;
-                        const int64_t row = (int64_t)tile * 128 + r;
+                        const uint32_t row = (uint32_t)tile * 128u + r;
                         float4 x = v[u];
-                        if (ln && row < g.M) {
+                        if (LN) {
                             const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.0f / D);
                             const float dx = x.x - mu, dy = x.y - mu, dz = x.z - mu, dw = x.w - mu;
                             const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
                             float rs = rsqrtf(var + 1e-5f);
                             rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
                             x = make_float4(dx * rs * gam.x + bet.x, dy * rs * gam.y + bet.y, dz * rs * gam.z + bet.z, dw * rs * gam.w + bet.w);
-                            if (P.ln_mean && blockIdx.y == 0 && lane == 0) {
+                            if (stats && row < (uint32_t)P.M) {
                                 P.ln_mean[row] = mu;
                                 P.ln_rstd[row] = rs;
                             }
@@ -171,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                         uint32_t h0, l0, h1, l1;
                         split2(x.x, x.y, h0, l0);
                         split2(x.z, x.w, h1, l1);
-                        const uint32_t off = kb * 16384 + sw128_off(r, chunk) + half * 8;
+                        const uint32_t off = sw128_off(r, chunk);
                         *reinterpret_cast<uint2*>(dst + off) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2*>(dst + A_PLANE + off) = make_uint2(l0, l1);
                     }
@@ -195,6 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 const int cb = ti & 1;
                 if (ti >= 2) mbar_wait(&bars[G_CEMPTY + cb], ((ti >> 1) - 1) & 1);
                 uint32_t acc = 0;
+#pragma unroll 1
                 for (int kc = 0; kc < KCH; ++kc, ++it) {
                     const int s = it & 1;
                     mbar_wait(&bars[G_AFULL + s], (it >> 1) & 1);
@@ -227,8 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             const int cb = ti & 1;
             mbar_wait(&bars[G_CFULL + cb], (ti >> 1) & 1);
             tc_fence_after();
-            const int64_t row0 = (int64_t)tile * 128 + q * 32;
-#pragma unroll
+            const uint32_t row0 = (uint32_t)tile * 128u + q * 32;
+#pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 float v[32];
                 tmem_ld32(lane_addr + cb * BN + ch * 32, v);
@@ -238,26 +250,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 }
                 const int c0 = n0 + ch * 32;
                 if (STAGED) {
-                    // transpose through shared memory: afterwards every warp instruction touches 8 rows x 128 contiguous bytes
+                    // transpose through shared memory: afterwards every warp instruction touches 4 rows x 128 contiguous bytes
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     __syncwarp();
-#pragma unroll
-                    for (int rr0 = 0; rr0 < 32; rr0 += 4) {
-                        const int rr = rr0 + (lane >> 3), cc = (lane & 7) * 4;
-                        const float4 t = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
-                        float x[4] = {t.x, t.y, t.z, t.w};
-                        if (row0 + rr < g.M) emit4(g, row0 + rr, c0 + cc, x);
+                    const int cc = (lane & 7) * 4;
+#pragma unroll 2
+                    for (int u = 0; u < 8; ++u) {
+                        const int rr = u * 4 + (lane >> 3);
+                        const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
+                        if (row0 + rr < (uint32_t)P.M) epilogue4(P, row0 + rr, c0 + cc, a4);
                     }
                     __syncwarp();
                 } else {
-                    const int64_t row = row0 + lane;
-                    if (row < g.M) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float x[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
-                            emit4(g, row, c0 + i, x);
-                        }
+                    if (row0 + lane < (uint32_t)P.M) {
+#pragma unroll 2
+                        for (int i = 0; i < 32; i += 4) epilogue4(P, row0 + lane, c0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
                     }
                 }
             }
@@ -268,18 +276,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (warp == 4) tmem_dealloc(tmem, 2 * BN);
 }
 
-template <int KCH, int BN>
+template <int KCH, int BN, bool LN>
 static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const Params& P, int n_blocks_y, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        DIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<KCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<KCH, BN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr = true;
     }
     int gx = sm_count() / n_blocks_y;
     if (gx < 1) gx = 1;
     if (gx > P.n_tiles) gx = P.n_tiles;
     dim3 grid(gx, n_blocks_y);
-    gemm_tc_kernel<KCH, BN><<<grid, 288, SMEM_BYTES, st>>>(whi, wlo, P);
+    gemm_tc_kernel<KCH, BN, LN><<<grid, 288, SMEM_BYTES, st>>>(whi, wlo, P);
     return 0;
 }
 
@@ -294,7 +302,8 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
                 const float* ln_beta, float* ln_mean, float* ln_rstd, dip_stream_t stream) {
     DIP_REQUIRE(args && w_hi && w_lo, "dip_gemm_tc: null argument");
     const dip_gemm_args& g = *args;
-    DIP_REQUIRE((g.A || (a_rows && a_rows->batch)) && (g.C || g.split_hi || g.preact), "dip_gemm_tc: no input / no output");
+    const bool rows_a = a_rows && a_rows->batch;
+    DIP_REQUIRE((g.A || rows_a) && (g.C || g.split_hi || g.preact), "dip_gemm_tc: no input / no output");
     DIP_REQUIRE(g.M > 0 && (g.K == 128 || g.K == 384), "dip_gemm_tc: K must be 128 or 384 (K=%d)", g.K);
     const int BN = g.K == 128 ? 128 : 64;
     DIP_REQUIRE(g.N % BN == 0, "dip_gemm_tc: N must be a multiple of %d (N=%d)", BN, g.N);
@@ -302,21 +311,50 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     DIP_REQUIRE(g.res.batch == nullptr || g.N == D, "dip_gemm_tc: residual needs N == 128");
     DIP_REQUIRE(g.act != DIP_ACT_MUL_QUICKGELU_GRAD || g.aux, "dip_gemm_tc: aux missing");
     DIP_REQUIRE((g.split_hi == nullptr) == (g.split_lo == nullptr), "dip_gemm_tc: split_hi and split_lo go together");
-    DIP_REQUIRE(!(a_rows && a_rows->batch) || g.K == 128, "dip_gemm_tc: row sources need K == 128");
+    DIP_REQUIRE(!rows_a || g.K == 128, "dip_gemm_tc: row sources need K == 128");
+    DIP_REQUIRE(g.K == 384 || rows_a || g.lda == 128, "dip_gemm_tc: K == 128 needs contiguous rows (lda == 128) or a row source");
     DIP_REQUIRE(ln_gamma == nullptr || (g.K == 128 && ln_beta), "dip_gemm_tc: LayerNorm prologue needs K == 128 and beta");
     DIP_REQUIRE((ln_mean == nullptr) == (ln_rstd == nullptr), "dip_gemm_tc: mean and rstd go together");
+    DIP_REQUIRE(g.rows_in == 0 || (g.rows_out >= g.rows_in + g.row_off), "dip_gemm_tc: bad row remap");
+    DIP_REQUIRE(g.bias || g.N <= 4 * 128, "dip_gemm_tc: N too large for the zero block");
+    float* zeros = nullptr;
+    DIP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&zeros), tcgemm::g_zeros));
     tcgemm::Params P;
-    P.g = g;
-    if (a_rows && a_rows->batch) P.a_rows = *a_rows;
-    else { P.a_rows.shared = nullptr; P.a_rows.batch = nullptr; P.a_rows.T = 0; P.a_rows.split = 0; }
+    memset(&P, 0, sizeof(P));
+    P.M = g.M; P.N = g.N; P.n_tiles = cdiv(g.M, 128); P.act = g.act;
+    if (rows_a) {
+        P.a_shared = a_rows->shared ? a_rows->shared : a_rows->batch; P.a_batch = a_rows->batch;
+        P.a_split = (uint32_t)a_rows->split;
+        P.a_T = a_rows->split > 0 ? (uint32_t)a_rows->T : tcgemm::BIG;
+    } else {
+        P.a_shared = g.A; P.a_batch = g.A; P.a_T = tcgemm::BIG; P.a_split = 0;
+    }
+    P.lda = g.lda;
     P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.ln_mean = ln_mean; P.ln_rstd = ln_rstd;
-    P.n_tiles = cdiv(g.M, 128);
+    if (g.rows_in > 0) { P.rows_in = (uint32_t)g.rows_in; P.rows_out = (uint32_t)g.rows_out; P.row_off = (uint32_t)g.row_off; }
+    else { P.rows_in = tcgemm::BIG; P.rows_out = 0; P.row_off = 0; }
+    P.bias = g.bias ? g.bias : zeros;
+    P.row_bias_scale = g.row_bias_scale;
+    P.addmat = g.addmat ? g.addmat : zeros; P.add_ld = g.addmat ? (uint32_t)g.N : 0u;
+    if (g.res.batch) {
+        P.res_shared = g.res.shared ? g.res.shared : g.res.batch; P.res_batch = g.res.batch;
+        P.res_split = (uint32_t)g.res.split; P.res_T = g.res.split > 0 ? (uint32_t)g.res.T : tcgemm::BIG; P.res_mul = 1;
+    } else {
+        P.res_shared = zeros; P.res_batch = zeros; P.res_split = 0; P.res_T = tcgemm::BIG; P.res_mul = 0;
+    }
+    P.aux = g.aux ? g.aux : zeros; P.aux_ld = g.aux ? (uint32_t)g.ldc : 0u;
+    P.C = g.C; P.preact = g.preact; P.split_hi = g.split_hi; P.split_lo = g.split_lo; P.ldc = g.ldc;
     CUtensorMap whi, wlo;
     DIP_TRY(make_tmap_bf16_2d(&whi, w_hi, g.N, g.K, g.K, BN, 64));
     DIP_TRY(make_tmap_bf16_2d(&wlo, w_lo, g.N, g.K, g.K, BN, 64));
     DIP_PROF(DIP_PROF_GEMM, stream);
-    if (g.K == 128) DIP_TRY((tcgemm::launch<1, 128>(whi, wlo, P, g.N / 128, as_stream(stream))));
-    else DIP_TRY((tcgemm::launch<3, 64>(whi, wlo, P, g.N / 64, as_stream(stream))));
+    cudaStream_t st = as_stream(stream);
+    if (g.K == 128) {
+        if (ln_gamma) DIP_TRY((tcgemm::launch<1, 128, true>(whi, wlo, P, g.N / 128, st)));
+        else DIP_TRY((tcgemm::launch<1, 128, false>(whi, wlo, P, g.N / 128, st)));
+    } else {
+        DIP_TRY((tcgemm::launch<3, 64, false>(whi, wlo, P, g.N / 64, st)));
+    }
     DIP_LAUNCHED();
     return 0;
 }

@@ -27,9 +27,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+// Bounded spin: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.  The report lives in
+// a non-inlined function so that the many inlined wait loops stay a handful of instructions each.
+static __device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+    printf("dip: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, addr, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar), done = 0;
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -38,10 +44,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && spin > (1u << 24)) {
-            printf("dip: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, addr, parity);
-            __trap();
-        }
+        if (!done && spin > (1u << 24)) mbar_timeout(addr, parity);
     }
 }
 

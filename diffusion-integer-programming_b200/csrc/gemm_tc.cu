@@ -3,12 +3,12 @@
 // into the operand load (every CTA tile holds complete 128-feature rows, so the statistics are
 // row-local).  These GEMMs have only 32 FLOP per HBM byte: the kernel is built to stream --
 // persistent CTAs, warp-specialised:
-//   warps 0-3  loaders : coalesced fp32 row loads (one warp per row, float4 per lane, 8 rows in flight per
+//   warps 0-7  loaders : coalesced fp32 row loads (one warp per row, float4 per lane, 16 rows = 8 KB in flight per
 //                        warp), optional LN by warp shuffles, split into bf16 hi/lo, swizzled K-major stores
 //                        into a 2-stage ring
-//   warp  4    MMA     : one thread issues 3 passes x K/16 tcgen05.mma per stage into a double-buffered
+//   warp  8    MMA     : one thread issues 3 passes x K/16 tcgen05.mma per stage into a double-buffered
 //                        TMEM accumulator; weights (bf16 hi/lo planes, TMA, SWIZZLE_128B) stay resident
-//   warps 5-8  epilogue: TMEM -> registers -> (K = 128: transposed through shared memory so that every
+//   warps 9-12 epilogue: TMEM -> registers -> (K = 128: transposed through shared memory so that every
 //                        global access is 4 rows x 128 contiguous bytes) -> bias / residual / activation -> global
 //                        (fp32 and/or bf16 hi/lo planes for the attention kernels)
 // The kernel body is written branch-free on purpose: an earlier version skipped unused epilogue features with
@@ -76,34 +76,47 @@ __device__ __forceinline__ float act_apply(float v, int act, float aux) {
     return act == DIP_ACT_RELU ? fmaxf(v, 0.f) : act == DIP_ACT_QUICKGELU ? gelu : act == DIP_ACT_SIGMOID ? sg : grad;
 }
 
-// the whole epilogue of one float4 of output row `row`, columns c..c+3 (a4 = accumulator)
-__device__ __forceinline__ void epilogue4(const Params& P, uint32_t row, int c, float4 a4) {
+// The epilogue of one float4 of output row `row`, columns c..c+3, in two phases so that a warp can request the
+// global operands of many slots before it stores anything (stores may alias the residual: in-place residual adds).
+struct EpiIn {
+    float4 ext;        // bias * row scale + addmat + residual
+    float4 aux;
+    size_t out_row;
+};
+__device__ __forceinline__ EpiIn epi_load(const Params& P, uint32_t row, int c) {
+    EpiIn e;
     const uint32_t b = row / P.rows_in, t_in = row - b * P.rows_in;
-    const size_t out_row = (size_t)b * P.rows_out + P.row_off + t_in;
+    e.out_row = (size_t)b * P.rows_out + P.row_off + t_in;
     float rbs = 1.0f;
     if (P.row_bias_scale) rbs = P.row_bias_scale[row];
     const float4 bv = *reinterpret_cast<const float4*>(P.bias + c);
     const float4 am = *reinterpret_cast<const float4*>(P.addmat + (size_t)t_in * P.add_ld + c);
-    const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, (uint32_t)out_row * P.res_mul) + c);
-    const float4 ax = *reinterpret_cast<const float4*>(P.aux + out_row * P.aux_ld + c);
-    float x[4] = {a4.x + bv.x * rbs + am.x + rv.x, a4.y + bv.y * rbs + am.y + rv.y, a4.z + bv.z * rbs + am.z + rv.z, a4.w + bv.w * rbs + am.w + rv.w};
-    if (P.preact) *reinterpret_cast<float4*>(P.preact + out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, (uint32_t)e.out_row * P.res_mul) + c);
+    e.aux = *reinterpret_cast<const float4*>(P.aux + e.out_row * P.aux_ld + c);
+    e.ext = make_float4(bv.x * rbs + am.x + rv.x, bv.y * rbs + am.y + rv.y, bv.z * rbs + am.z + rv.z, bv.w * rbs + am.w + rv.w);
+    return e;
+}
+__device__ __forceinline__ void epi_finish(const Params& P, const EpiIn& e, int c, float4 a4) {
+    float x[4] = {a4.x + e.ext.x, a4.y + e.ext.y, a4.z + e.ext.z, a4.w + e.ext.w};
+    if (P.preact) *reinterpret_cast<float4*>(P.preact + e.out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
     if (P.act != DIP_ACT_NONE) {
-        x[0] = act_apply(x[0], P.act, ax.x); x[1] = act_apply(x[1], P.act, ax.y);
-        x[2] = act_apply(x[2], P.act, ax.z); x[3] = act_apply(x[3], P.act, ax.w);
+        x[0] = act_apply(x[0], P.act, e.aux.x); x[1] = act_apply(x[1], P.act, e.aux.y);
+        x[2] = act_apply(x[2], P.act, e.aux.z); x[3] = act_apply(x[3], P.act, e.aux.w);
     }
-    if (P.C) *reinterpret_cast<float4*>(P.C + out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (P.C) *reinterpret_cast<float4*>(P.C + e.out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
     if (P.split_hi) {
         uint32_t h0, l0, h1, l1;
         split2(x[0], x[1], h0, l0);
         split2(x[2], x[3], h1, l1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_hi) + out_row * P.ldc + c) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_lo) + out_row * P.ldc + c) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_hi) + e.out_row * P.ldc + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_lo) + e.out_row * P.ldc + c) = make_uint2(l0, l1);
     }
 }
 
+constexpr int N_LOADERS = 8, W_MMA = 8, W_EPI = 9, N_THREADS = 13 * 32;
+
 template <int KCH, int BN, bool LN>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(N_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Params P) {
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
@@ -121,21 +134,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (threadIdx.x == 0) {
         mbar_init(&bars[G_WFULL], 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[G_AFULL + s], 128);
+            mbar_init(&bars[G_AFULL + s], N_LOADERS * 32);
             mbar_init(&bars[G_AEMPTY + s], 1);
             mbar_init(&bars[G_CFULL + s], 1);
             mbar_init(&bars[G_CEMPTY + s], 128);
         }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, 2 * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 4) {
-        // ------------------------------------------------------------------ loaders
+    if (warp < N_LOADERS) {
+        // ------------------------------------------------------------------ loaders: warp w owns rows 16w .. 16w+15 of every tile
         float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
         if (LN) {
             gam = reinterpret_cast<const float4*>(P.ln_gamma)[lane];
@@ -152,19 +165,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 const int s = it & 1;
                 if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);
                 uint8_t* dst = sm + s * A_STAGE + lane_off;
-#pragma unroll 1
-                for (int rr0 = 0; rr0 < 32; rr0 += 8) {
-                    float4 v[8];
-                    // 8 independent 512-byte row loads in flight per warp before any is consumed; rows past M re-read row M-1
+                {
+                    float4 v[16];
+                    // 16 independent 512-byte row loads in flight per warp (64 KB per SM) before any is consumed; rows past M re-read row M-1
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint32_t row = min((uint32_t)tile * 128u + warp * 32 + rr0 + u, (uint32_t)P.M - 1u);
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t row = min((uint32_t)tile * 128u + warp * 16 + u, (uint32_t)P.M - 1u);
                         const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
                         v[u] = reinterpret_cast<const float4*>(src)[lane];
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int r = warp * 32 + rr0 + u;
+                    for (int u = 0; u < 16; ++u) {
+                        const int r = warp * 16 + u;
                         const uint32_t row = (uint32_t)tile * 128u + r;
                         float4 x = v[u];
                         if (LN) {
@@ -191,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 mbar_arrive(&bars[G_AFULL + s]);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ weights (TMA) + MMA issue
         if (lane == 0) {
             mbar_expect_tx(&bars[G_WFULL], 2 * W_PLANE);
@@ -233,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
         // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp % 4
         const int q = warp & 3;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        float* stg = reinterpret_cast<float*>(sW + 2 * W_PLANE + (warp - 5) * STG_WARP);
+        float* stg = reinterpret_cast<float*>(sW + 2 * W_PLANE + (warp - W_EPI) * STG_WARP);
         int ti = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
             const int cb = ti & 1;
@@ -255,17 +267,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     __syncwarp();
                     const int cc = (lane & 7) * 4;
-#pragma unroll 2
-                    for (int u = 0; u < 8; ++u) {
-                        const int rr = u * 4 + (lane >> 3);
-                        const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
-                        if (row0 + rr < (uint32_t)P.M) epilogue4(P, row0 + rr, c0 + cc, a4);
+                    const uint32_t last = (uint32_t)P.M - 1u;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        EpiIn in[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) in[u] = epi_load(P, min(row0 + (h * 4 + u) * 4 + (lane >> 3), last), c0 + cc);   // 4 slots requested before any store
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int rr = (h * 4 + u) * 4 + (lane >> 3);
+                            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
+                            if (row0 + rr <= last) epi_finish(P, in[u], c0 + cc, a4);
+                        }
                     }
                     __syncwarp();
                 } else {
                     if (row0 + lane < (uint32_t)P.M) {
 #pragma unroll 2
-                        for (int i = 0; i < 32; i += 4) epilogue4(P, row0 + lane, c0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                        for (int i = 0; i < 32; i += 4) {
+                            const EpiIn in = epi_load(P, row0 + lane, c0 + i);
+                            epi_finish(P, in, c0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                        }
                     }
                 }
             }
@@ -273,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 2 * BN);
+    if (warp == W_MMA) tmem_dealloc(tmem, 2 * BN);
 }
 
 template <int KCH, int BN, bool LN>
@@ -287,7 +309,7 @@ static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const Params& 
     if (gx < 1) gx = 1;
     if (gx > P.n_tiles) gx = P.n_tiles;
     dim3 grid(gx, n_blocks_y);
-    gemm_tc_kernel<KCH, BN, LN><<<grid, 288, SMEM_BYTES, st>>>(whi, wlo, P);
+    gemm_tc_kernel<KCH, BN, LN><<<grid, N_THREADS, SMEM_BYTES, st>>>(whi, wlo, P);
     return 0;
 }
 

@@ -1,5 +1,7 @@
 """GPU: every exported kernel launcher against the CPU oracle (torch fp64 / oracle/restate.py) on
 seeded inputs, through the C-ABI (dip_b200.ops is a 1:1 ctypes wrapper)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -285,3 +287,29 @@ def test_gnn_kernels(cuda):
     xs = rnd((11, 5), 7); W = rnd((D, 5), 8); bb = rnd((D,), 9); sh = rnd((5,), 10); sc = 1 + 0.1 * rnd((5,), 11)
     yk = ops.linear_smallk(xs.to(cuda), W.to(cuda), bb.to(cuda), sh.to(cuda), sc.to(cuda), act="relu")
     assert rel_l2(yk, torch.relu(((xs.double() + sh.double()) * sc.double()) @ W.double().t() + bb.double())) < 2e-6
+
+
+def test_round_feasibility_toy_lp_known_answers(cuda):
+    """Known-answer test from the reference's own fixture toy_example.lp (via tests/golden/toy_is15.npz): all 2^15
+    assignments through dip_round_feasibility -> 1118 feasible, optimum 8, 4 optimal."""
+    import itertools
+    from dip_b200 import ops
+    from dip_b200.engine import coo_to_csr_csc
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "toy_is15.npz"))
+    n, M = len(d["c"]), len(d["b"])
+    X = np.array(list(itertools.product((0, 1), repeat=n)), np.float32)
+    L = 16
+    # probabilities on either side of 1/2 instead of exact bits, so that the rounding is exercised as well
+    p_full = np.zeros((X.shape[0], L), np.float32)
+    p_full[:, :n] = np.where(X > 0, 0.5 + 1e-3, 0.5 - 1e-3)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    csr = coo_to_csr_csc(d["rows"], d["cols"], d["vals"].astype(np.float32), M, n)
+    csr_d = {k: (dev(v) if isinstance(v, np.ndarray) else v) for k, v in csr.items()}
+    out = ops.round_feasibility(dev(p_full), torch.arange(n, dtype=torch.int32, device=cuda), csr_d, dev(d["b"].astype(np.float32)), M,
+                                csr_val_int=dev(csr["csr_val"].astype(np.int32)), b_int=dev(d["b"]), c_int=dev(d["c"]))
+    assert np.array_equal(out["xbits"].cpu().numpy(), X.astype(np.uint8))
+    viol, obj = out["viol_int"].cpu().numpy(), out["obj_int"].cpu().numpy()
+    feas = viol == 0
+    assert np.array_equal(feas, out["penalty"].cpu().numpy() <= 1e-5)
+    assert feas.sum() == 1118 and obj[feas].max() == 8 and (feas & (obj == 8)).sum() == 4
+    assert viol.sum() == int(d["viol_checksum"]) and (obj * feas).sum() == int(d["obj_checksum"])

@@ -1,5 +1,7 @@
 """CPU: the restatement (oracle/restate.py) against the golden vectors produced by the UNMODIFIED
 reference (oracle/gen_golden.py).  This is what pins the oracle."""
+import os
+
 import numpy as np
 import torch
 
@@ -118,3 +120,37 @@ def test_guidance_closed_form_matches_autograd():
     p0 = torch.zeros(1, cs.n, dtype=torch.float64)
     _, r0, h0 = restate.guidance_grad_p(p0, rows, cols, vals.double(), M, b, c, 0.0)
     assert float(h0[0, 0]) == 0.5 and float(r0[0, 0]) == 0.0       # b[0] == 0 in the fixture
+
+
+def _toy():
+    import itertools
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "toy_is15.npz"))
+    X = np.array(list(itertools.product((0, 1), repeat=len(d["c"]))), np.int64)
+    return d, X
+
+
+def test_toy_lp_known_answers_both_oracles():
+    """The reference's toy_example.lp (IndependentSet-15) brute-forced: 1118 feasible of 32768 assignments, optimum 8
+    reached by 4 of them.  Both integer oracles (numpy and the C restatement) must reproduce that."""
+    import ctypes as C
+    import subprocess
+    from oracle import restate
+    d, X = _toy()
+    assert (int(d["n_feasible"]), int(d["best_obj"]), int(d["n_optimal"])) == (1118, 8, 4)
+    M = len(d["b"])
+    feas, obj, viol = restate.feasibility_int(X, d["rows"], d["cols"], d["vals"], M, d["b"], d["c"])
+    assert feas.sum() == 1118 and obj[feas].max() == 8 and (feas & (obj == 8)).sum() == 4
+    assert viol.sum() == int(d["viol_checksum"]) and (obj * feas).sum() == int(d["obj_checksum"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_build", "libfeas_int.so")
+    if not os.path.isfile(so):
+        subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True)
+    lib = C.CDLL(so)
+    B, n = X.shape
+    p = X.astype(np.float32)
+    xb = np.zeros((B, n), np.uint8); v2 = np.zeros(B, np.int64); o2 = np.zeros(B, np.int64); scratch = np.zeros(M, np.int64)
+    ptr = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    rows, cols, vals, b, c = (np.ascontiguousarray(d[k]) for k in ("rows", "cols", "vals", "b", "c"))
+    lib.oracle_round_feasibility(C.c_int64(B), C.c_int64(n), C.c_int64(M), C.c_int64(len(vals)), ptr(rows), ptr(cols), ptr(vals), ptr(b),
+                                 ptr(c), ptr(p), ptr(xb), ptr(v2), ptr(o2), ptr(scratch))
+    assert np.array_equal(v2, viol) and np.array_equal(o2, obj) and np.array_equal(xb, X)

@@ -87,7 +87,7 @@ enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFUL
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_constant__ CUtensorMap tm_lo128,
                    const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64, float* __restrict__ o,
-                   float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T) {
+                   float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin) {
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint8_t* sQ = sm;
@@ -99,7 +99,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     volatile float* xm = reinterpret_cast<volatile float*>(sm + OFF_XM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, q0 = blockIdx.x * BM;
+    const int b = blockIdx.y, q0 = q_begin + blockIdx.x * BM;      // queries q_begin .. T-1 only
     const int row_base = b * T;
     const int n_tiles = (T + BN - 1) / BN;
     Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : -1);
@@ -137,10 +137,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
                 mbar_expect_tx(&bars[B_KFULL + s], K_STAGE);
                 uint8_t* dst = sK + s * K_STAGE;
-                const int krow = row_base + j * BN;
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_2d(dst + kb * 16384, &tm_hi64, &bars[B_KFULL + s], 128 + kb * 64, krow);           // rows 0-63 of the stacked operand
-                    tma_load_2d(dst + kb * 16384 + 8192, &tm_lo64, &bars[B_KFULL + s], 128 + kb * 64, krow);    // rows 64-127
+                    tma_load_3d(dst + kb * 16384, &tm_hi64, &bars[B_KFULL + s], 128 + kb * 64, j * BN, b);           // rows 0-63 of the stacked operand
+                    tma_load_3d(dst + kb * 16384 + 8192, &tm_lo64, &bars[B_KFULL + s], 128 + kb * 64, j * BN, b);    // rows 64-127
                 }
             }
             __syncwarp();
@@ -149,8 +148,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             tma_prefetch_desc(&tm_hi128); tma_prefetch_desc(&tm_lo128); tma_prefetch_desc(&tm_hi64); tma_prefetch_desc(&tm_lo64);
             mbar_expect_tx(&bars[B_QFULL], Q_BYTES);
             for (int kb = 0; kb < 2; ++kb) {
-                tma_load_2d(sQ + kb * 16384, &tm_hi128, &bars[B_QFULL], kb * 64, row_base + q0);
-                tma_load_2d(sQ + 32768 + kb * 16384, &tm_lo128, &bars[B_QFULL], kb * 64, row_base + q0);
+                tma_load_3d(sQ + kb * 16384, &tm_hi128, &bars[B_QFULL], kb * 64, q0, b);
+                tma_load_3d(sQ + 32768 + kb * 16384, &tm_lo128, &bars[B_QFULL], kb * 64, q0, b);
             }
         }
         load_K(0);
@@ -161,10 +160,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 if (j >= 2) mbar_wait(&bars[B_VEMPTY + s], ((j >> 1) - 1) & 1);
                 mbar_expect_tx(&bars[B_VFULL + s], V_STAGE);
                 uint8_t* dst = sV + s * V_STAGE;
-                const int krow = row_base + j * BN;
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_2d(dst + kb * 8192, &tm_hi64, &bars[B_VFULL + s], 256 + kb * 64, krow);            // V hi, d-half kb
-                    tma_load_2d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_VFULL + s], 256 + kb * 64, krow);    // V lo
+                    tma_load_3d(dst + kb * 8192, &tm_hi64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, b);            // V hi, d-half kb
+                    tma_load_3d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, b);    // V lo
                 }
             }
             __syncwarp();
@@ -383,7 +381,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                    const __grid_constant__ CUtensorMap tm_do_hi128, const __grid_constant__ CUtensorMap tm_do_lo128,
                    const __grid_constant__ CUtensorMap tm_do_hi32, const __grid_constant__ CUtensorMap tm_do_lo32,
                    float* __restrict__ out1, float* __restrict__ out2, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
-                   const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T) {
+                   const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int stat_begin, int str_begin) {
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BOFF_BAR);
@@ -391,9 +389,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
     volatile uint32_t* bits_ring = reinterpret_cast<volatile uint32_t*>(sm + BOFF_BITS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, r0 = blockIdx.x * 128;      // first stationary row (key for KS, query otherwise)
+    // stationary rows stat_begin .. T-1 (one CTA per 128), streamed rows str_begin .. T-1: rows below the two bounds
+    // take no part (their dO is zero / their gradient is not wanted)
+    const int b = blockIdx.y, r0 = stat_begin + blockIdx.x * 128;      // first stationary row (key for KS, query otherwise)
     const int row_base = b * T;
-    const int n_tiles = (T + BT - 1) / BT;
+    const int n_tiles = (T - str_begin + BT - 1) / BT;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[C_XFULL], 1);
@@ -425,16 +425,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             const int col_y = KS ? 256 : 0;  // V : dO
             mbar_expect_tx(&bars[C_XFULL], 4 * ST_PLANE);
             for (int kb = 0; kb < 2; ++kb) {
-                tma_load_2d(sm + BOFF_X + kb * 16384, &tm_qkv_hi128, &bars[C_XFULL], COL_X + kb * 64, row_base + r0);
-                tma_load_2d(sm + BOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[C_XFULL], COL_X + kb * 64, row_base + r0);
-                tma_load_2d(sm + BOFF_Y + kb * 16384, yhi, &bars[C_XFULL], col_y + kb * 64, row_base + r0);
-                tma_load_2d(sm + BOFF_Y + ST_PLANE + kb * 16384, ylo, &bars[C_XFULL], col_y + kb * 64, row_base + r0);
+                tma_load_3d(sm + BOFF_X + kb * 16384, &tm_qkv_hi128, &bars[C_XFULL], COL_X + kb * 64, r0, b);
+                tma_load_3d(sm + BOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[C_XFULL], COL_X + kb * 64, r0, b);
+                tma_load_3d(sm + BOFF_Y + kb * 16384, yhi, &bars[C_XFULL], col_y + kb * 64, r0, b);
+                tma_load_3d(sm + BOFF_Y + ST_PLANE + kb * 16384, ylo, &bars[C_XFULL], col_y + kb * 64, r0, b);
             }
         }
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j % TL_STAGES;
             // invalid streamed rows of this tile: beyond T, or (query-stationary: streamed rows are keys) masked keys
-            const int c = j * BT + lane;
+            const int c = str_begin + j * BT + lane;
             const bool bad = (c >= T) || (!KS && mrow && mrow[c]);
             const uint32_t bits = __ballot_sync(0xffffffffu, bad);
             if (lane == 0) {
@@ -442,12 +442,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 bits_ring[j & 7] = bits;
                 mbar_expect_tx(&bars[C_TLFULL + s], TL_STAGE);
                 uint8_t* dst = sm + BOFF_TL + s * TL_STAGE;
-                const int trow = row_base + j * BT;
+                const int trow = str_begin + j * BT;
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_2d(dst + kb * 8192, &tm_qkv_hi32, &bars[C_TLFULL + s], COL_U + kb * 64, trow);                // U hi, d-half kb
-                    tma_load_2d(dst + kb * 8192 + 4096, &tm_qkv_lo32, &bars[C_TLFULL + s], COL_U + kb * 64, trow);         // U lo
-                    tma_load_2d(dst + TL_HALF + kb * 8192, whi, &bars[C_TLFULL + s], col_w + kb * 64, trow);               // W hi
-                    tma_load_2d(dst + TL_HALF + kb * 8192 + 4096, wlo, &bars[C_TLFULL + s], col_w + kb * 64, trow);        // W lo
+                    tma_load_3d(dst + kb * 8192, &tm_qkv_hi32, &bars[C_TLFULL + s], COL_U + kb * 64, trow, b);                // U hi, d-half kb
+                    tma_load_3d(dst + kb * 8192 + 4096, &tm_qkv_lo32, &bars[C_TLFULL + s], COL_U + kb * 64, trow, b);         // U lo
+                    tma_load_3d(dst + TL_HALF + kb * 8192, whi, &bars[C_TLFULL + s], col_w + kb * 64, trow, b);               // W hi
+                    tma_load_3d(dst + TL_HALF + kb * 8192 + 4096, wlo, &bars[C_TLFULL + s], col_w + kb * 64, trow, b);        // W lo
                 }
             }
             __syncwarp();
@@ -532,7 +532,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             // key-stationary: lanes 0-15 fetch lse, lanes 16-31 delta of this thread's 16 queries; broadcast by shuffle below
             float qstat = 0.f;
             if (KS) {
-                const int cq = j * BT + h * 16 + (lane & 15);
+                const int cq = str_begin + j * BT + h * 16 + (lane & 15);
                 if (cq < T) qstat = (lane < 16) ? __ldg(lse + (int64_t)row_base + cq) * LOG2E : __ldg(delta + (int64_t)row_base + cq);
             }
             mbar_wait(&bars[C_GFULL], j & 1);
@@ -560,7 +560,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 const bool ok = row_ok && !((bad >> c) & 1u);
                 const float p = ok ? ex2_approx(fmaf(g1[c], SC2, -l2)) : 0.f;
                 g1[c] = p;
-                g2[c] = p * (g2[c] - dl) * SM_SCALE;
+                g2[c] = ok ? p * (g2[c] - dl) * SM_SCALE : 0.f;
             }
             uint32_t ph[8], pl[8], dh[8], dlw[8];
 #pragma unroll
@@ -603,11 +603,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-__global__ void __launch_bounds__(256) delta_kernel(float* __restrict__ delta, const float* __restrict__ o, const float* __restrict__ d_o, int64_t rows) {
+// delta[row] = o[row] . dO[row] for the rows t >= begin of every sample (rows = B * (T - begin))
+__global__ void __launch_bounds__(256) delta_kernel(float* __restrict__ delta, const float* __restrict__ o, const float* __restrict__ d_o, int64_t rows,
+                                                    int T, int begin) {
     int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < rows; r += nwarps) {
+    const int w = T - begin;
+    for (int64_t i = warp; i < rows; i += nwarps) {
+        const int64_t r = (i / w) * T + begin + (i % w);
         float4 a = reinterpret_cast<const float4*>(o + r * D)[lane];
         float4 g = reinterpret_cast<const float4*>(d_o + r * D)[lane];
         float s = warp_sum(a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w);
@@ -649,6 +653,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return 0;
 }
 
+// (batch, rows, cols) bf16 tensor, row stride `row_stride_elems`, samples `rows` rows apart; box = box_rows x box_cols of one sample.
+// Out-of-range rows / columns of a box read as zero.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                      uint32_t box_cols) {
+    EncodeTiledFn fn = encode_fn();
+    DIP_REQUIRE(fn, "cuTensorMapEncodeTiled entry point not available");
+    DIP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride_elems * 2) % 16 == 0, "tensor map: base / row stride must be 16-byte aligned");
+    cuuint64_t gdim[3] = {cols, rows, batch};
+    cuuint64_t gstr[2] = {row_stride_elems * 2, rows * row_stride_elems * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DIP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with code %d", (int)r);
+    return 0;
+}
+
 }  // namespace dip
 
 using namespace dip;
@@ -656,23 +677,23 @@ using namespace dip;
 extern "C" {
 
 int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo, const uint8_t* key_mask, int64_t mask_stride, int B, int T,
-                    dip_stream_t stream) {
+                    int q_begin, dip_stream_t stream) {
     DIP_REQUIRE(o && qkv_hi && qkv_lo && B > 0 && T > 0, "dip_attn_fwd_tc: null/empty argument");
+    DIP_REQUIRE(q_begin >= 0 && q_begin < T, "dip_attn_fwd_tc: q_begin %d outside [0, T)", q_begin);
     DIP_REQUIRE(B <= 65535, "dip_attn_fwd_tc: B too large for one launch");
     static bool attr = false;
     if (!attr) {
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::FWD_SMEM));
         attr = true;
     }
-    const uint64_t R = (uint64_t)B * T;
     CUtensorMap hi128, lo128, hi64, lo64;
-    DIP_TRY(make_tmap_bf16_2d(&hi128, qkv_hi, R, 3 * D, 3 * D, 128, 64));
-    DIP_TRY(make_tmap_bf16_2d(&lo128, qkv_lo, R, 3 * D, 3 * D, 128, 64));
-    DIP_TRY(make_tmap_bf16_2d(&hi64, qkv_hi, R, 3 * D, 3 * D, 64, 64));
-    DIP_TRY(make_tmap_bf16_2d(&lo64, qkv_lo, R, 3 * D, 3 * D, 64, 64));
-    dim3 grid(cdiv(T, tcattn::BM), B);
+    DIP_TRY(make_tmap_bf16_3d(&hi128, qkv_hi, B, T, 3 * D, 3 * D, 128, 64));
+    DIP_TRY(make_tmap_bf16_3d(&lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
+    DIP_TRY(make_tmap_bf16_3d(&hi64, qkv_hi, B, T, 3 * D, 3 * D, 64, 64));
+    DIP_TRY(make_tmap_bf16_3d(&lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
+    dim3 grid(cdiv(T - q_begin, tcattn::BM), B);
     DIP_PROF(DIP_PROF_ATTN_FWD, stream);
-    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T);
+    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T, q_begin);
     DIP_LAUNCHED();
     return 0;
 }
@@ -686,10 +707,12 @@ int dip_debug_set_trace(unsigned long long* device_buffer) {
 
 int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo, const void* do_hi, const void* do_lo,
                     const float* o, const float* d_o, const float* lse, const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T,
-                    dip_stream_t stream) {
+                    int do_begin, int q_begin, int k_begin, dip_stream_t stream) {
     DIP_REQUIRE(dq && dk && dv && qkv_hi && qkv_lo && do_hi && do_lo && o && d_o && lse && delta_ws && B > 0 && T > 0,
                 "dip_attn_bwd_tc: null/empty argument");
     DIP_REQUIRE(ld_d % 4 == 0 && B <= 65535, "dip_attn_bwd_tc: bad ld_d / B");
+    DIP_REQUIRE(0 <= do_begin && do_begin <= q_begin && q_begin < T && 0 <= k_begin && k_begin < T,
+                "dip_attn_bwd_tc: need 0 <= do_begin <= q_begin < T and 0 <= k_begin < T (got %d, %d, %d)", do_begin, q_begin, k_begin);
     static bool attr = false;
     if (!attr) {
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::BWD_SMEM));
@@ -697,33 +720,34 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
         attr = true;
     }
     cudaStream_t st = as_stream(stream);
-    const uint64_t R = (uint64_t)B * T;
     CUtensorMap q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32, d_lo32;
-    DIP_TRY(make_tmap_bf16_2d(&q_hi128, qkv_hi, R, 3 * D, 3 * D, 128, 64));
-    DIP_TRY(make_tmap_bf16_2d(&q_lo128, qkv_lo, R, 3 * D, 3 * D, 128, 64));
-    DIP_TRY(make_tmap_bf16_2d(&q_hi32, qkv_hi, R, 3 * D, 3 * D, 32, 64));
-    DIP_TRY(make_tmap_bf16_2d(&q_lo32, qkv_lo, R, 3 * D, 3 * D, 32, 64));
-    DIP_TRY(make_tmap_bf16_2d(&d_hi128, do_hi, R, D, D, 128, 64));
-    DIP_TRY(make_tmap_bf16_2d(&d_lo128, do_lo, R, D, D, 128, 64));
-    DIP_TRY(make_tmap_bf16_2d(&d_hi32, do_hi, R, D, D, 32, 64));
-    DIP_TRY(make_tmap_bf16_2d(&d_lo32, do_lo, R, D, D, 32, 64));
+    DIP_TRY(make_tmap_bf16_3d(&q_hi128, qkv_hi, B, T, 3 * D, 3 * D, 128, 64));
+    DIP_TRY(make_tmap_bf16_3d(&q_lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
+    DIP_TRY(make_tmap_bf16_3d(&q_hi32, qkv_hi, B, T, 3 * D, 3 * D, 32, 64));
+    DIP_TRY(make_tmap_bf16_3d(&q_lo32, qkv_lo, B, T, 3 * D, 3 * D, 32, 64));
+    DIP_TRY(make_tmap_bf16_3d(&d_hi128, do_hi, B, T, D, D, 128, 64));
+    DIP_TRY(make_tmap_bf16_3d(&d_lo128, do_lo, B, T, D, D, 128, 64));
+    DIP_TRY(make_tmap_bf16_3d(&d_hi32, do_hi, B, T, D, D, 32, 64));
+    DIP_TRY(make_tmap_bf16_3d(&d_lo32, do_lo, B, T, D, D, 32, 64));
     {
         DIP_PROF(DIP_PROF_OTHER, stream);
-        int64_t blocks = ((int64_t)R + 7) / 8, cap = (int64_t)sm_count() * 8;
-        tcattn::delta_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(delta_ws, o, d_o, (int64_t)R);
+        const int64_t rows = (int64_t)B * (T - do_begin);
+        int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 8;
+        tcattn::delta_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(delta_ws, o, d_o, rows, T, do_begin);
         DIP_LAUNCHED();
     }
-    dim3 grid(cdiv(T, 128), B);
     {
+        dim3 grid(cdiv(T - k_begin, 128), B);      // keys k_begin.. stationary, queries do_begin.. streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DKDV, stream);
         tcattn::attn_bwd_tc_kernel<true><<<grid, tcattn::NTHREADS, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32,
-                                                                                           d_lo32, dv, dk, ld_d, lse, delta_ws, key_mask, mask_stride, T);
+                                                                                           d_lo32, dv, dk, ld_d, lse, delta_ws, key_mask, mask_stride, T, k_begin, do_begin);
         DIP_LAUNCHED();
     }
     {
+        dim3 grid(cdiv(T - q_begin, 128), B);      // queries q_begin.. stationary, all keys streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
         tcattn::attn_bwd_tc_kernel<false><<<grid, tcattn::NTHREADS, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32,
-                                                                                            d_lo32, nullptr, dq, ld_d, lse, delta_ws, key_mask, mask_stride, T);
+                                                                                            d_lo32, nullptr, dq, ld_d, lse, delta_ws, key_mask, mask_stride, T, q_begin, 0);
         DIP_LAUNCHED();
     }
     return 0;

@@ -222,61 +222,96 @@ static int linear(int mode, dip_gemm_args g, const WRef& w, const dip_rows* a_ro
     return dip_gemm_nt(&g, st);
 }
 
+// Restrict a Linear to the tokens t >= w of every sample; it keeps reading and writing the full-length (B*T) buffers in place.
+static void window(dip_gemm_args& g, int B, int T, int w) {
+    if (w <= 0) return;
+    g.M = B * (T - w);
+    g.rows_in = T - w; g.rows_out = T; g.row_off = w;
+    g.in_T = T; g.in_off = w;
+}
+
 // One ResidualAttentionBlock forward (model/modules.py:293-296).  xin -> xmid -> xout; h, h2 are
 // transients.  Statistics / lse / u are saved when non-null.
+// win > 0 (tensor-core mode only): the caller will use the output tokens t >= win only (the decoder keeps the last L of
+// its 2L tokens, model/decoder.py:45), so in the last layer just those tokens act as queries and go through the
+// out-projection and the MLP; keys and values still cover the whole sequence.
 static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, float* qkv, void* qkv_hi,
                      void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
-                     int B, int T, dip_stream_t st) {
+                     int B, int T, int win, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     DIP_REQUIRE(R < (1ll << 31), "wave too large: B*T = %lld rows", (long long)R);
+    if (!tc) win = 0;
     // q|k|v = LN1(x) . W_in^T + b_in   (tensor-core mode: only the bf16 planes are written)
     dip_gemm_args g = gemm(nullptr, D, tc ? nullptr : qkv, 3 * D, R, 3 * D, D, w.in_b, DIP_ACT_NONE);
     if (tc) { g.split_hi = qkv_hi; g.split_lo = qkv_lo; }
     DIP_TRY(linear(mode, g, w.in_w, &xin, w.ln1_w, w.ln1_b, mean1, rstd1, h, st));
-    if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, st));
+    if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, win, st));
     else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
     // x_mid = x + attn . W_out^T + b_out
     g = gemm(ao, D, xmid, D, R, D, D, w.out_b, DIP_ACT_NONE);
     g.res = xin;
+    window(g, B, T, win);
     DIP_TRY(linear(mode, g, w.out_w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // g = QuickGELU(LN2(x_mid) . W_fc^T + b_fc)   (pre-activation saved for the backward pass)
     dip_rows xm = plain_rows(xmid, T);
     g = gemm(nullptr, D, h2, D, R, D, D, w.fc_b, DIP_ACT_QUICKGELU);
     g.preact = u;
+    window(g, B, T, win);
     DIP_TRY(linear(mode, g, w.fc_w, &xm, w.ln2_w, w.ln2_b, mean2, rstd2, h, st));
     // x_out = x_mid + g . W_proj^T + b_proj
     g = gemm(h2, D, xout, D, R, D, D, w.proj_b, DIP_ACT_NONE);
     g.res = xm;
+    window(g, B, T, win);
     DIP_TRY(linear(mode, g, w.proj_w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     return 0;
 }
 
-// Input-gradient backward of one block.  dxout -> dxin (rows with t >= t_min only).
+// Input-gradient backward of one block: dxout -> dxin.
+//   t_min    : dxin is wanted for the tokens t >= t_min only (layer 0: the mip tokens are constants);
+//   do_begin : (tensor-core mode) dxout is identically zero for t < do_begin and those rows of dxout are not read
+//              (last layer: only the kept tokens carry a gradient).
+// Tokens outside these windows are skipped by every kernel that does not need them: the row-wise chain (MLP, LN2,
+// out-projection) runs on t >= do_begin, the attention backward streams queries t >= do_begin only and produces
+// dK, dV for t >= t_min and dQ for t >= max(t_min, do_begin), the in-projection backward runs on t >= t_min.
 static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int B, int T, float* dt1,
-                     float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, float* dxin, int t_min,
+                     float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, float* dxin, int t_min, int do_begin,
                      dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
+    if (!tc) do_begin = 0;
+    cudaStream_t cs = as_stream(st);
     // dU = (dxout . W_proj) * gelu'(u)
     dip_gemm_args g = gemm(dxout, D, dt1, D, R, D, D, nullptr, DIP_ACT_MUL_QUICKGELU_GRAD);
     g.aux = s.u;
+    window(g, B, T, do_begin);
     DIP_TRY(linear(mode, g, w.proj_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dH2 = dU . W_fc
     g = gemm(dt1, D, dt2, D, R, D, D, nullptr, DIP_ACT_NONE);
+    window(g, B, T, do_begin);
     DIP_TRY(linear(mode, g, w.fc_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dxmid = dxout + LN2'(dH2)
-    DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, 0, st));
+    DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, do_begin, st));
     // dAO = dxmid . W_out   (+ bf16 planes for the tensor-core attention backward)
     g = gemm(dxm, D, dao, D, R, D, D, nullptr, DIP_ACT_NONE);
     if (tc) { g.split_hi = do_hi; g.split_lo = do_lo; }
+    window(g, B, T, do_begin);
     DIP_TRY(linear(mode, g, w.out_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
-    if (tc)
-        DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
-    else
+    if (tc) {
+        const int q_begin = t_min > do_begin ? t_min : do_begin;
+        if (t_min < do_begin) {
+            // tokens t_min .. do_begin-1 still receive a gradient through their keys / values: their dQ and dxmid are exactly zero
+            DIP_CUDA(cudaMemset2DAsync(dqkv, 3 * D * sizeof(float), 0, D * sizeof(float), (size_t)R, cs));
+            DIP_CUDA(cudaMemset2DAsync(dxm, (size_t)T * D * sizeof(float), 0, (size_t)do_begin * D * sizeof(float), (size_t)B, cs));
+        }
+        DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, 0, delta, B, T,
+                                do_begin, q_begin, t_min, st));
+    } else {
         DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
+    }
     // dH1 = dQKV . W_in
     g = gemm(dqkv, 3 * D, dt1, D, R, D, 3 * D, nullptr, DIP_ACT_NONE);
+    if (tc) window(g, B, T, t_min);
     DIP_TRY(linear(mode, g, w.in_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dxin = dxmid + LN1'(dH1)
     DIP_TRY(dip_layernorm_bwd(dxin, dt1, xin, s.mean1, s.rstd1, w.ln1_w, dxm, R, t_min, st));
@@ -317,7 +352,7 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     DIP_TRY(linear(e->mode, g, e->w2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     for (int l = 0; l < e->n_den; ++l)
         DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
-                          nullptr, nullptr, nullptr, nullptr, e->mask_den, B, T1, st));
+                          nullptr, nullptr, nullptr, nullptr, e->mask_den, B, T1, 0, st));
     return 0;
 }
 
@@ -330,7 +365,7 @@ static int decode(dip_engine* e, const Workspace& w, const float* x, int B, dip_
         else xin = plain_rows(w.ls[l - 1].xout, T2);
         const LayerSave& s = w.ls[l];
         DIP_TRY(block_fwd(e->mode, e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, s.qkv, s.qkv_hi, s.qkv_lo, s.ao, s.lse, s.mean1, s.rstd1, s.mean2,
-                          s.rstd2, s.u, e->mask_dec, B, T2, st));
+                          s.rstd2, s.u, e->mask_dec, B, T2, l == e->n_dec - 1 ? L : 0, st));
     }
     DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, e->inst.kpm, st));
     return 0;
@@ -351,9 +386,10 @@ static int guidance_grad(dip_engine* e, const Workspace& w, const float* x, int 
         dip_rows xin;
         if (l == 0) { xin.shared = in.mip; xin.batch = x; xin.T = T2; xin.split = L; }
         else xin = plain_rows(w.ls[l - 1].xout, T2);
-        // the gradient w.r.t. the (constant) mip tokens of layer 0 is never used: skip those rows
+        // the gradient w.r.t. the (constant) mip tokens of layer 0 is never used, and only the last L tokens of the last
+        // layer's output carry a gradient (head_bwd writes zeros elsewhere; in tensor-core mode those rows are not even read)
         DIP_TRY(block_bwd(e->mode, e->dec[l], dcur, xin, w.ls[l], e->mask_dec, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.do_hi, w.do_lo, w.dqkv, w.delta,
-                          dnext, l == 0 ? L : 0, st));
+                          dnext, l == 0 ? L : 0, l == e->n_dec - 1 ? L : 0, st));
         float* t = dcur; dcur = dnext; dnext = t;
     }
     *grad = dcur + (int64_t)L * D;

@@ -157,6 +157,7 @@ extern "C" {
 
 int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream) {
     DIP_REQUIRE(args && args->A && args->W && args->C, "dip_gemm_nt: null argument");
+    DIP_REQUIRE(args->in_T == 0, "dip_gemm_nt: input row windows are a dip_gemm_tc feature");
     const dip_gemm_args& g = *args;
     DIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "dip_gemm_nt: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
     DIP_REQUIRE(g.N % GBN == 0 && g.K % GBK == 0, "dip_gemm_nt: N must be a multiple of 128 and K of 16 (N=%d K=%d)", g.N, g.K);

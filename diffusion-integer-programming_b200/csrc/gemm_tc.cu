@@ -43,8 +43,10 @@ struct Params {
     int M, N, n_tiles, act;
     // A: K = 128 -> row r = (b, t) with b = r / a_T, t = r % a_T: t < a_split ? a_shared + t*128 : a_batch + (b*(a_T-a_split) + t-a_split)*128
     //    K = 384 -> a_batch + r*lda + kc*128
+    //    row windows: GEMM row r reads input row (r / in_rows) * in_T + in_off + r % in_rows (identity: in_rows = BIG, in_T = in_off = 0)
     const float *a_shared, *a_batch;
     uint32_t a_T, a_split;
+    uint32_t in_rows, in_T, in_off;
     int lda;
     const float *ln_gamma, *ln_beta;
     float *ln_mean, *ln_rstd;
@@ -170,7 +172,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                     // 16 independent 512-byte row loads in flight per warp (64 KB per SM) before any is consumed; rows past M re-read row M-1
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const uint32_t row = min((uint32_t)tile * 128u + warp * 16 + u, (uint32_t)P.M - 1u);
+                        const uint32_t gr = min((uint32_t)tile * 128u + warp * 16 + u, (uint32_t)P.M - 1u);
+                        const uint32_t gb = gr / P.in_rows;
+                        const uint32_t row = gb * P.in_T + P.in_off + (gr - gb * P.in_rows);
                         const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
                         v[u] = reinterpret_cast<const float4*>(src)[lane];
                     }
@@ -187,8 +191,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                             rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
                             x = make_float4(dx * rs * gam.x + bet.x, dy * rs * gam.y + bet.y, dz * rs * gam.z + bet.z, dw * rs * gam.w + bet.w);
                             if (stats && row < (uint32_t)P.M) {
-                                P.ln_mean[row] = mu;
-                                P.ln_rstd[row] = rs;
+                                const uint32_t gb = row / P.in_rows;
+                                const uint32_t vrow = gb * P.in_T + P.in_off + (row - gb * P.in_rows);     // statistics are indexed like the input rows
+                                P.ln_mean[vrow] = mu;
+                                P.ln_rstd[vrow] = rs;
                             }
                         }
                         uint32_t h0, l0, h1, l1;
@@ -339,6 +345,7 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     DIP_REQUIRE((ln_mean == nullptr) == (ln_rstd == nullptr), "dip_gemm_tc: mean and rstd go together");
     DIP_REQUIRE(g.rows_in == 0 || (g.rows_out >= g.rows_in + g.row_off), "dip_gemm_tc: bad row remap");
     DIP_REQUIRE(g.bias || g.N <= 4 * 128, "dip_gemm_tc: N too large for the zero block");
+    DIP_REQUIRE(g.in_T == 0 || (g.rows_in > 0 && g.in_off >= 0 && g.in_T >= g.rows_in + g.in_off), "dip_gemm_tc: bad input row window");
     float* zeros = nullptr;
     DIP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&zeros), tcgemm::g_zeros));
     tcgemm::Params P;
@@ -352,6 +359,8 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
         P.a_shared = g.A; P.a_batch = g.A; P.a_T = tcgemm::BIG; P.a_split = 0;
     }
     P.lda = g.lda;
+    if (g.in_T > 0) { P.in_rows = (uint32_t)g.rows_in; P.in_T = (uint32_t)g.in_T; P.in_off = (uint32_t)g.in_off; }
+    else { P.in_rows = tcgemm::BIG; P.in_T = 0; P.in_off = 0; }
     P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.ln_mean = ln_mean; P.ln_rstd = ln_rstd;
     if (g.rows_in > 0) { P.rows_in = (uint32_t)g.rows_in; P.rows_out = (uint32_t)g.rows_out; P.row_off = (uint32_t)g.row_off; }
     else { P.rows_in = tcgemm::BIG; P.rows_out = 0; P.row_off = 0; }

@@ -40,8 +40,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(float* __restrict__ dx, con
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     float4 gv = reinterpret_cast<const float4*>(gamma)[lane];
-    for (int64_t r = warp; r < rows; r += nwarps) {
-        if (t_min > 0 && (int)(r % T) < t_min) continue;
+    // only the rows t >= t_min of every sample: `rows` counts those, i -> full row index r
+    const int w = t_min > 0 ? T - t_min : 1;
+    for (int64_t i = warp; i < rows; i += nwarps) {
+        const int64_t r = t_min > 0 ? (i / w) * T + t_min + (i % w) : i;
         float4 xv = reinterpret_cast<const float4*>(row_ptr(x, r))[lane];
         float4 dv = reinterpret_cast<const float4*>(dy + r * D)[lane];
         float mu = mean[r], rs = rstd[r];
@@ -87,8 +89,10 @@ int dip_layernorm_bwd(float* dx, const float* dy, dip_rows x, const float* mean,
                       const float* dres, int64_t rows, int t_min, dip_stream_t stream) {
     DIP_REQUIRE(dx && dy && x.batch && mean && rstd && gamma && rows > 0, "dip_layernorm_bwd: bad argument");
     DIP_REQUIRE(t_min == 0 || x.T > 0, "dip_layernorm_bwd: t_min needs rows.T");
+    DIP_REQUIRE(t_min == 0 || (t_min < x.T && rows % x.T == 0), "dip_layernorm_bwd: t_min needs whole samples of T rows");
     DIP_PROF(DIP_PROF_LN, stream);
-    ln_bwd_kernel<<<ln_grid(rows), 256, 0, as_stream(stream)>>>(dx, dy, x, mean, rstd, gamma, dres, rows, x.T > 0 ? x.T : 1, t_min);
+    const int64_t live = t_min > 0 ? rows / x.T * (x.T - t_min) : rows;       // rows with t >= t_min
+    ln_bwd_kernel<<<ln_grid(live), 256, 0, as_stream(stream)>>>(dx, dy, x, mean, rstd, gamma, dres, live, x.T > 0 ? x.T : 1, t_min);
     DIP_LAUNCHED();
     return 0;
 }

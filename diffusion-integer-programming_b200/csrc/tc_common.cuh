@@ -54,6 +54,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// 3-D tile (c0 = column, c1 = row within the sample, c2 = sample): rows past the sample's end are zero-filled by the
+// tensor map instead of running into the next sample
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -189,6 +196,8 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)r
 }  // namespace tc
 
 // host: 2-D bf16 tensor map, box = box_cols x box_rows, SWIZZLE_128B (box_cols * 2 bytes must be 128)
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                      uint32_t box_cols);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
                       uint32_t box_cols);
 

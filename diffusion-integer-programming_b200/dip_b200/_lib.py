@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("aux", vp),
         ("split_hi", vp),
         ("split_lo", vp),
+        ("in_T", C.c_int), ("in_off", C.c_int),
     ]
 
 
@@ -84,8 +85,8 @@ PROTOTYPES = {
     "dip_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp]),
     "dip_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp, i32, i32, vp]),
     "dip_split_bf16": (i32, [vp, vp, vp, i64, vp]),
-    "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
-    "dip_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, vp]),
+    "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "dip_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     "dip_gemm_tc": (i32, [C.POINTER(GemmArgs), vp, vp, C.POINTER(Rows), vp, vp, vp, vp, vp]),
     "dip_time_token": (i32, [vp, i32, i32, f32, vp, vp, vp]),
     "dip_decoder_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),

@@ -45,7 +45,7 @@ def gemm_nt(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=
 
 def gemm_tc(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=0, addmat=None, res=None, res_shared=None, res_T=0,
             res_split=0, row_bias_scale=None, preact=None, aux=None, out_rows=None, a_shared=None, a_T=0, a_split=0, ln=None,
-            want_stats=False, want_split=False, want_c=True, M=None):
+            want_stats=False, want_split=False, want_c=True, M=None, in_T=0, in_off=0, n_stats=None):
     """tcgen05 version of gemm_nt.  ln = (gamma, beta) fuses LayerNorm into the A load; a_shared/a_T/a_split
     give a two-source A (then A is the per-sample part and M the total row count)."""
     lib = _lib.load()
@@ -60,8 +60,9 @@ def gemm_tc(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=
         out = torch.empty((n_out, N), dtype=torch.float32, device=dev)
     hi = torch.empty((n_out, N), dtype=torch.bfloat16, device=dev) if want_split else None
     lo = torch.empty((n_out, N), dtype=torch.bfloat16, device=dev) if want_split else None
-    mean = torch.empty(M, dtype=torch.float32, device=dev) if want_stats else None
-    rstd = torch.empty(M, dtype=torch.float32, device=dev) if want_stats else None
+    n_stats = M if n_stats is None else n_stats
+    mean = torch.empty(n_stats, dtype=torch.float32, device=dev) if want_stats else None
+    rstd = torch.empty(n_stats, dtype=torch.float32, device=dev) if want_stats else None
     g = GemmArgs()
     g.A, g.lda, g.W, g.bias, g.C, g.ldc = ptr(A), K, None, ptr(bias), ptr(out), N
     g.M, g.N, g.K, g.act = M, N, K, ACT[act]
@@ -70,6 +71,7 @@ def gemm_tc(A, W, bias=None, act=None, out=None, rows_in=0, rows_out=0, row_off=
     g.res = Rows(ptr(res_shared), ptr(res), int(res_T), int(res_split))
     g.row_bias_scale, g.preact, g.aux = ptr(row_bias_scale), ptr(preact), ptr(aux)
     g.split_hi, g.split_lo = ptr(hi), ptr(lo)
+    g.in_T, g.in_off = int(in_T), int(in_off)
     ar = Rows(ptr(a_shared), ptr(A), int(a_T), int(a_split)) if a_shared is not None else None
     check(lib.dip_gemm_tc(C.byref(g), ptr(w_hi), ptr(w_lo), C.byref(ar) if ar is not None else None, ptr(ln[0]) if ln else None,
                           ptr(ln[1]) if ln else None, ptr(mean), ptr(rstd), _stream()))
@@ -143,26 +145,28 @@ def split_bf16(x):
     return hi, lo
 
 
-def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None):
-    """tcgen05 attention forward on the bf16 (hi, lo) planes of the packed (B*T, 384) qkv."""
+def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None, q_begin=0):
+    """tcgen05 attention forward on the bf16 (hi, lo) planes of the packed (B*T, 384) qkv.  Rows t < q_begin of
+    every sample are not computed (returned as NaN so that a test reading them fails)."""
     lib = _lib.load()
-    o = torch.empty((B * T, D), dtype=torch.float32, device=qkv_hi.device)
-    lse = torch.empty(B * T, dtype=torch.float32, device=qkv_hi.device)
+    o = torch.full((B * T, D), float("nan"), dtype=torch.float32, device=qkv_hi.device)
+    lse = torch.full((B * T,), float("nan"), dtype=torch.float32, device=qkv_hi.device)
     km, ms = _mask(key_mask, B, T, mask_stride)
-    check(lib.dip_attn_fwd_tc(ptr(o), ptr(lse), ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, _stream()))
+    check(lib.dip_attn_fwd_tc(ptr(o), ptr(lse), ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, int(q_begin), _stream()))
     return o, lse
 
 
-def attn_bwd_tc(qkv_hi, qkv_lo, o, d_o, lse, B, T, key_mask=None, mask_stride=None):
+def attn_bwd_tc(qkv_hi, qkv_lo, o, d_o, lse, B, T, key_mask=None, mask_stride=None, do_begin=0, q_begin=0, k_begin=0):
+    """Rows outside the windows (dq: t < q_begin; dk, dv: t < k_begin) come back as NaN."""
     lib = _lib.load()
     o, d_o = _f32(o), _f32(d_o)
     do_hi, do_lo = split_bf16(d_o)
-    dqkv = torch.empty((B * T, 3 * D), dtype=torch.float32, device=o.device)
+    dqkv = torch.full((B * T, 3 * D), float("nan"), dtype=torch.float32, device=o.device)
     delta = torch.empty(B * T, dtype=torch.float32, device=o.device)
     km, ms = _mask(key_mask, B, T, mask_stride)
     dbase = dqkv.data_ptr()
     check(lib.dip_attn_bwd_tc(dbase, dbase + 4 * D, dbase + 8 * D, 3 * D, ptr(qkv_hi), ptr(qkv_lo), ptr(do_hi), ptr(do_lo), ptr(o), ptr(d_o),
-                              ptr(lse), ptr(km), ms, ptr(delta), B, T, _stream()))
+                              ptr(lse), ptr(km), ms, ptr(delta), B, T, int(do_begin), int(q_begin), int(k_begin), _stream()))
     return dqkv
 
 

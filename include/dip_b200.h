@@ -127,6 +127,11 @@ typedef struct {
      * indexing as C (row stride ldc elements): the operand format of the tensor-core kernels below */
     void* split_hi;
     void* split_lo;
+    /* input row window (dip_gemm_tc only; in_T > 0 needs rows_in > 0): GEMM row r = b*rows_in + t reads input row
+     * b*in_T + in_off + t (of A, of the row source, and of the LayerNorm statistics).  With rows_out = in_T and
+     * row_off = in_off a Linear is applied in place to the tokens in_off .. in_off+rows_in-1 of every sample only --
+     * e.g. the last L tokens of the decoder's 2L, the only ones model/decoder.py:45 keeps. */
+    int in_T, in_off;
 } dip_gemm_args;
 int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream);
 
@@ -160,14 +165,20 @@ int dip_split_bf16(void* hi, void* lo, const float* x, int64_t n, dip_stream_t s
 /* Same contract as dip_attn_fwd, operands given as the bf16 (hi, lo) planes of the packed (B*T, 384)
  * in_proj output [q | k | v].  Every product is evaluated as hi.hi + hi.lo + lo.hi with fp32
  * accumulation in tensor memory. */
+/* q_begin: only the queries t >= q_begin of every sample are computed (o / lse rows below are not written) -- the last
+ * decoder layer needs just the L tokens model/decoder.py:45 keeps. */
 int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo, const uint8_t* key_mask,
-                    int64_t mask_stride, int B, int T, dip_stream_t stream);
+                    int64_t mask_stride, int B, int T, int q_begin, dip_stream_t stream);
 
 /* Same contract as dip_attn_bwd on split planes; do_hi/do_lo: planes of d_o (B*T,128).  Two tcgen05
  * kernels (key-stationary dK/dV, query-stationary dQ); deterministic. */
 int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo,
                     const void* do_hi, const void* do_lo, const float* o, const float* d_o, const float* lse,
-                    const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T, dip_stream_t stream);
+                    const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T,
+                    int do_begin, int q_begin, int k_begin, dip_stream_t stream);
+/* Row windows of dip_attn_bwd_tc (0, 0, 0 = everything): d_o is taken as zero for queries t < do_begin (those rows of
+ * d_o / o / lse are never read); dq is written for t >= q_begin only (q_begin >= do_begin); dk, dv for t >= k_begin
+ * only.  Unwritten rows keep their previous content. */
 
 /* dip_gemm_nt on tcgen05 (bf16x2-split operands): w_hi / w_lo are the bf16 planes of the (N,K) weight
  * (dip_split_bf16 of the nn.Linear weight).  K must be 128 or 384.  Extras over dip_gemm_nt:

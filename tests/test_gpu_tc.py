@@ -152,3 +152,79 @@ def test_gemm_tc_layernorm_two_source_and_epilogues(cuda):
     p4 = (A4.double() @ W2.double().t()).view(B, Lr, D) + addmat.double()
     got = out4.view(B, T1, D)
     assert rel_l2(got[:, 1:], p4 * torch.sigmoid(1.702 * p4)) < 2e-5 and float(got[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,T,qb", [(2, 200, 100), (1, 257, 129), (3, 130, 1), (2, 4000, 2000)])
+def test_attention_fwd_tc_query_window(cuda, B, T, qb):
+    """Only the queries t >= q_begin are computed; they must be bit-identical to the same rows of the full launch when the
+    window starts on a 128-row tile boundary of the full launch, and within tolerance otherwise; rows below stay untouched."""
+    from dip_b200 import ops
+    qkv = rnd((B * T, 3 * D), T + qb, 1.2).to(cuda)
+    mask = torch.zeros((B, T), dtype=torch.bool)
+    mask[:, T - 3:] = True
+    mask[:, 5] = True
+    hi, lo = ops.split_bf16(qkv)
+    o_full, lse_full = ops.attn_fwd_tc(hi, lo, B, T, mask.to(cuda))
+    o, lse = ops.attn_fwd_tc(hi, lo, B, T, mask.to(cuda), q_begin=qb)
+    o, lse, o_full, lse_full = o.view(B, T, D), lse.view(B, T), o_full.view(B, T, D), lse_full.view(B, T)
+    assert torch.isnan(o[:, :qb]).all() and torch.isnan(lse[:, :qb]).all()             # never written
+    assert torch.equal(o[:, qb:], o_full[:, qb:]) and torch.equal(lse[:, qb:], lse_full[:, qb:])   # a query row's result does not depend on its tile
+
+
+@pytest.mark.parametrize("B,T,do_b,q_b,k_b", [(2, 200, 100, 100, 0), (2, 200, 0, 100, 100), (1, 257, 129, 129, 129), (3, 130, 1, 7, 3),
+                                              (2, 4000, 2000, 2000, 0), (2, 4000, 0, 2000, 2000)])
+def test_attention_bwd_tc_windows(cuda, B, T, do_b, q_b, k_b):
+    """Row windows of the backward: dO == 0 below do_begin (and never read: poisoned with NaN here), dq for t >= q_begin,
+    dk / dv for t >= k_begin -- against the full launch on the zero-extended dO and against fp64 autograd."""
+    from dip_b200 import ops
+    qkv = rnd((B * T, 3 * D), T + do_b + 1, 1.2)
+    mask = torch.zeros((B, T), dtype=torch.bool)
+    mask[:, T - 3:] = True
+    mask[:, 5] = True
+    d_o = rnd((B, T, D), 17)
+    d_o[:, :do_b] = 0
+    hi, lo = ops.split_bf16(qkv.to(cuda))
+    o, lse = ops.attn_fwd_tc(hi, lo, B, T, mask.to(cuda))
+    full = ops.attn_bwd_tc(hi, lo, o, d_o.reshape(B * T, D).to(cuda), lse, B, T, mask.to(cuda)).view(B, T, 3 * D)
+    # the windowed launch must not read anything below do_begin: poison those rows of dO, o and lse
+    d_o_p, o_p, lse_p = d_o.clone().to(cuda), o.clone().view(B, T, D), lse.clone().view(B, T)
+    d_o_p[:, :do_b] = float("nan"); o_p[:, :do_b] = float("nan"); lse_p[:, :do_b] = float("nan")
+    win = ops.attn_bwd_tc(hi, lo, o_p.reshape(B * T, D), d_o_p.reshape(B * T, D), lse_p.reshape(B * T), B, T, mask.to(cuda),
+                          do_begin=do_b, q_begin=q_b, k_begin=k_b).view(B, T, 3 * D)
+    assert torch.isnan(win[:, :q_b, :D]).all() and torch.isnan(win[:, :k_b, D:]).all()
+    assert not torch.isnan(win[:, q_b:, :D]).any() and not torch.isnan(win[:, k_b:, D:]).any()
+    # dq rows are computed by the same instruction sequence whatever the window -> identical; dk / dv sum over fewer
+    # (all-zero) query tiles -> equal up to the order-independent zeros, i.e. identical as well
+    assert rel_l2(win[:, q_b:, :D], full[:, q_b:, :D]) < 1e-6
+    assert rel_l2(win[:, k_b:, D:], full[:, k_b:, D:]) < 1e-6
+    if T <= 300:
+        ref_in = qkv.double().requires_grad_(True)
+        _attn_ref(ref_in, B, T, mask).backward(d_o.reshape(B * T, D).double())
+        g = ref_in.grad.view(B, T, 3 * D)
+        assert rel_l2(win[:, q_b:, :D], g[:, q_b:, :D]) < TC_TOL and rel_l2(win[:, k_b:, D:], g[:, k_b:, D:]) < TC_TOL
+
+
+def test_gemm_tc_row_window(cuda):
+    """in_T / in_off: the Linear runs on the tokens t >= w of every sample in place (A rows, LayerNorm statistics, residual,
+    outputs all indexed by the full-length row), everything else untouched."""
+    from dip_b200 import ops
+    B, T, w = 3, 90, 41
+    x = rnd((B * T, D), 0, 2.0)
+    gamma, beta = 1 + 0.1 * rnd((D,), 2), 0.1 * rnd((D,), 3)
+    W, bias = rnd((D, D), 4, 0.1), rnd((D,), 5)
+    h = F.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+    ref = (h @ W.double().t() + bias.double() + x.double()).view(B, T, D)
+    out = torch.full((B * T, D), 7.0, device=cuda)
+    r = ops.gemm_tc(x.to(cuda), W.to(cuda), bias.to(cuda), out=out, M=B * (T - w), rows_in=T - w, rows_out=T, row_off=w, in_T=T, in_off=w,
+                    ln=(gamma.to(cuda), beta.to(cuda)), want_stats=True, n_stats=B * T, res=x.to(cuda), res_T=T)
+    got = out.view(B, T, D)
+    assert rel_l2(got[:, w:], ref[:, w:]) < 2e-5 and float((got[:, :w] - 7.0).abs().max()) == 0.0
+    mean = r["mean"].view(B, T)
+    assert rel_l2(mean[:, w:], x.view(B, T, D).double().mean(-1)[:, w:]) < 1e-5
+    # K = 384 with a window (the in-projection backward of layer 0)
+    A3, W3 = rnd((B * T, 3 * D), 6), rnd((D, 3 * D), 7, 0.1)
+    out3 = torch.full((B * T, D), -1.0, device=cuda)
+    ops.gemm_tc(A3.to(cuda), W3.to(cuda), out=out3, M=B * (T - w), rows_in=T - w, rows_out=T, row_off=w, in_T=T, in_off=w)
+    ref3 = (A3.double() @ W3.double().t()).view(B, T, D)
+    got3 = out3.view(B, T, D)
+    assert rel_l2(got3[:, w:], ref3[:, w:]) < 2e-5 and float((got3[:, :w] + 1.0).abs().max()) == 0.0

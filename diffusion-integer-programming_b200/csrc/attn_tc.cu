@@ -21,6 +21,7 @@
 //               and half of its columns.
 //   warp 8    : TMA producer; its 32 lanes also ballot the key-padding mask of every streamed tile into a
 //               bit word, so the row warps never touch global memory inside the loop.
+//   warp 11   : (forward only) second TMA producer, for the V ring
 //   warps 9,10: one thread each issues tcgen05.mma / tcgen05.commit -- warp 9 the score GEMMs, warp 10 the
 //               accumulating GEMMs.  Issue is throttled to the tensor pipe's rate and every mbarrier wait costs
 //               ~250 cycles (measured, tools/ktrace.py); two issuers hide each other's waits.
@@ -37,6 +38,7 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float SM_SCALE = 0.08838834764831845f;
 constexpr float SC2 = SM_SCALE * LOG2E;         // scores are exponentiated in base 2
 constexpr int NTHREADS = 352, ROW_THREADS = 256, W_PRODUCER = 8, W_MMA = 9, W_MMA2 = 10;
+constexpr int FWD_THREADS = 384, W_PRODUCER_V = 11;       // the forward has a second TMA producer warp (V ring)
 constexpr uint32_t SMEM_LIMIT = 232448;
 
 #ifdef DIP_TRACE
@@ -84,7 +86,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;                   // log2 units: P sta
 
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_constant__ CUtensorMap tm_lo128,
                    const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64, float* __restrict__ o,
                    float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin) {
@@ -102,7 +104,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     const int b = blockIdx.y, q0 = q_begin + blockIdx.x * BM;      // queries q_begin .. T-1 only
     const int row_base = b * T;
     const int n_tiles = (T + BN - 1) / BN;
-    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : -1);
+    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && (warp == W_PRODUCER || warp == W_PRODUCER_V)) ? (warp == W_PRODUCER ? 1 : 4) : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[B_QFULL], 1);
@@ -133,7 +135,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
             const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
             if (lane == 0) {
+                TR(40, j);
                 if (j >= K_STAGES) mbar_wait(&bars[B_KEMPTY + s], ((j / K_STAGES) - 1) & 1);
+                TR(41, j);
                 bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
                 mbar_expect_tx(&bars[B_KFULL + s], K_STAGE);
                 uint8_t* dst = sK + s * K_STAGE;
@@ -152,12 +156,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 tma_load_3d(sQ + 32768 + kb * 16384, &tm_lo128, &bars[B_QFULL], kb * 64, q0, b);
             }
         }
-        load_K(0);
-        for (int j = 0; j < n_tiles; ++j) {
-            if (j + 1 < n_tiles) load_K(j + 1);          // K runs one tile ahead of V: it is released after S_j, long before P_j.V_j
-            if (lane == 0) {
+        // K runs up to three tiles ahead, independent of the V ring: a single producer thread alternating between the two rings
+        // stalled the K loads behind the V ring's empty-waits and left the TMA queue idle a third of the time (tools/ktrace.py)
+        for (int j = 0; j < n_tiles; ++j) load_K(j);
+    } else if (warp == W_PRODUCER_V) {
+        // ------------------------------------------------------------------ TMA producer of the V ring
+        if (lane == 0) {
+            for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
+                TR(42, j);
                 if (j >= 2) mbar_wait(&bars[B_VEMPTY + s], ((j >> 1) - 1) & 1);
+                TR(43, j);
                 mbar_expect_tx(&bars[B_VFULL + s], V_STAGE);
                 uint8_t* dst = sV + s * V_STAGE;
                 for (int kb = 0; kb < 2; ++kb) {
@@ -165,7 +174,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                     tma_load_3d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, b);    // V lo
                 }
             }
-            __syncwarp();
         }
     } else if (warp == W_MMA || warp == W_MMA2) {
         // ------------------------------------------------------------------ MMA issuers (one thread each)
@@ -693,7 +701,7 @@ int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo
     DIP_TRY(make_tmap_bf16_3d(&lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
     dim3 grid(cdiv(T - q_begin, tcattn::BM), B);
     DIP_PROF(DIP_PROF_ATTN_FWD, stream);
-    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T, q_begin);
+    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::FWD_THREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T, q_begin);
     DIP_LAUNCHED();
     return 0;
 }

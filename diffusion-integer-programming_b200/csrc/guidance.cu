@@ -8,7 +8,11 @@
 #include <numeric>
 #include <vector>
 #include <math.h>
+#include <string.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dip {
 
@@ -32,33 +36,44 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     return t;
 }
 
-__global__ void __launch_bounds__(256) guidance_kernel(
+// A cluster of GCL CTAs works on one sample: CTA `rank` owns a contiguous slice of the rows (pass 1) and of the columns
+// (pass 2); the hinge indicators of the other slices are fetched through distributed shared memory after a cluster
+// barrier, and the per-CTA partial sums of viol / obj are added by rank 0 in rank order (fixed order -> deterministic).
+constexpr int GCL = 4, GTHREADS = 512;
+
+__global__ void __launch_bounds__(GTHREADS) guidance_kernel(
     float* __restrict__ dz, float* __restrict__ viol, float* __restrict__ obj, float* __restrict__ r_out, float* __restrict__ dp_out,
     const float* __restrict__ p_full, const int32_t* __restrict__ pos_of_col, const int32_t* __restrict__ rowptr,
     const int32_t* __restrict__ col, const float* __restrict__ val, const int32_t* __restrict__ colptr,
     const int32_t* __restrict__ crow, const float* __restrict__ cval, const float* __restrict__ bvec, const float* __restrict__ cvec,
     float one_minus_lam, float lam, int L, int n, int M, int Gr, int Gc) {
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) float sm[];
     float* p_s = sm;
     float* h_s = sm + n;
-    __shared__ float red[8];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ float red[GTHREADS / 32];
+    __shared__ float part[2];                       // this CTA's share of viol and obj
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / GCL, tid = threadIdx.x;
+    const int Mq = (M + GCL - 1) / GCL, nq = (n + GCL - 1) / GCL, Lq = (L + GCL - 1) / GCL;
+    const int i_lo = rank * Mq, i_hi = min(M, i_lo + Mq);
+    const int j_lo = rank * nq, j_hi = min(n, j_lo + nq);
 
-    for (int j = tid; j < n; j += blockDim.x) p_s[j] = p_full[(int64_t)b * L + pos_of_col[j]];
-    for (int t = tid; t < L; t += blockDim.x) dz[(int64_t)b * L + t] = 0.f;
+    for (int j = tid; j < n; j += GTHREADS) p_s[j] = p_full[(int64_t)b * L + pos_of_col[j]];
+    for (int t = rank * Lq + tid; t < min(L, (rank + 1) * Lq); t += GTHREADS) dz[(int64_t)b * L + t] = 0.f;      // padding positions stay zero
     __syncthreads();
 
-    // r = A p - b ; h ; viol
+    // r = A p - b ; h ; viol   (rows i_lo .. i_hi-1)
     float v_part = 0.f;
     {
-        const int groups = blockDim.x / Gr, gid = tid / Gr, gl = tid % Gr;
-        for (int i0 = 0; i0 < M; i0 += groups) {
+        const int groups = GTHREADS / Gr, gid = tid / Gr, gl = tid % Gr;
+        for (int i0 = i_lo; i0 < i_hi; i0 += groups) {
             int i = i0 + gid;
             float acc = 0.f;
-            if (i < M)
+            if (i < i_hi)
                 for (int e = rowptr[i] + gl; e < rowptr[i + 1]; e += Gr) acc = fmaf(val[e], p_s[col[e]], acc);
             acc = group_sum(acc, Gr);
-            if (i < M && gl == 0) {
+            if (i < i_hi && gl == 0) {
                 float r = acc - bvec[i];
                 h_s[i] = r > 0.f ? 1.0f : (r == 0.f ? 0.5f : 0.f);
                 v_part += fmaxf(r, 0.f);
@@ -66,20 +81,32 @@ __global__ void __launch_bounds__(256) guidance_kernel(
             }
         }
     }
-    float vt = block_sum(v_part, red);   // contains the __syncthreads that publishes h_s
-    if (tid == 0 && viol) viol[b] = vt;
+    float vt = block_sum(v_part, red);
+    if (tid == 0) part[0] = vt;
+    cluster.sync();                                  // every slice of h (and the zeroed dz) is published
+    for (int q = 0; q < GCL; ++q) {
+        if (q == rank) continue;
+        const float* remote = cluster.map_shared_rank(h_s, q);
+        for (int i = q * Mq + tid; i < min(M, (q + 1) * Mq); i += GTHREADS) h_s[i] = remote[i];
+    }
+    if (rank == 0 && tid == 0 && viol) {
+        float t = 0.f;
+        for (int q = 0; q < GCL; ++q) t += *cluster.map_shared_rank(&part[0], q);
+        viol[b] = t;
+    }
+    __syncthreads();
 
-    // dp = (1-lam) A^T h + lam c ; dz = dp * p (1-p) ; obj = p.c
+    // dp = (1-lam) A^T h + lam c ; dz = dp * p (1-p) ; obj = p.c   (columns j_lo .. j_hi-1)
     float o_part = 0.f;
     {
-        const int groups = blockDim.x / Gc, gid = tid / Gc, gl = tid % Gc;
-        for (int j0 = 0; j0 < n; j0 += groups) {
+        const int groups = GTHREADS / Gc, gid = tid / Gc, gl = tid % Gc;
+        for (int j0 = j_lo; j0 < j_hi; j0 += groups) {
             int j = j0 + gid;
             float acc = 0.f;
-            if (j < n)
+            if (j < j_hi)
                 for (int e = colptr[j] + gl; e < colptr[j + 1]; e += Gc) acc = fmaf(cval[e], h_s[crow[e]], acc);
             acc = group_sum(acc, Gc);
-            if (j < n && gl == 0) {
+            if (j < j_hi && gl == 0) {
                 float pj = p_s[j], cj = cvec[j];
                 float dp = one_minus_lam * acc + lam * cj;
                 dz[(int64_t)b * L + pos_of_col[j]] = (dp * (1.0f - pj)) * pj;   // sigmoid backward, torch order
@@ -89,7 +116,14 @@ __global__ void __launch_bounds__(256) guidance_kernel(
         }
     }
     float ot = block_sum(o_part, red);
-    if (tid == 0 && obj) obj[b] = ot;
+    if (tid == 0) part[1] = ot;
+    cluster.sync();
+    if (rank == 0 && tid == 0 && obj) {
+        float t = 0.f;
+        for (int q = 0; q < GCL; ++q) t += *cluster.map_shared_rank(&part[1], q);
+        obj[b] = t;
+    }
+    cluster.sync();                                  // no CTA leaves while its shared memory may still be read
 }
 
 __global__ void __launch_bounds__(256) round_feas_kernel(
@@ -174,8 +208,18 @@ int dip_guidance(float* dz, float* viol, float* obj, float* r_out, float* dp_out
     // (1 - lam) is formed in double like the reference's Python float and rounded once (diffusion.py:633)
     float oml = (float)(1.0 - (double)lam);
     DIP_PROF(DIP_PROF_GUIDANCE, stream);
-    guidance_kernel<<<B, 256, smem, as_stream(stream)>>>(dz, viol, obj, r_out, dp_out, p_full, pos_of_col, csr_rowptr, csr_col, csr_val,
-                                                         csc_colptr, csc_row, csc_val, b, c, oml, lam, L, n, M, Gr, Gc);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)B * GCL);
+    cfg.blockDim = dim3(GTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DIP_CUDA(cudaLaunchKernelEx(&cfg, guidance_kernel, dz, viol, obj, r_out, dp_out, p_full, pos_of_col, csr_rowptr, csr_col, csr_val, csc_colptr,
+                                csc_row, csc_val, b, c, oml, lam, L, n, M, Gr, Gc));
     DIP_LAUNCHED();
     return 0;
 }

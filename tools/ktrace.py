@@ -13,7 +13,7 @@ dev = torch.device("cuda")
 qkv = torch.randn(B * T, 3 * D, device=dev)
 hi, lo = ops.split_bf16(qkv)
 for _ in range(2): ops.attn_fwd_tc(hi, lo, B, T)
-buf = torch.zeros(3 * 16384, dtype=torch.int64, device=dev)
+buf = torch.zeros(5 * 16384, dtype=torch.int64, device=dev)
 fn = lib.dip_debug_set_trace; fn.restype = C.c_int; fn.argtypes = [C.c_void_p]
 fn(buf.data_ptr())
 ops.attn_fwd_tc(hi, lo, B, T)
@@ -22,7 +22,7 @@ fn(None)
 a = buf.cpu().numpy().astype(np.uint64)
 names = {20: "mma:S begin", 21: "mma:k_full", 22: "mma:s_free", 23: "mma:S issued", 24: "mma:PV begin", 25: "mma:v_full", 26: "mma:p_full", 27: "mma:pv_free",
          28: "mma:PV issued", 30: "row:iter", 31: "row:s_full", 32: "row:S loaded", 33: "row:max xchg", 34: "row:exps+split", 35: "row:P stored", 36: "row:pv_full",
-         37: "row:PV folded"}
+         37: "row:PV folded", 40: "prod:K begin", 41: "prod:K issue", 42: "prod:V begin", 43: "prod:V issue"}
 evs = []
 for v in a:
     v = int(v)

@@ -36,7 +36,44 @@ constexpr uint32_t BIG = 1u << 30;
 
 enum { G_WFULL = 0, G_AFULL = 1, G_AEMPTY = 3, G_CFULL = 5, G_CEMPTY = 7 };
 
+#ifdef DIP_TRACE
+// Development aid (-DDIP_TRACE): CTA (0,0) logs (event << 48 | tile << 32 | clock) from loader warp 0, the MMA lane and
+// epilogue warp 0 into three regions of a global buffer.
+__device__ unsigned long long* g_trace = nullptr;
+struct Tracer {
+    unsigned long long* p; int n;
+    __device__ Tracer(int region) : p(nullptr), n(0) { if (g_trace && blockIdx.x == 0 && blockIdx.y == 0 && region >= 0) p = g_trace + region * 16384; }
+    __device__ __forceinline__ void ev(int e, int tile) { if (p && n < 16384) p[n++] = ((unsigned long long)e << 48) | ((unsigned long long)tile << 32) | (unsigned long long)(unsigned int)clock64(); }
+};
+#define TR(e, t) tracer.ev((e), (t))
+__device__ int g_dbg = 0;      // bit 0: epilogue skips its global stores; bit 1: loaders skip their global loads
+#define DBG(bit) (g_dbg & (bit))
+#else
+#define DBG(bit) 0
+struct Tracer { __device__ Tracer(int) {} };
+#define TR(e, t)
+#endif
+
 __device__ float g_zeros[4 * 128];                  // what absent operands read (stride 0)
+
+// n / d for n < 2^31 in three instructions (multiplier and shift precomputed on the host): the row maps below need a few
+// divisions per row, and plain integer division made this memory-bound kernel instruction-bound (measured).
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1u ? n : (__umulhi(n, mul) >> shr); }
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1ull << lg) < d) ++lg;                       // ceil(log2 d)
+        const int p = 31 + lg;
+        f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+        f.shr = (uint32_t)(p - 32);
+    }
+    return f;
+}
 
 // Every optional feature is expressed as data: absent inputs point at g_zeros with stride 0, absent outputs are null.
 struct Params {
@@ -45,32 +82,37 @@ struct Params {
     //    K = 384 -> a_batch + r*lda + kc*128
     //    row windows: GEMM row r reads input row (r / in_rows) * in_T + in_off + r % in_rows (identity: in_rows = BIG, in_T = in_off = 0)
     const float *a_shared, *a_batch;
-    uint32_t a_T, a_split;
-    uint32_t in_rows, in_T, in_off;
+    FastDiv a_T; uint32_t a_split;
+    FastDiv in_rows; uint32_t in_T, in_off;
     int lda;
     const float *ln_gamma, *ln_beta;
     float *ln_mean, *ln_rstd;
     // epilogue
-    uint32_t rows_in, rows_out, row_off;            // output row = (r / rows_in) * rows_out + row_off + r % rows_in
+    FastDiv rows_in; uint32_t rows_out, row_off;    // output row = (r / rows_in) * rows_out + row_off + r % rows_in
     const float* bias;                              // N entries (or zeros)
     const float* row_bias_scale;                    // M entries or null (-> 1)
     const float* addmat; uint32_t add_ld;           // row t_in, stride add_ld (0 when absent)
-    const float *res_shared, *res_batch; uint32_t res_T, res_split, res_mul;   // residual rows like A; res_mul = 0 when absent
+    const float *res_shared, *res_batch; FastDiv res_T; uint32_t res_split, res_mul;   // residual rows like A; res_mul = 0 when absent
     const float* aux; uint32_t aux_ld;              // operand of the QuickGELU-gradient epilogue (stride 0 when absent)
     float *C, *preact; void *split_hi, *split_lo;
     int ldc;
 };
 
-__device__ __forceinline__ const float* src_row(const float* shared, const float* batch, uint32_t T, uint32_t split, uint32_t r) {
-    const uint32_t b = r / T, t = r - b * T;
+__device__ __forceinline__ const float* src_row(const float* shared, const float* batch, const FastDiv& T, uint32_t split, uint32_t r) {
+    const uint32_t b = T.div(r), t = r - b * T.d;
     const bool sh = t < split;
     const float* base = sh ? shared : batch;
-    const uint32_t idx = sh ? t : b * (T - split) + (t - split);
+    const uint32_t idx = sh ? t : b * (T.d - split) + (t - split);
     return base + (size_t)idx * D;
 }
 
-// sigmoid by MUFU.EX2 + MUFU.RCP: the slow paths of expf / IEEE division would triple the epilogue's size
-__device__ __forceinline__ float fast_sigmoid(float z) { return __frcp_rn(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+// sigmoid by MUFU.EX2 + MUFU.RCP (~2 ulp): the slow paths of expf / IEEE division / __frcp_rn would triple the epilogue's size
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float z) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
 __device__ __forceinline__ float act_apply(float v, int act, float aux) {
     const float z = act == DIP_ACT_MUL_QUICKGELU_GRAD ? aux : v;
     const float sg = fast_sigmoid((act == DIP_ACT_SIGMOID ? 1.0f : 1.702f) * z);
@@ -78,46 +120,65 @@ __device__ __forceinline__ float act_apply(float v, int act, float aux) {
     return act == DIP_ACT_RELU ? fmaxf(v, 0.f) : act == DIP_ACT_QUICKGELU ? gelu : act == DIP_ACT_SIGMOID ? sg : grad;
 }
 
-// The epilogue of one float4 of output row `row`, columns c..c+3, in two phases so that a warp can request the
-// global operands of many slots before it stores anything (stores may alias the residual: in-place residual adds).
+// Epilogue of one float4 (columns c..c+3) of one output row, in two phases so that a warp can request the global operands of
+// several rows before it stores anything (stores may alias the residual: in-place residual adds).  ROWOPS = false: the GEMM has
+// no per-row operand (no residual / aux / addmat / row-scaled bias) and phase one only maps the row.
 struct EpiIn {
     float4 ext;        // bias * row scale + addmat + residual
     float4 aux;
-    size_t out_row;
+    uint32_t out_row;
 };
-__device__ __forceinline__ EpiIn epi_load(const Params& P, uint32_t row, int c) {
+template <bool ROWOPS>
+__device__ __forceinline__ EpiIn epi_load(const Params& P, uint32_t row, int c, const float4& bv) {
     EpiIn e;
-    const uint32_t b = row / P.rows_in, t_in = row - b * P.rows_in;
-    e.out_row = (size_t)b * P.rows_out + P.row_off + t_in;
-    float rbs = 1.0f;
-    if (P.row_bias_scale) rbs = P.row_bias_scale[row];
-    const float4 bv = *reinterpret_cast<const float4*>(P.bias + c);
-    const float4 am = *reinterpret_cast<const float4*>(P.addmat + (size_t)t_in * P.add_ld + c);
-    const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, (uint32_t)e.out_row * P.res_mul) + c);
-    e.aux = *reinterpret_cast<const float4*>(P.aux + e.out_row * P.aux_ld + c);
-    e.ext = make_float4(bv.x * rbs + am.x + rv.x, bv.y * rbs + am.y + rv.y, bv.z * rbs + am.z + rv.z, bv.w * rbs + am.w + rv.w);
+    const uint32_t b = P.rows_in.div(row), t_in = row - b * P.rows_in.d;
+    e.out_row = b * P.rows_out + P.row_off + t_in;
+    if (ROWOPS) {
+        float rbs = 1.0f;
+        if (P.row_bias_scale) rbs = P.row_bias_scale[row];
+        const float4 am = *reinterpret_cast<const float4*>(P.addmat + (size_t)t_in * P.add_ld + c);
+        const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, e.out_row * P.res_mul) + c);
+        e.aux = *reinterpret_cast<const float4*>(P.aux + (size_t)e.out_row * P.aux_ld + c);
+        e.ext = make_float4(bv.x * rbs + am.x + rv.x, bv.y * rbs + am.y + rv.y, bv.z * rbs + am.z + rv.z, bv.w * rbs + am.w + rv.w);
+    } else {
+        e.ext = bv;
+        e.aux = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     return e;
 }
-__device__ __forceinline__ void epi_finish(const Params& P, const EpiIn& e, int c, float4 a4) {
+// predicated global stores without a branch: the slots of a batch stay one basic block, so their shared-memory loads, adds
+// and stores overlap instead of running one slot after the other
+__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a), "f"(b), "f"(c),
+                 "f"(d), "r"((uint32_t)ok)
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(a), "r"(b), "r"((uint32_t)ok) : "memory");
+}
+
+template <bool ACT>
+__device__ __forceinline__ void epi_finish(const Params& P, const EpiIn& e, int c, float4 a4, bool ok) {
     float x[4] = {a4.x + e.ext.x, a4.y + e.ext.y, a4.z + e.ext.z, a4.w + e.ext.w};
-    if (P.preact) *reinterpret_cast<float4*>(P.preact + e.out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
-    if (P.act != DIP_ACT_NONE) {
+    const size_t o = (size_t)e.out_row * P.ldc + c;
+    if (P.preact) st_global_v4(P.preact + o, x[0], x[1], x[2], x[3], ok);
+    if (ACT) {          // compiled out of the variants without activation: a skipped block this size costs instruction-fetch stalls
         x[0] = act_apply(x[0], P.act, e.aux.x); x[1] = act_apply(x[1], P.act, e.aux.y);
         x[2] = act_apply(x[2], P.act, e.aux.z); x[3] = act_apply(x[3], P.act, e.aux.w);
     }
-    if (P.C) *reinterpret_cast<float4*>(P.C + e.out_row * P.ldc + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (P.C) st_global_v4(P.C + o, x[0], x[1], x[2], x[3], ok);
     if (P.split_hi) {
         uint32_t h0, l0, h1, l1;
         split2(x[0], x[1], h0, l0);
         split2(x[2], x[3], h1, l1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_hi) + e.out_row * P.ldc + c) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.split_lo) + e.out_row * P.ldc + c) = make_uint2(l0, l1);
+        st_global_v2(reinterpret_cast<__nv_bfloat16*>(P.split_hi) + o, h0, h1, ok);
+        st_global_v2(reinterpret_cast<__nv_bfloat16*>(P.split_lo) + o, l0, l1, ok);
     }
 }
 
 constexpr int N_LOADERS = 8, W_MMA = 8, W_EPI = 9, N_THREADS = 13 * 32;
 
-template <int KCH, int BN, bool LN>
+template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT>
 __global__ void __launch_bounds__(N_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Params P) {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -149,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    Tracer tracer(lane != 0 ? -1 : warp == 0 ? 0 : warp == W_MMA ? 1 : warp == W_EPI ? 2 : -1);
     if (warp < N_LOADERS) {
         // ------------------------------------------------------------------ loaders: warp w owns rows 16w .. 16w+15 of every tile
         float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -165,7 +227,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
 #pragma unroll 1
             for (int kc = 0; kc < KCH; ++kc, ++it) {
                 const int s = it & 1;
+                TR(1, tile);
                 if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);
+                TR(2, tile);
                 uint8_t* dst = sm + s * A_STAGE + lane_off;
                 {
                     float4 v[16];
@@ -173,10 +237,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         const uint32_t gr = min((uint32_t)tile * 128u + warp * 16 + u, (uint32_t)P.M - 1u);
-                        const uint32_t gb = gr / P.in_rows;
-                        const uint32_t row = gb * P.in_T + P.in_off + (gr - gb * P.in_rows);
+                        const uint32_t gb = P.in_rows.div(gr);
+                        const uint32_t row = gb * P.in_T + P.in_off + (gr - gb * P.in_rows.d);
                         const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
-                        v[u] = reinterpret_cast<const float4*>(src)[lane];
+                        v[u] = DBG(2) ? make_float4(1.f, 2.f, 3.f, 4.f) : reinterpret_cast<const float4*>(src)[lane];
                     }
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
@@ -191,8 +255,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                             rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
                             x = make_float4(dx * rs * gam.x + bet.x, dy * rs * gam.y + bet.y, dz * rs * gam.z + bet.z, dw * rs * gam.w + bet.w);
                             if (stats && row < (uint32_t)P.M) {
-                                const uint32_t gb = row / P.in_rows;
-                                const uint32_t vrow = gb * P.in_T + P.in_off + (row - gb * P.in_rows);     // statistics are indexed like the input rows
+                                const uint32_t gb = P.in_rows.div(row);
+                                const uint32_t vrow = gb * P.in_T + P.in_off + (row - gb * P.in_rows.d);     // statistics are indexed like the input rows
                                 P.ln_mean[vrow] = mu;
                                 P.ln_rstd[vrow] = rs;
                             }
@@ -207,6 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 }
                 fence_proxy_async();
                 mbar_arrive(&bars[G_AFULL + s]);
+                TR(3, tile);
             }
         }
     } else if (warp == W_MMA) {
@@ -227,7 +292,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
 #pragma unroll 1
                 for (int kc = 0; kc < KCH; ++kc, ++it) {
                     const int s = it & 1;
+                    TR(10, tile);
                     mbar_wait(&bars[G_AFULL + s], (it >> 1) & 1);
+                    TR(11, tile);
                     tc_fence_after();
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
@@ -245,6 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                     tc_commit(&bars[G_AEMPTY + s]);
                 }
                 tc_commit(&bars[G_CFULL + cb]);
+                TR(12, tile);
             }
         }
     } else {
@@ -255,13 +323,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
         int ti = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
             const int cb = ti & 1;
+            TR(20, tile);
             mbar_wait(&bars[G_CFULL + cb], (ti >> 1) & 1);
+            TR(21, tile);
             tc_fence_after();
             const uint32_t row0 = (uint32_t)tile * 128u + q * 32;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 float v[32];
+                TR(22, tile);
                 tmem_ld32(lane_addr + cb * BN + ch * 32, v);
+                TR(23, tile);
                 if (ch == BN / 32 - 1) {
                     tc_fence_before();
                     mbar_arrive(&bars[G_CEMPTY + cb]);           // accumulator drained: the MMA warp may reuse it
@@ -272,28 +344,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     __syncwarp();
+                    TR(24, tile);
                     const int cc = (lane & 7) * 4;
                     const uint32_t last = (uint32_t)P.M - 1u;
+                    const float4 bv = *reinterpret_cast<const float4*>(P.bias + c0 + cc);
+                    constexpr int NB = 8;                        // rows whose global operands are requested before any store
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        EpiIn in[4];
+                    for (int h = 0; h < 8 / NB; ++h) {
+                        EpiIn in[NB];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) in[u] = epi_load(P, min(row0 + (h * 4 + u) * 4 + (lane >> 3), last), c0 + cc);   // 4 slots requested before any store
+                        for (int u = 0; u < NB; ++u) in[u] = epi_load<ROWOPS>(P, min(row0 + (h * NB + u) * 4 + (lane >> 3), last), c0 + cc, bv);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int rr = (h * 4 + u) * 4 + (lane >> 3);
+                        for (int u = 0; u < NB; ++u) {
+                            const int rr = (h * NB + u) * 4 + (lane >> 3);
                             const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
-                            if (row0 + rr <= last) epi_finish(P, in[u], c0 + cc, a4);
+                            epi_finish<ACT>(P, in[u], c0 + cc, a4, row0 + rr <= last);
                         }
+                        TR(25, tile);
                     }
                     __syncwarp();
                 } else {
-                    if (row0 + lane < (uint32_t)P.M) {
+                    const bool ok = row0 + lane < (uint32_t)P.M;
+                    const uint32_t row = min(row0 + lane, (uint32_t)P.M - 1u);
 #pragma unroll 2
-                        for (int i = 0; i < 32; i += 4) {
-                            const EpiIn in = epi_load(P, row0 + lane, c0 + i);
-                            epi_finish(P, in, c0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-                        }
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(P.bias + c0 + i);
+                        const EpiIn in = epi_load<ROWOPS>(P, row, c0 + i, bv);
+                        epi_finish<ACT>(P, in, c0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]), ok);
                     }
                 }
             }
@@ -304,18 +381,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (warp == W_MMA) tmem_dealloc(tmem, 2 * BN);
 }
 
-template <int KCH, int BN, bool LN>
+template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT>
 static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const Params& P, int n_blocks_y, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        DIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<KCH, BN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<KCH, BN, LN, ROWOPS, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr = true;
     }
     int gx = sm_count() / n_blocks_y;
     if (gx < 1) gx = 1;
     if (gx > P.n_tiles) gx = P.n_tiles;
     dim3 grid(gx, n_blocks_y);
-    gemm_tc_kernel<KCH, BN, LN><<<grid, N_THREADS, SMEM_BYTES, st>>>(whi, wlo, P);
+    gemm_tc_kernel<KCH, BN, LN, ROWOPS, ACT><<<grid, N_THREADS, SMEM_BYTES, st>>>(whi, wlo, P);
     return 0;
 }
 
@@ -325,6 +402,17 @@ static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const Params& 
 using namespace dip;
 
 extern "C" {
+
+#ifdef DIP_TRACE
+int dip_debug_set_gemm_knobs(int knobs) {
+    DIP_CUDA(cudaMemcpyToSymbol(tcgemm::g_dbg, &knobs, sizeof(knobs)));
+    return 0;
+}
+int dip_debug_set_trace_gemm(unsigned long long* device_buffer) {
+    DIP_CUDA(cudaMemcpyToSymbol(tcgemm::g_trace, &device_buffer, sizeof(device_buffer)));
+    return 0;
+}
+#endif
 
 int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, const dip_rows* a_rows, const float* ln_gamma,
                 const float* ln_beta, float* ln_mean, float* ln_rstd, dip_stream_t stream) {
@@ -354,24 +442,24 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     if (rows_a) {
         P.a_shared = a_rows->shared ? a_rows->shared : a_rows->batch; P.a_batch = a_rows->batch;
         P.a_split = (uint32_t)a_rows->split;
-        P.a_T = a_rows->split > 0 ? (uint32_t)a_rows->T : tcgemm::BIG;
+        P.a_T = tcgemm::make_fastdiv(a_rows->split > 0 ? (uint32_t)a_rows->T : tcgemm::BIG);
     } else {
-        P.a_shared = g.A; P.a_batch = g.A; P.a_T = tcgemm::BIG; P.a_split = 0;
+        P.a_shared = g.A; P.a_batch = g.A; P.a_T = tcgemm::make_fastdiv(tcgemm::BIG); P.a_split = 0;
     }
     P.lda = g.lda;
-    if (g.in_T > 0) { P.in_rows = (uint32_t)g.rows_in; P.in_T = (uint32_t)g.in_T; P.in_off = (uint32_t)g.in_off; }
-    else { P.in_rows = tcgemm::BIG; P.in_T = 0; P.in_off = 0; }
+    if (g.in_T > 0) { P.in_rows = tcgemm::make_fastdiv((uint32_t)g.rows_in); P.in_T = (uint32_t)g.in_T; P.in_off = (uint32_t)g.in_off; }
+    else { P.in_rows = tcgemm::make_fastdiv(tcgemm::BIG); P.in_T = 0; P.in_off = 0; }
     P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.ln_mean = ln_mean; P.ln_rstd = ln_rstd;
-    if (g.rows_in > 0) { P.rows_in = (uint32_t)g.rows_in; P.rows_out = (uint32_t)g.rows_out; P.row_off = (uint32_t)g.row_off; }
-    else { P.rows_in = tcgemm::BIG; P.rows_out = 0; P.row_off = 0; }
+    if (g.rows_in > 0) { P.rows_in = tcgemm::make_fastdiv((uint32_t)g.rows_in); P.rows_out = (uint32_t)g.rows_out; P.row_off = (uint32_t)g.row_off; }
+    else { P.rows_in = tcgemm::make_fastdiv(tcgemm::BIG); P.rows_out = 0; P.row_off = 0; }
     P.bias = g.bias ? g.bias : zeros;
     P.row_bias_scale = g.row_bias_scale;
     P.addmat = g.addmat ? g.addmat : zeros; P.add_ld = g.addmat ? (uint32_t)g.N : 0u;
     if (g.res.batch) {
         P.res_shared = g.res.shared ? g.res.shared : g.res.batch; P.res_batch = g.res.batch;
-        P.res_split = (uint32_t)g.res.split; P.res_T = g.res.split > 0 ? (uint32_t)g.res.T : tcgemm::BIG; P.res_mul = 1;
+        P.res_split = (uint32_t)g.res.split; P.res_T = tcgemm::make_fastdiv(g.res.split > 0 ? (uint32_t)g.res.T : tcgemm::BIG); P.res_mul = 1;
     } else {
-        P.res_shared = zeros; P.res_batch = zeros; P.res_split = 0; P.res_T = tcgemm::BIG; P.res_mul = 0;
+        P.res_shared = zeros; P.res_batch = zeros; P.res_split = 0; P.res_T = tcgemm::make_fastdiv(tcgemm::BIG); P.res_mul = 0;
     }
     P.aux = g.aux ? g.aux : zeros; P.aux_ld = g.aux ? (uint32_t)g.ldc : 0u;
     P.C = g.C; P.preact = g.preact; P.split_hi = g.split_hi; P.split_lo = g.split_lo; P.ldc = g.ldc;
@@ -380,11 +468,20 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     DIP_TRY(make_tmap_bf16_2d(&wlo, w_lo, g.N, g.K, g.K, BN, 64));
     DIP_PROF(DIP_PROF_GEMM, stream);
     cudaStream_t st = as_stream(stream);
-    if (g.K == 128) {
-        if (ln_gamma) DIP_TRY((tcgemm::launch<1, 128, true>(whi, wlo, P, g.N / 128, st)));
-        else DIP_TRY((tcgemm::launch<1, 128, false>(whi, wlo, P, g.N / 128, st)));
-    } else {
-        DIP_TRY((tcgemm::launch<3, 64, false>(whi, wlo, P, g.N / 64, st)));
+    const bool rowops = g.row_bias_scale || g.addmat || g.res.batch || g.aux;
+    const bool act = g.act != DIP_ACT_NONE;
+    const int variant = (g.K == 128 ? (ln_gamma ? 1 : 0) : 2) * 4 + (rowops ? 2 : 0) + (act ? 1 : 0);
+    const int ny = g.N / BN;
+    switch (variant) {
+#define DIP_GEMM_CASE(v, KCH, BNv, LNv, RO, AC) case v: DIP_TRY((tcgemm::launch<KCH, BNv, LNv, RO, AC>(whi, wlo, P, ny, st))); break;
+        DIP_GEMM_CASE(0, 1, 128, false, false, false) DIP_GEMM_CASE(1, 1, 128, false, false, true)
+        DIP_GEMM_CASE(2, 1, 128, false, true, false)  DIP_GEMM_CASE(3, 1, 128, false, true, true)
+        DIP_GEMM_CASE(4, 1, 128, true, false, false)  DIP_GEMM_CASE(5, 1, 128, true, false, true)
+        DIP_GEMM_CASE(6, 1, 128, true, true, false)   DIP_GEMM_CASE(7, 1, 128, true, true, true)
+        DIP_GEMM_CASE(8, 3, 64, false, false, false)  DIP_GEMM_CASE(9, 3, 64, false, false, true)
+        DIP_GEMM_CASE(10, 3, 64, false, true, false)  DIP_GEMM_CASE(11, 3, 64, false, true, true)
+#undef DIP_GEMM_CASE
+        default: DIP_FAIL("dip_gemm_tc: no kernel variant %d", variant);
     }
     DIP_LAUNCHED();
     return 0;

@@ -6,9 +6,10 @@
 //   warps 0-7  loaders : coalesced fp32 row loads (one warp per row, float4 per lane, 16 rows = 8 KB in flight per
 //                        warp), optional LN by warp shuffles, split into bf16 hi/lo, swizzled K-major stores
 //                        into a 2-stage ring
-//   warp  8    MMA     : one thread issues 3 passes x K/16 tcgen05.mma per stage into a double-buffered
-//                        TMEM accumulator; weights (bf16 hi/lo planes, TMA, SWIZZLE_128B) stay resident
-//   warps 9-12 epilogue: TMEM -> registers -> (K = 128: transposed through shared memory so that every
+//   (warp 0, lane 0)   : MMA issue -- 3 passes x K/16 tcgen05.mma per stage into a double-buffered TMEM
+//                        accumulator, issued while the warp's next row loads are in flight; weights (bf16 hi/lo
+//                        planes, TMA, SWIZZLE_128B) stay resident
+//   warps 8-15 epilogue (two per TMEM lane quarter, splitting the columns): TMEM -> registers -> (K = 128: transposed through shared memory so that every
 //                        global access is 4 rows x 128 contiguous bytes) -> bias / residual / activation -> global
 //                        (fp32 and/or bf16 hi/lo planes for the attention kernels)
 // The kernel body is written branch-free on purpose: an earlier version skipped unused epilogue features with
@@ -30,8 +31,7 @@ constexpr uint32_t OFF_W = 2 * A_STAGE;             // after the 2-stage A ring 
 constexpr uint32_t W_BYTES = 98304;                 // up to 96 KB of weight planes (K = 128: 64 KB + output staging)
 constexpr uint32_t OFF_BAR = OFF_W + W_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
-constexpr int STG_LD = 36;                          // staging row stride in floats (conflict-free float4 access)
-constexpr uint32_t STG_WARP = 32 * STG_LD * 4;      // per epilogue warp
+constexpr uint32_t STG_WARP = 32 * 32 * 4;          // per epilogue warp: a 32 x 32 fp32 block, 16-byte chunks XOR-swizzled by row (conflict-free both ways)
 constexpr uint32_t BIG = 1u << 30;
 
 enum { G_WFULL = 0, G_AFULL = 1, G_AEMPTY = 3, G_CFULL = 5, G_CEMPTY = 7 };
@@ -176,7 +176,8 @@ __device__ __forceinline__ void epi_finish(const Params& P, const EpiIn& e, int 
     }
 }
 
-constexpr int N_LOADERS = 8, W_MMA = 8, W_EPI = 9, N_THREADS = 13 * 32;
+constexpr int N_LOADERS = 8, W_MMA = 0, W_EPI = N_LOADERS, N_EPI = 8, N_THREADS = (N_LOADERS + N_EPI) * 32;      // 16 warps: 128 registers each
+constexpr int RPW = 128 / N_LOADERS;      // rows of a tile per loader warp, loaded in batches of 16
 
 template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT>
 __global__ void __launch_bounds__(N_THREADS, 1)
@@ -189,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     constexpr uint32_t W_BLOCK = BN * 128;                 // one 64-column k-block of BN weight rows
     constexpr uint32_t W_PLANE = 2 * KCH * W_BLOCK;
     constexpr uint32_t IDESC = instr_desc(128, BN, 0, 0);
-    constexpr bool STAGED = (2 * W_PLANE + 4 * STG_WARP <= W_BYTES);
+    constexpr bool STAGED = (2 * W_PLANE + N_EPI * STG_WARP <= W_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -200,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             mbar_init(&bars[G_AFULL + s], N_LOADERS * 32);
             mbar_init(&bars[G_AEMPTY + s], 1);
             mbar_init(&bars[G_CFULL + s], 1);
-            mbar_init(&bars[G_CEMPTY + s], 128);
+            mbar_init(&bars[G_CEMPTY + s], N_EPI * 32);
         }
         mbar_fence_init();
     }
@@ -210,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    Tracer tracer(lane != 0 ? -1 : warp == 0 ? 0 : warp == W_MMA ? 1 : warp == W_EPI ? 2 : -1);
+    Tracer tracer(lane != 0 ? -1 : warp == 0 ? 0 : warp == 1 ? 1 : warp == W_EPI ? 2 : -1);
     if (warp < N_LOADERS) {
         // ------------------------------------------------------------------ loaders: warp w owns rows 16w .. 16w+15 of every tile
         float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -222,29 +223,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
         const uint32_t lane_off = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
         const int chunk = (lane & 15) >> 1;
         const bool stats = LN && P.ln_mean != nullptr && blockIdx.y == 0 && lane == 0;
+        // Loader warp 0 doubles as the MMA issuer: lane 0 issues the MMAs of stage it-1 right after the warp has requested the
+        // rows of stage it, i.e. in the shadow of its own global-load latency (a 17th warp would cut the register budget to 96).
+        const bool issuer = warp == W_MMA && lane == 0;
+        const uint32_t aA = smem_u32(sm), aW = smem_u32(sW);
+        if (issuer) {
+            mbar_expect_tx(&bars[G_WFULL], 2 * W_PLANE);
+            for (int kb = 0; kb < 2 * KCH; ++kb) {
+                tma_load_2d(sW + kb * W_BLOCK, &tm_w_hi, &bars[G_WFULL], kb * 64, n0);
+                tma_load_2d(sW + W_PLANE + kb * W_BLOCK, &tm_w_lo, &bars[G_WFULL], kb * 64, n0);
+            }
+        }
+        auto mma_issue = [&](int itx) {                     // lane 0 of warp 0 only
+            const int ti = itx / KCH, kc = itx - ti * KCH, cb = ti & 1, s = itx & 1;
+            if (itx == 0) mbar_wait(&bars[G_WFULL], 0);
+            if (kc == 0 && ti >= 2) mbar_wait(&bars[G_CEMPTY + cb], ((ti >> 1) - 1) & 1);
+            TR(10, ti);
+            mbar_wait(&bars[G_AFULL + s], (itx >> 1) & 1);
+            TR(11, ti);
+            tc_fence_after();
+            uint32_t acc = kc > 0 ? 1u : 0u;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t a = aA + s * A_STAGE + (pass == 2 ? A_PLANE : 0);      // hi, hi, lo
+                const uint32_t w = aW + (pass == 1 ? W_PLANE : 0);                    // hi, lo, hi
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc_mma(tmem + cb * BN, smem_desc(a + kb * 16384 + ks * 32, 16, 1024), smem_desc(w + (kc * 2 + kb) * W_BLOCK + ks * 32, 16, 1024),
+                               IDESC, acc);
+                        acc = 1;
+                    }
+            }
+            tc_commit(&bars[G_AEMPTY + s]);
+            if (kc == KCH - 1) tc_commit(&bars[G_CFULL + cb]);
+            TR(12, ti);
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
 #pragma unroll 1
             for (int kc = 0; kc < KCH; ++kc, ++it) {
                 const int s = it & 1;
                 TR(1, tile);
-                if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);
-                TR(2, tile);
                 uint8_t* dst = sm + s * A_STAGE + lane_off;
-                {
+#pragma unroll 1
+                for (int bt = 0; bt < RPW; bt += 16) {
                     float4 v[16];
-                    // 16 independent 512-byte row loads in flight per warp (64 KB per SM) before any is consumed; rows past M re-read row M-1
+                    // 16 independent 512-byte row loads in flight per warp before any is consumed; rows past M re-read row M-1
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const uint32_t gr = min((uint32_t)tile * 128u + warp * 16 + u, (uint32_t)P.M - 1u);
+                        const uint32_t gr = min((uint32_t)tile * 128u + warp * RPW + bt + u, (uint32_t)P.M - 1u);
                         const uint32_t gb = P.in_rows.div(gr);
                         const uint32_t row = gb * P.in_T + P.in_off + (gr - gb * P.in_rows.d);
                         const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
                         v[u] = DBG(2) ? make_float4(1.f, 2.f, 3.f, 4.f) : reinterpret_cast<const float4*>(src)[lane];
                     }
+                    if (bt == 0) {
+                        if (issuer && it > 0) mma_issue(it - 1);
+                        __syncwarp();
+                        if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);      // the stage's previous MMAs have read it
+                        TR(2, tile);
+                    }
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const int r = warp * 16 + u;
+                        const int r = warp * RPW + bt + u;
                         const uint32_t row = (uint32_t)tile * 128u + r;
                         float4 x = v[u];
                         if (LN) {
@@ -274,52 +317,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 TR(3, tile);
             }
         }
-    } else if (warp == W_MMA) {
-        // ------------------------------------------------------------------ weights (TMA) + MMA issue
-        if (lane == 0) {
-            mbar_expect_tx(&bars[G_WFULL], 2 * W_PLANE);
-            for (int kb = 0; kb < 2 * KCH; ++kb) {
-                tma_load_2d(sW + kb * W_BLOCK, &tm_w_hi, &bars[G_WFULL], kb * 64, n0);
-                tma_load_2d(sW + W_PLANE + kb * W_BLOCK, &tm_w_lo, &bars[G_WFULL], kb * 64, n0);
-            }
-            mbar_wait(&bars[G_WFULL], 0);
-            const uint32_t aA = smem_u32(sm), aW = smem_u32(sW);
-            int it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
-                const int cb = ti & 1;
-                if (ti >= 2) mbar_wait(&bars[G_CEMPTY + cb], ((ti >> 1) - 1) & 1);
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int kc = 0; kc < KCH; ++kc, ++it) {
-                    const int s = it & 1;
-                    TR(10, tile);
-                    mbar_wait(&bars[G_AFULL + s], (it >> 1) & 1);
-                    TR(11, tile);
-                    tc_fence_after();
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a = aA + s * A_STAGE + (pass == 2 ? A_PLANE : 0);      // hi, hi, lo
-                        const uint32_t w = aW + (pass == 1 ? W_PLANE : 0);                    // hi, lo, hi
-#pragma unroll
-                        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                tc_mma(tmem + cb * BN, smem_desc(a + kb * 16384 + ks * 32, 16, 1024),
-                                       smem_desc(w + (kc * 2 + kb) * W_BLOCK + ks * 32, 16, 1024), IDESC, acc);
-                                acc = 1;
-                            }
-                    }
-                    tc_commit(&bars[G_AEMPTY + s]);
-                }
-                tc_commit(&bars[G_CFULL + cb]);
-                TR(12, tile);
-            }
-        }
+        if (issuer && it > 0) mma_issue(it - 1);
+        __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp % 4
-        const int q = warp & 3;
+        // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp % 4; the two warps of a
+        // quarter split the tile's 32-column chunks between them
+        const int q = warp & 3, half = (warp - W_EPI) >> 2;
+        constexpr int CPW = BN / 32 / 2;                    // chunks per warp
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         float* stg = reinterpret_cast<float*>(sW + 2 * W_PLANE + (warp - W_EPI) * STG_WARP);
+        const int cc = (lane & 7) * 4;
+        float4 bias4[CPW];                                  // this lane's bias columns, fixed for the whole launch
+#pragma unroll
+        for (int k = 0; k < CPW; ++k) bias4[k] = *reinterpret_cast<const float4*>(P.bias + n0 + (half * CPW + k) * 32 + (STAGED ? cc : 0));
         int ti = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
             const int cb = ti & 1;
@@ -328,13 +338,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             TR(21, tile);
             tc_fence_after();
             const uint32_t row0 = (uint32_t)tile * 128u + q * 32;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+#pragma unroll
+            for (int k = 0; k < CPW; ++k) {
+                const int ch = half * CPW + k;
                 float v[32];
                 TR(22, tile);
                 tmem_ld32(lane_addr + cb * BN + ch * 32, v);
                 TR(23, tile);
-                if (ch == BN / 32 - 1) {
+                if (k == CPW - 1) {
                     tc_fence_before();
                     mbar_arrive(&bars[G_CEMPTY + cb]);           // accumulator drained: the MMA warp may reuse it
                 }
@@ -342,22 +353,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 if (STAGED) {
                     // transpose through shared memory: afterwards every warp instruction touches 4 rows x 128 contiguous bytes
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     __syncwarp();
                     TR(24, tile);
-                    const int cc = (lane & 7) * 4;
                     const uint32_t last = (uint32_t)P.M - 1u;
-                    const float4 bv = *reinterpret_cast<const float4*>(P.bias + c0 + cc);
-                    constexpr int NB = 8;                        // rows whose global operands are requested before any store
+                    constexpr int NB = ROWOPS ? 4 : 8;           // rows whose global operands are requested before any store
 #pragma unroll
                     for (int h = 0; h < 8 / NB; ++h) {
                         EpiIn in[NB];
 #pragma unroll
-                        for (int u = 0; u < NB; ++u) in[u] = epi_load<ROWOPS>(P, min(row0 + (h * NB + u) * 4 + (lane >> 3), last), c0 + cc, bv);
+                        for (int u = 0; u < NB; ++u) in[u] = epi_load<ROWOPS>(P, min(row0 + (h * NB + u) * 4 + (lane >> 3), last), c0 + cc, bias4[k]);
 #pragma unroll
                         for (int u = 0; u < NB; ++u) {
                             const int rr = (h * NB + u) * 4 + (lane >> 3);
-                            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
+                            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
                             epi_finish<ACT>(P, in[u], c0 + cc, a4, row0 + rr <= last);
                         }
                         TR(25, tile);

@@ -611,6 +611,246 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// backward, dQ: query-stationary with 64-key tiles
+// =============================================================================================
+// The generic kernel above streams 32-row tiles because its two stationary operand pairs and two accumulators leave room
+// for nothing larger -- and pays for it: a score MMA with N = 64 costs 67 cycles, as much as one with N = 128 (73).  The dQ
+// pass needs neither P nor a second accumulator, and its V tile is dead as soon as dP is formed, so here the tiles are 64
+// keys: K double-buffered (it is also the B operand of dS.K), V single-buffered, score MMAs at N = 128.
+//   G1 = Q.[K_hi;K_lo]^T (= S), G2 = dO.[V_hi;V_lo]^T (= dP), dS = P (dP - delta) / sqrt(d), dQ += dS.K
+// shared memory: Q hi/lo, dO hi/lo (128 KB) | K ring 2 x 32 KB | V 32 KB; a streamed tile is [d-half][hi,lo][64 keys][64 d]
+// tensor memory: [0,128) G1, [128,256) G2, [256,384) dQ, [384,512) two dS buffers of (32 hi + 32 lo) packed columns
+constexpr int QT = 64;
+constexpr uint32_t Q_TILE = 32768;
+constexpr uint32_t QOFF_X = 0, QOFF_Y = 2 * ST_PLANE, QOFF_U = 4 * ST_PLANE, QOFF_W = QOFF_U + 2 * Q_TILE, QOFF_BAR = QOFF_W + Q_TILE;
+constexpr uint32_t QOFF_BITS = QOFF_BAR + 192;
+constexpr uint32_t DQ_SMEM = QOFF_BAR + 256;
+static_assert(QOFF_BAR == 229376 && DQ_SMEM <= SMEM_LIMIT, "dQ kernel shared memory");
+constexpr uint32_t QTM_G1 = 0, QTM_G2 = 128, QTM_ACC = 256, QTM_DS = 384;
+constexpr uint32_t IDESC_G128 = instr_desc(128, 128, 0, 0);
+enum { D_XFULL = 0, D_UFULL = 1, D_UEMPTY = 3, D_WFULL = 5, D_WEMPTY = 6, D_GFULL = 7, D_GFREE = 8, D_DSFULL = 9, D_DSFREE = 11, D_DONE = 13 };
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
+                      const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64,
+                      const __grid_constant__ CUtensorMap tm_do_hi128, const __grid_constant__ CUtensorMap tm_do_lo128, float* __restrict__ dq, int ld_d,
+                      const float* __restrict__ lse, const float* __restrict__ delta, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T,
+                      int q_begin) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    require_aligned_smem(sm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    volatile uint64_t* bits_ring = reinterpret_cast<volatile uint64_t*>(sm + QOFF_BITS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, r0 = q_begin + blockIdx.x * 128;      // first query of this CTA
+    const int row_base = b * T;
+    const int n_tiles = (T + QT - 1) / QT;
+    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[D_XFULL], 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars[D_UFULL + s], 1);
+            mbar_init(&bars[D_UEMPTY + s], 1);
+            mbar_init(&bars[D_DSFULL + s], ROW_THREADS);
+            mbar_init(&bars[D_DSFREE + s], 1);
+        }
+        mbar_init(&bars[D_WFULL], 1);
+        mbar_init(&bars[D_WEMPTY], 1);
+        mbar_init(&bars[D_GFULL], 1);
+        mbar_init(&bars[D_GFREE], ROW_THREADS);
+        mbar_init(&bars[D_DONE], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
+
+    if (warp == W_PRODUCER) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[D_XFULL], 4 * ST_PLANE);
+            for (int kb = 0; kb < 2; ++kb) {
+                tma_load_3d(sm + QOFF_X + kb * 16384, &tm_qkv_hi128, &bars[D_XFULL], kb * 64, r0, b);
+                tma_load_3d(sm + QOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[D_XFULL], kb * 64, r0, b);
+                tma_load_3d(sm + QOFF_Y + kb * 16384, &tm_do_hi128, &bars[D_XFULL], kb * 64, r0, b);
+                tma_load_3d(sm + QOFF_Y + ST_PLANE + kb * 16384, &tm_do_lo128, &bars[D_XFULL], kb * 64, r0, b);
+            }
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j & 1;
+            const int k0 = j * QT + lane, k1 = k0 + 32;
+            const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
+            const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
+            if (lane == 0) {
+                TR(40, j);
+                if (j >= 2) mbar_wait(&bars[D_UEMPTY + s], ((j >> 1) - 1) & 1);
+                TR(41, j);
+                bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);
+                mbar_expect_tx(&bars[D_UFULL + s], Q_TILE);
+                uint8_t* du = sm + QOFF_U + s * Q_TILE;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(du + kb * 16384, &tm_qkv_hi64, &bars[D_UFULL + s], 128 + kb * 64, j * QT, b);            // K hi, d-half kb
+                    tma_load_3d(du + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_UFULL + s], 128 + kb * 64, j * QT, b);     // K lo
+                }
+                TR(42, j);
+                if (j >= 1) mbar_wait(&bars[D_WEMPTY], (j - 1) & 1);
+                TR(43, j);
+                mbar_expect_tx(&bars[D_WFULL], Q_TILE);
+                uint8_t* dw = sm + QOFF_W;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(dw + kb * 16384, &tm_qkv_hi64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);                // V hi
+                    tma_load_3d(dw + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);         // V lo
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == W_MMA || warp == W_MMA2) {
+        if (lane == 0) {
+            const uint32_t aX = smem_u32(sm + QOFF_X), aY = smem_u32(sm + QOFF_Y), aU = smem_u32(sm + QOFF_U), aW = smem_u32(sm + QOFF_W);
+            if (warp == W_MMA) {
+                mbar_wait(&bars[D_XFULL], 0);
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int s = j & 1;
+                    TR(20, j);
+                    mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
+                    TR(21, j);
+                    if (j >= 1) mbar_wait(&bars[D_GFREE], (j - 1) & 1);
+                    TR(22, j);
+                    tc_fence_after();
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {                   // g = 0: Q.[K_hi;K_lo]^T, g = 1: dO.[V_hi;V_lo]^T
+                        if (g == 1) {
+                            TR(23, j);
+                            mbar_wait(&bars[D_WFULL], j & 1);
+                            TR(24, j);
+                            tc_fence_after();
+                        }
+                        const uint32_t st = g == 0 ? aX : aY;
+                        const uint32_t tp = g == 0 ? aU + s * Q_TILE : aW;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int pl = 0; pl < 2; ++pl)              // A = stationary hi, then lo, into the same 128 columns
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    tc_mma(tmem + (g == 0 ? QTM_G1 : QTM_G2), smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024),
+                                           smem_desc(tp + kb * 16384 + ks * 32, 16, 1024), IDESC_G128, acc);
+                                    acc = 1;
+                                }
+                    }
+                    tc_commit(&bars[D_GFULL]);
+                    tc_commit(&bars[D_WEMPTY]);
+                    TR(25, j);
+                }
+            } else {
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int s = j & 1, pb = j & 1;
+                    mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);        // this issuer observes the TMA completion itself
+                    TR(26, j);
+                    mbar_wait(&bars[D_DSFULL + pb], (j >> 1) & 1);
+                    TR(27, j);
+                    tc_fence_after();
+                    const uint32_t tl = aU + s * Q_TILE;
+                    const uint32_t ds = tmem + QTM_DS + pb * 64;
+                    uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t a = ds + (pass == 2 ? 32 : 0);               // dS hi, hi, lo
+                        const uint32_t bb = tl + (pass == 1 ? 8192 : 0);            // K hi, lo, hi
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            // K tile as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step = 2048 bytes
+                            tc_mma_ts(tmem + QTM_ACC, a + ks * 8, smem_desc(bb + ks * 2048, 16384, 1024), IDESC_ACC, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc_commit(&bars[D_DSFREE + pb]);
+                    tc_commit(&bars[D_UEMPTY + s]);
+                    TR(28, j);
+                }
+                tc_commit(&bars[D_DONE]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ row warps: thread = (query row, 32 of the 64 keys)
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const int r_idx = r0 + row;
+        const bool row_ok = r_idx < T;
+        float row_lse2 = 0.f, row_delta = 0.f;
+        if (row_ok) {
+            row_lse2 = lse[(int64_t)row_base + r_idx] * LOG2E;
+            row_delta = delta[(int64_t)row_base + r_idx];
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            const int pb = j & 1;
+            TR(30, j);
+            mbar_wait(&bars[D_GFULL], j & 1);
+            TR(31, j);
+            tc_fence_after();
+            float g1[32], g2[32];
+            {
+                float t[32];
+                tmem_ld32(lane_addr + QTM_G1 + h * 32, g1);
+                tmem_ld32(lane_addr + QTM_G1 + 64 + h * 32, t);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) g1[c] += t[c];
+                tmem_ld32(lane_addr + QTM_G2 + h * 32, g2);
+                tmem_ld32(lane_addr + QTM_G2 + 64 + h * 32, t);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) g2[c] += t[c];
+            }
+            tc_fence_before();
+            mbar_arrive(&bars[D_GFREE]);
+            TR(32, j);
+            const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
+            uint32_t dh[16], dl[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const bool ok0 = row_ok && !((bad >> (2 * c)) & 1u), ok1 = row_ok && !((bad >> (2 * c + 1)) & 1u);
+                const float p0 = ex2_approx(fmaf(g1[2 * c], SC2, -row_lse2)), p1 = ex2_approx(fmaf(g1[2 * c + 1], SC2, -row_lse2));
+                const float d0 = ok0 ? p0 * (g2[2 * c] - row_delta) * SM_SCALE : 0.f;
+                const float d1 = ok1 ? p1 * (g2[2 * c + 1] - row_delta) * SM_SCALE : 0.f;
+                split2(d0, d1, dh[c], dl[c]);
+            }
+            TR(33, j);
+            if (j >= 2) mbar_wait(&bars[D_DSFREE + pb], ((j >> 1) - 1) & 1);     // dS.K of tile j-2 is done with this buffer
+            TR(34, j);
+            tc_fence_after();
+            const uint32_t pd = lane_addr + QTM_DS + pb * 64 + h * 16;
+            tmem_st16(pd, dh);
+            tmem_st16(pd + 32, dl);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[D_DSFULL + pb]);
+            TR(35, j);
+        }
+        mbar_wait(&bars[D_DONE], 0);
+        tc_fence_after();
+        float* dst = dq + ((int64_t)row_base + r_idx) * ld_d + h * 64;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float t[32];
+            tmem_ld32(lane_addr + QTM_ACC + h * 64 + ch * 32, t);
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // delta[row] = o[row] . dO[row] for the rows t >= begin of every sample (rows = B * (T - begin))
 __global__ void __launch_bounds__(256) delta_kernel(float* __restrict__ delta, const float* __restrict__ o, const float* __restrict__ d_o, int64_t rows,
                                                     int T, int begin) {
@@ -724,13 +964,16 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     static bool attr = false;
     if (!attr) {
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::BWD_SMEM));
-        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::BWD_SMEM));
+        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
         attr = true;
     }
     cudaStream_t st = as_stream(stream);
     CUtensorMap q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32, d_lo32;
     DIP_TRY(make_tmap_bf16_3d(&q_hi128, qkv_hi, B, T, 3 * D, 3 * D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
+    CUtensorMap q_hi64, q_lo64;
+    DIP_TRY(make_tmap_bf16_3d(&q_hi64, qkv_hi, B, T, 3 * D, 3 * D, 64, 64));
+    DIP_TRY(make_tmap_bf16_3d(&q_lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_hi32, qkv_hi, B, T, 3 * D, 3 * D, 32, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_lo32, qkv_lo, B, T, 3 * D, 3 * D, 32, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_hi128, do_hi, B, T, D, D, 128, 64));
@@ -754,8 +997,8 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     {
         dim3 grid(cdiv(T - q_begin, 128), B);      // queries q_begin.. stationary, all keys streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
-        tcattn::attn_bwd_tc_kernel<false><<<grid, tcattn::NTHREADS, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32,
-                                                                                            d_lo32, nullptr, dq, ld_d, lse, delta_ws, key_mask, mask_stride, T, q_begin, 0);
+        tcattn::attn_bwd_dq_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, d_hi128, d_lo128, dq, ld_d, lse,
+                                                                                       delta_ws, key_mask, mask_stride, T, q_begin);
         DIP_LAUNCHED();
     }
     return 0;

@@ -402,6 +402,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
     const int b = blockIdx.y, r0 = stat_begin + blockIdx.x * 128;      // first stationary row (key for KS, query otherwise)
     const int row_base = b * T;
     const int n_tiles = (T - str_begin + BT - 1) / BT;
+    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[C_XFULL], 1);
@@ -446,7 +447,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             const bool bad = (c >= T) || (!KS && mrow && mrow[c]);
             const uint32_t bits = __ballot_sync(0xffffffffu, bad);
             if (lane == 0) {
+                TR(40, j);
                 if (j >= TL_STAGES) mbar_wait(&bars[C_TLEMPTY + s], ((j / TL_STAGES) - 1) & 1);
+                TR(41, j);
                 bits_ring[j & 7] = bits;
                 mbar_expect_tx(&bars[C_TLFULL + s], TL_STAGE);
                 uint8_t* dst = sm + BOFF_TL + s * TL_STAGE;
@@ -466,8 +469,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             if (warp == W_MMA) mbar_wait(&bars[C_XFULL], 0);
             auto issue_G = [&](int j) {
                 const int s = j % TL_STAGES;
+                TR(20, j);
                 mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);
+                TR(21, j);
                 if (j >= 1) mbar_wait(&bars[C_GFREE], (j - 1) & 1);
+                TR(22, j);
                 tc_fence_after();
                 const uint32_t tl = aTL + s * TL_STAGE;
 #pragma unroll
@@ -487,11 +493,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                             }
                 }
                 tc_commit(&bars[C_GFULL]);
+                TR(25, j);
             };
             auto issue_acc = [&](int j) {
                 const int s = j % TL_STAGES, pb = j & 1;
                 mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);     // this issuer observes the TMA completion itself
+                TR(26, j);
                 mbar_wait(&bars[C_PDFULL + pb], (j >> 1) & 1);
+                TR(27, j);
                 tc_fence_after();
                 const uint32_t tl = aTL + s * TL_STAGE;
                 const uint32_t pd = tmem + TM_PD + pb * 64;
@@ -513,6 +522,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 }
                 tc_commit(&bars[C_PDFREE + pb]);
                 tc_commit(&bars[C_TLEMPTY + s]);
+                TR(28, j);
             };
             if (warp == W_MMA) {
                 for (int j = 0; j < n_tiles; ++j) issue_G(j);
@@ -543,7 +553,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 const int cq = str_begin + j * BT + h * 16 + (lane & 15);
                 if (cq < T) qstat = (lane < 16) ? __ldg(lse + (int64_t)row_base + cq) * LOG2E : __ldg(delta + (int64_t)row_base + cq);
             }
+            TR(30, j);
             mbar_wait(&bars[C_GFULL], j & 1);
+            TR(31, j);
             tc_fence_after();
             float g1[16], g2[16];
             {
@@ -557,6 +569,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             }
             tc_fence_before();
             mbar_arrive(&bars[C_GFREE]);
+            TR(32, j);
             const uint32_t bad = (bits_ring[j & 7] >> (16 * h)) & 0xffffu;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
@@ -576,7 +589,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
                 split2(g1[2 * c], g1[2 * c + 1], ph[c], pl[c]);
                 split2(g2[2 * c], g2[2 * c + 1], dh[c], dlw[c]);
             }
+            TR(33, j);
             if (j >= 2) mbar_wait(&bars[C_PDFREE + pb], ((j >> 1) - 1) & 1);     // the accumulating MMAs of tile j-2 are done with this buffer
+            TR(34, j);
             tc_fence_after();
             const uint32_t pd = lane_addr + TM_PD + pb * 64 + h * 8;
             if (KS) {
@@ -588,6 +603,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __gri
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[C_PDFULL + pb]);
+            TR(35, j);
         }
         mbar_wait(&bars[C_DONE], 0);
         tc_fence_after();
@@ -647,7 +663,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     const int b = blockIdx.y, r0 = q_begin + blockIdx.x * 128;      // first query of this CTA
     const int row_base = b * T;
     const int n_tiles = (T + QT - 1) / QT;
-    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
+    Tracer tracer(threadIdx.x == 0 ? 5 : (lane == 0 && warp == W_PRODUCER) ? 6 : (lane == 0 && warp == W_MMA) ? 7 : (lane == 0 && warp == W_MMA2) ? 8 : -1);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[D_XFULL], 1);

@@ -645,7 +645,8 @@ constexpr uint32_t DQ_SMEM = QOFF_BAR + 256;
 static_assert(QOFF_BAR == 229376 && DQ_SMEM <= SMEM_LIMIT, "dQ kernel shared memory");
 constexpr uint32_t QTM_G1 = 0, QTM_G2 = 128, QTM_ACC = 256, QTM_DS = 384;
 constexpr uint32_t IDESC_G128 = instr_desc(128, 128, 0, 0);
-enum { D_XFULL = 0, D_UFULL = 1, D_UEMPTY = 3, D_WFULL = 5, D_WEMPTY = 6, D_GFULL = 7, D_GFREE = 8, D_DSFULL = 9, D_DSFREE = 11, D_DONE = 13 };
+enum { D_XFULL = 0, D_UFULL = 1, D_UEMPTY = 3, D_WFULL = 5, D_WEMPTY = 6, D_G1FULL = 7, D_G1FREE = 8, D_G2FULL = 9, D_G2FREE = 10, D_DSFULL = 11, D_DSFREE = 13,
+       D_DONE = 15 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
@@ -656,14 +657,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
     volatile uint64_t* bits_ring = reinterpret_cast<volatile uint64_t*>(sm + QOFF_BITS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, r0 = q_begin + blockIdx.x * 128;      // first query of this CTA
     const int row_base = b * T;
     const int n_tiles = (T + QT - 1) / QT;
-    Tracer tracer(threadIdx.x == 0 ? 5 : (lane == 0 && warp == W_PRODUCER) ? 6 : (lane == 0 && warp == W_MMA) ? 7 : (lane == 0 && warp == W_MMA2) ? 8 : -1);
+    Tracer tracer(threadIdx.x == 0 ? 5 : (lane == 0 && warp == W_PRODUCER) ? 6 : (lane == 0 && warp == W_MMA) ? 7 : -1);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[D_XFULL], 1);
@@ -675,8 +676,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         }
         mbar_init(&bars[D_WFULL], 1);
         mbar_init(&bars[D_WEMPTY], 1);
-        mbar_init(&bars[D_GFULL], 1);
-        mbar_init(&bars[D_GFREE], ROW_THREADS);
+        mbar_init(&bars[D_G1FULL], 1);
+        mbar_init(&bars[D_G1FREE], ROW_THREADS);
+        mbar_init(&bars[D_G2FULL], 1);
+        mbar_init(&bars[D_G2FREE], ROW_THREADS);
         mbar_init(&bars[D_DONE], 1);
         mbar_fence_init();
     }
@@ -726,75 +729,72 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             }
             __syncwarp();
         }
-    } else if (warp == W_MMA || warp == W_MMA2) {
+    } else if (warp == W_MMA) {
+        // One issuer, in the order  S_j , dS_{j-1}.K_{j-1} , dP_j : the accumulating product runs as soon as its dS exists instead of
+        // queueing behind a whole tile of score MMAs, which frees its K buffer one score GEMM earlier -- the K ring is only two deep.
         if (lane == 0) {
             const uint32_t aX = smem_u32(sm + QOFF_X), aY = smem_u32(sm + QOFF_Y), aU = smem_u32(sm + QOFF_U), aW = smem_u32(sm + QOFF_W);
-            if (warp == W_MMA) {
-                mbar_wait(&bars[D_XFULL], 0);
-                for (int j = 0; j < n_tiles; ++j) {
-                    const int s = j & 1;
-                    TR(20, j);
-                    mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
-                    TR(21, j);
-                    if (j >= 1) mbar_wait(&bars[D_GFREE], (j - 1) & 1);
-                    TR(22, j);
-                    tc_fence_after();
+            auto issue_G = [&](uint32_t st, uint32_t tp, uint32_t dst) {
+                uint32_t acc = 0;
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {                   // g = 0: Q.[K_hi;K_lo]^T, g = 1: dO.[V_hi;V_lo]^T
-                        if (g == 1) {
-                            TR(23, j);
-                            mbar_wait(&bars[D_WFULL], j & 1);
-                            TR(24, j);
-                            tc_fence_after();
-                        }
-                        const uint32_t st = g == 0 ? aX : aY;
-                        const uint32_t tp = g == 0 ? aU + s * Q_TILE : aW;
-                        uint32_t acc = 0;
+                for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
 #pragma unroll
-                        for (int pl = 0; pl < 2; ++pl)              // A = stationary hi, then lo, into the same 128 columns
-#pragma unroll
-                            for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    tc_mma(tmem + (g == 0 ? QTM_G1 : QTM_G2), smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024),
-                                           smem_desc(tp + kb * 16384 + ks * 32, 16, 1024), IDESC_G128, acc);
-                                    acc = 1;
-                                }
-                    }
-                    tc_commit(&bars[D_GFULL]);
-                    tc_commit(&bars[D_WEMPTY]);
-                    TR(25, j);
-                }
-            } else {
-                for (int j = 0; j < n_tiles; ++j) {
-                    const int s = j & 1, pb = j & 1;
-                    mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);        // this issuer observes the TMA completion itself
-                    TR(26, j);
-                    mbar_wait(&bars[D_DSFULL + pb], (j >> 1) & 1);
-                    TR(27, j);
-                    tc_fence_after();
-                    const uint32_t tl = aU + s * Q_TILE;
-                    const uint32_t ds = tmem + QTM_DS + pb * 64;
-                    uint32_t acc = j > 0 ? 1u : 0u;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a = ds + (pass == 2 ? 32 : 0);               // dS hi, hi, lo
-                        const uint32_t bb = tl + (pass == 1 ? 8192 : 0);            // K hi, lo, hi
+                    for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            // K tile as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step = 2048 bytes
-                            tc_mma_ts(tmem + QTM_ACC, a + ks * 8, smem_desc(bb + ks * 2048, 16384, 1024), IDESC_ACC, acc);
+                            tc_mma(dst, smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024), smem_desc(tp + kb * 16384 + ks * 32, 16, 1024), IDESC_G128, acc);
                             acc = 1;
                         }
+            };
+            auto issue_acc = [&](int j) {
+                const int s = j & 1, pb = j & 1;
+                TR(26, j);
+                mbar_wait(&bars[D_DSFULL + pb], (j >> 1) & 1);
+                TR(27, j);
+                tc_fence_after();
+                const uint32_t tl = aU + s * Q_TILE;
+                const uint32_t ds = tmem + QTM_DS + pb * 64;
+                uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = ds + (pass == 2 ? 32 : 0);               // dS hi, hi, lo
+                    const uint32_t bb = tl + (pass == 1 ? 8192 : 0);            // K hi, lo, hi
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        // K tile as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step = 2048 bytes
+                        tc_mma_ts(tmem + QTM_ACC, a + ks * 8, smem_desc(bb + ks * 2048, 16384, 1024), IDESC_ACC, acc);
+                        acc = 1;
                     }
-                    tc_commit(&bars[D_DSFREE + pb]);
-                    tc_commit(&bars[D_UEMPTY + s]);
-                    TR(28, j);
                 }
-                tc_commit(&bars[D_DONE]);
+                tc_commit(&bars[D_DSFREE + pb]);
+                tc_commit(&bars[D_UEMPTY + s]);
+                TR(28, j);
+            };
+            mbar_wait(&bars[D_XFULL], 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j & 1;
+                TR(20, j);
+                mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
+                if (j >= 1) mbar_wait(&bars[D_G1FREE], (j - 1) & 1);
+                TR(21, j);
+                tc_fence_after();
+                issue_G(aX, aU + s * Q_TILE, tmem + QTM_G1);
+                tc_commit(&bars[D_G1FULL]);
+                TR(22, j);
+                if (j >= 1) issue_acc(j - 1);
+                mbar_wait(&bars[D_WFULL], j & 1);
+                if (j >= 1) mbar_wait(&bars[D_G2FREE], (j - 1) & 1);
+                TR(24, j);
+                tc_fence_after();
+                issue_G(aY, aW, tmem + QTM_G2);
+                tc_commit(&bars[D_G2FULL]);
+                tc_commit(&bars[D_WEMPTY]);
+                TR(25, j);
             }
+            issue_acc(n_tiles - 1);
+            tc_commit(&bars[D_DONE]);
         }
-    } else {
+    } else if (warp < 8) {
         // ------------------------------------------------------------------ row warps: thread = (query row, 32 of the 64 keys)
         const int q = warp & 3, h = warp >> 2;
         const int row = q * 32 + lane;
@@ -809,35 +809,41 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         for (int j = 0; j < n_tiles; ++j) {
             const int pb = j & 1;
             TR(30, j);
-            mbar_wait(&bars[D_GFULL], j & 1);
+            mbar_wait(&bars[D_G1FULL], j & 1);
             TR(31, j);
             tc_fence_after();
-            float g1[32], g2[32];
+            float pr[32];
             {
                 float t[32];
-                tmem_ld32(lane_addr + QTM_G1 + h * 32, g1);
+                tmem_ld32(lane_addr + QTM_G1 + h * 32, pr);
                 tmem_ld32(lane_addr + QTM_G1 + 64 + h * 32, t);
+                tc_fence_before();
+                mbar_arrive(&bars[D_G1FREE]);
+                const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
 #pragma unroll
-                for (int c = 0; c < 32; ++c) g1[c] += t[c];
+                for (int c = 0; c < 32; ++c) {
+                    const bool ok = row_ok && !((bad >> c) & 1u);
+                    pr[c] = ok ? ex2_approx(fmaf(pr[c] + t[c], SC2, -row_lse2)) : 0.f;
+                }
+            }
+            TR(32, j);
+            mbar_wait(&bars[D_G2FULL], j & 1);
+            TR(33, j);
+            tc_fence_after();
+            uint32_t dh[16], dl[16];
+            {
+                float g2[32], t[32];
                 tmem_ld32(lane_addr + QTM_G2 + h * 32, g2);
                 tmem_ld32(lane_addr + QTM_G2 + 64 + h * 32, t);
+                tc_fence_before();
+                mbar_arrive(&bars[D_G2FREE]);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) g2[c] += t[c];
+                for (int c = 0; c < 16; ++c) {
+                    const float d0 = pr[2 * c] * (g2[2 * c] + t[2 * c] - row_delta) * SM_SCALE;
+                    const float d1 = pr[2 * c + 1] * (g2[2 * c + 1] + t[2 * c + 1] - row_delta) * SM_SCALE;
+                    split2(d0, d1, dh[c], dl[c]);
+                }
             }
-            tc_fence_before();
-            mbar_arrive(&bars[D_GFREE]);
-            TR(32, j);
-            const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
-            uint32_t dh[16], dl[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const bool ok0 = row_ok && !((bad >> (2 * c)) & 1u), ok1 = row_ok && !((bad >> (2 * c + 1)) & 1u);
-                const float p0 = ex2_approx(fmaf(g1[2 * c], SC2, -row_lse2)), p1 = ex2_approx(fmaf(g1[2 * c + 1], SC2, -row_lse2));
-                const float d0 = ok0 ? p0 * (g2[2 * c] - row_delta) * SM_SCALE : 0.f;
-                const float d1 = ok1 ? p1 * (g2[2 * c + 1] - row_delta) * SM_SCALE : 0.f;
-                split2(d0, d1, dh[c], dl[c]);
-            }
-            TR(33, j);
             if (j >= 2) mbar_wait(&bars[D_DSFREE + pb], ((j >> 1) - 1) & 1);     // dS.K of tile j-2 is done with this buffer
             TR(34, j);
             tc_fence_after();

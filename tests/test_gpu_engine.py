@@ -230,3 +230,64 @@ def test_full_size_set_cover_step_vs_oracle(cuda, mode):
     feas, objv, violv = restate.feasibility_int(fd["xbits"].cpu().numpy(), inst.rows, inst.cols, inst.a_int, inst.M, inst.b_int, inst.c_int)
     assert np.array_equal(fd["viol_int"].cpu().numpy(), violv) and np.array_equal(fd["obj_int"].cpu().numpy(), objv)
     assert np.array_equal(fd["penalty"].cpu().numpy() <= 1e-5, feas)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_independent_set_config_step_vs_oracle(cuda, mode):
+    """configs[2] shapes scaled to a seconds-long oracle run: Independent Set (2 non-zeros per edge row + singleton rows, M > n),
+    n < L so a third of the tokens are padding, TWO denoiser layers like the shipped IS checkpoint, gs = 2e4, lambda = 0.5."""
+    from dip_b200.engine import Engine
+    from oracle import restate
+    TOL = TOLS[mode]
+    n, L, B = 600, 900, 3
+    inst = synth.independent_set(n_nodes=n, n_edges=1900, n_single=n, seed=5)
+    mip = synth.mip_features(L, n, seed=15)
+    kpm = np.zeros(L, dtype=bool); kpm[n:] = True
+    x = synth.initial_noise(5, range(B), L)
+    Wd, Wdec = synth.denoiser_weights(2, seed=3), synth.decoder_weights(2, seed=4)
+    eng = Engine()
+    eng.set_precision(mode)
+    eng.set_denoiser(tw(Wd, cuda)); eng.set_decoder(tw(Wdec, cuda))
+    eng.set_instance(torch.from_numpy(mip).to(cuda), torch.from_numpy(kpm).to(cuda), inst.rows, inst.cols, inst.a_val, inst.M, inst.b, inst.c,
+                     a_int=inst.a_int, b_int=inst.b_int, c_int=inst.c_int)
+    S, gs, lam = 100, 2e4, 0.5
+    tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], S)
+    A = (torch.from_numpy(inst.rows), torch.from_numpy(inst.cols), torch.from_numpy(inst.a_val), inst.M)
+    mipB, kpmB = torch.from_numpy(mip)[None].repeat(B, 1, 1), torch.from_numpy(kpm)[None].repeat(B, 1)
+    for index in (0, 57):
+        ref = restate.guided_ddim_step(tw(Wd), tw(Wdec), torch.from_numpy(x), S - 1 - index, restate.ddim_step_coeffs(tab, index), mipB, kpmB, A,
+                                       torch.from_numpy(inst.b), torch.from_numpy(inst.c), gs, lam)
+        xg = torch.from_numpy(x).to(cuda).clone()
+        x0 = torch.empty_like(xg)
+        grad, p_full, viol, obj = eng.guidance_grad(xg, lam)
+        assert rel_l2(p_full, ref["p_full"]) < TOL and float(p_full[:, n:].abs().max()) == 0.0
+        assert rel_l2(grad[:, :n], ref["grad"][:, :n]) < TOL
+        assert float(grad[:, n:].abs().max()) == 0.0 and float(ref["grad"][:, n:].abs().max()) == 0.0      # padding tokens get no gradient
+        eng.guided_ddim_step(xg, coeffs(S, index), gs, lam, x0_out=x0)
+        assert rel_l2(x0[:, :n], ref["x0"][:, :n]) < TOL and rel_l2(xg[:, :n], ref["x_prev"][:, :n]) < TOL
+    fd = eng.final_decode(ref["x_prev"].to(cuda))
+    ofd = restate.final_decode(tw(Wdec), mipB, ref["x_prev"], kpmB, A, torch.from_numpy(inst.b))
+    safe = ((ofd["p"] - 0.5).abs() > 1e-4).numpy()
+    assert np.array_equal(fd["xbits"].cpu().numpy()[safe], ofd["x_int"].numpy().astype(np.uint8)[safe])
+    feas, objv, violv = restate.feasibility_int(fd["xbits"].cpu().numpy(), inst.rows, inst.cols, inst.a_int, inst.M, inst.b_int, inst.c_int)
+    assert np.array_equal(fd["viol_int"].cpu().numpy(), violv) and np.array_equal(fd["obj_int"].cpu().numpy(), objv)
+
+
+def test_facility_location_length_tc_vs_fp32(cuda):
+    """configs[3]'s longest sequence (CF: L = 5050, decoder sequence 10100; too slow for the CPU oracle inside the test budget): the
+    tensor-core path against the fp32 SIMT path of the same engine -- which the other tests tie to the oracle -- on one guided step."""
+    from dip_b200.engine import Engine
+    inst, mip, kpm, x = sc_case(L=5050, n=5050, M=600, density=0.004, B=1, seed=9)
+    Wd, Wdec = synth.denoiser_weights(1, seed=1), synth.decoder_weights(2, seed=2)
+    out = {}
+    for mode in MODES:
+        eng = Engine()
+        eng.set_precision(mode)
+        eng.set_denoiser(tw(Wd, cuda)); eng.set_decoder(tw(Wdec, cuda))
+        eng.set_instance(torch.from_numpy(mip).to(cuda), torch.from_numpy(kpm).to(cuda), inst.rows, inst.cols, inst.a_val, inst.M, inst.b, inst.c)
+        xg = torch.from_numpy(x).to(cuda).clone()
+        grad, p_full, _, _ = eng.guidance_grad(xg, 0.7)
+        eng.guided_ddim_step(xg, coeffs(100, 0), 1e3, 0.7)
+        out[mode] = (grad.clone(), p_full.clone(), xg)
+    for a, r in zip(out["tc"], out["fp32"]):
+        assert rel_l2(a, r) < 1e-3, rel_l2(a, r)

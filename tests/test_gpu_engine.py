@@ -291,3 +291,33 @@ def test_facility_location_length_tc_vs_fp32(cuda):
         out[mode] = (grad.clone(), p_full.clone(), xg)
     for a, r in zip(out["tc"], out["fp32"]):
         assert rel_l2(a, r) < 1e-3, rel_l2(a, r)
+
+
+def test_toy_instance_end_to_end_known_answers(cuda):
+    """The reference's toy instance (15 binaries, 25 rows) through the whole path -- lpio.make_instance -> engine -> S guided DDIM
+    steps -> decode -> round -> integer check -- with every returned flag / objective looked up in the brute-forced table of all
+    2^15 assignments (1118 feasible, optimum 8)."""
+    import itertools
+    import os
+    from dip_b200 import lpio, schedule
+    from dip_b200.engine import Engine
+    from oracle import restate
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "toy_is15.npz"))
+    inst = lpio.make_instance([str(s) for s in d["names"]], d["rows"], d["cols"], d["vals"], d["b"], (-d["c"]).astype(np.int32), sense=-1)
+    n, L, B, S = inst.n, 16, 64, 10
+    X = np.array(list(itertools.product((0, 1), repeat=n)), np.int64)
+    feas_tab, obj_tab, viol_tab = restate.feasibility_int(X, inst.rows, inst.cols, inst.a_int, inst.M, inst.b_int, inst.c_int)
+    assert feas_tab.sum() == 1118 and obj_tab[feas_tab].min() == -8
+    mip = synth.mip_features(L, n, seed=21)
+    kpm = np.zeros(L, dtype=bool); kpm[n:] = True
+    eng = Engine()
+    eng.set_denoiser(tw(synth.denoiser_weights(1, seed=1), cuda)); eng.set_decoder(tw(synth.decoder_weights(2, seed=2), cuda))
+    eng.set_instance(torch.from_numpy(mip).to(cuda), torch.from_numpy(kpm).to(cuda), inst.rows, inst.cols, inst.a_val, inst.M, inst.b, inst.c,
+                     a_int=inst.a_int, b_int=inst.b_int, c_int=inst.c_int)
+    x = torch.from_numpy(synth.initial_noise(3, range(B), L)).to(cuda)
+    out = eng.sample_guided_ddim(x, schedule.ddim_coeffs(S), 2e4, 0.5)
+    bits = out["xbits"].cpu().numpy().astype(np.int64)
+    idx = (bits * (1 << np.arange(n - 1, -1, -1))).sum(1)               # row of X holding this assignment
+    assert np.array_equal(X[idx], bits)
+    assert np.array_equal(out["viol_int"].cpu().numpy(), viol_tab[idx]) and np.array_equal(out["obj_int"].cpu().numpy(), obj_tab[idx])
+    assert np.array_equal(out["penalty"].cpu().numpy() <= 1e-5, feas_tab[idx])

@@ -169,3 +169,80 @@ def test_state_dict_layouts_load_synthetic_weights():
     missing, unexpected = cm.load_state_dict(t(synth.encoder_weights()), strict=False)
     assert not unexpected and all(k.startswith("sol_encoder") or k == "logit_scale" for k in missing)
     assert len(cm.state_dict()) == 84 and sum(v.numel() for v in cm.state_dict().values()) == 598707
+
+
+def test_partial_solution_handoff_matches_reference_loop():
+    """The hand-off of sample_partialsol.py:172-199 restated inline (same module-level `random` stream, same pred_x[0, k] quirk,
+    same membership test) against dip_b200.handoff, plus the bit-packed round trip."""
+    import random
+    from dip_b200 import handoff
+    rng = np.random.default_rng(3)
+    B, n, coverage = 5, 37, 0.2
+    pred_x = rng.integers(0, 2, size=(B, n)).astype(np.float32)
+    names = ["x%d" % k for k in range(n)]
+    random.seed(11)
+    ref = []
+    num_vars = int(pred_x.shape[1] * coverage)
+    for j in range(pred_x.shape[0]):
+        sol_val = {}
+        for k, name in enumerate(names):
+            sol_val[name] = int(pred_x[0, k])                         # sic: sample 0 for every j
+        selected_vars = random.sample(range(pred_x.shape[1]), num_vars)
+        ref.append({name: sol_val[name] for k, name in enumerate(names) if k in selected_vars})
+    random.seed(11)
+    got = handoff.partial_solutions(pred_x, names, coverage)
+    assert got == ref and all(len(d) == num_vars for d in got)
+    random.seed(11)
+    own = handoff.partial_solutions(pred_x, names, coverage, reference_quirk=False)
+    assert [set(d) for d in own] == [set(d) for d in ref]             # same selections, own values
+    assert all(own[j][nm] == int(pred_x[j, names.index(nm)]) for j in range(B) for nm in own[j])
+    r2 = random.Random(5)
+    sels = [handoff.select_variables(n, coverage, r2) for _ in range(B)]
+    vals, mask = handoff.pack(pred_x, sels)
+    assert vals.shape == (B, 5) and mask.shape == (B, 5)
+    back = handoff.unpack(vals, mask, n)
+    assert back == [{int(k): int(pred_x[j, k]) for k in sorted(sels[j])} for j in range(B)]
+    with pytest.raises(ValueError):
+        handoff.partial_solutions(pred_x, names[:-1], coverage)
+
+
+def test_lp_and_mps_ingestion_known_answers_and_round_trip():
+    """dip_b200.lpio on the reference's toy instance (rebuilt as LP text from tests/golden/toy_is15.npz): parse -> same matrix,
+    brute-forced known answers (1118 feasible, optimum 8, 4 optimal); LP round trip; MPS twin; '>=' and '=' rows; error paths."""
+    import itertools
+    from dip_b200 import lpio
+    from oracle import restate
+    d = np.load(os.path.join(ROOT, "tests", "golden", "toy_is15.npz"))
+    names = [str(s) for s in d["names"]]
+    n, M = len(names), len(d["b"])
+    # the toy file maximises sum x: write it that way and let the parser turn it into minimisation
+    lines = ["Maximize", " Obj: " + " ".join("+1 %s" % v for v in names), "Subject to"]
+    for i in range(M):
+        e = np.flatnonzero(d["rows"] == i)
+        lines.append(" c_%d: %s <= +%d" % (i, " ".join("%+d %s" % (d["vals"][k], names[d["cols"][k]]) for k in e), d["b"][i]))
+    lines += ["Bounds"] + [" 0 <= %s <= 1" % v for v in names] + ["Binaries", " " + " ".join(names), "End"]
+    inst = lpio.parse_lp("\n".join(lines))
+    assert inst.n == n and inst.M == M and inst.sense == -1 and inst.var_names == names
+    dense = np.zeros((M, n), np.int64); np.add.at(dense, (inst.rows, inst.cols), inst.a_int)
+    ref = np.zeros((M, n), np.int64); np.add.at(ref, (d["rows"], d["cols"]), d["vals"])
+    assert np.array_equal(dense, ref) and np.array_equal(inst.b_int, d["b"]) and np.array_equal(inst.c_int, -d["c"])
+    X = np.array(list(itertools.product((0, 1), repeat=n)), np.int64)
+    feas, obj, viol = restate.feasibility_int(X, inst.rows, inst.cols, inst.a_int, M, inst.b_int, inst.c_int)
+    assert feas.sum() == 1118 and obj[feas].min() == -8 and (feas & (obj == -8)).sum() == 4
+    assert np.allclose(inst.constraint_features[:, 0], inst.b) and np.allclose(inst.variable_features[:, 0], inst.c)
+    back = lpio.parse_lp(lpio.write_lp(inst))
+    for k in ("rows", "cols", "a_int", "b_int", "c_int"):
+        assert np.array_equal(getattr(back, k), getattr(inst, k)), k
+    mps = ["NAME toy", "ROWS", " N obj", " L r1", " G r2", " E r3", "COLUMNS", " MARKER 'MARKER' 'INTORG'", " x obj 2 r1 1", " x r2 1", " y obj -1 r1 1",
+           " y r3 1", " z r2 1 r3 1", " MARKER 'MARKER' 'INTEND'", "RHS", " rhs r1 1 r2 1", " rhs r3 1", "BOUNDS", " BV bnd x", " BV bnd y", " BV bnd z", "ENDATA"]
+    m = lpio.parse_mps("\n".join(mps))
+    assert m.var_names == ["x", "y", "z"] and m.M == 4 and list(m.b_int) == [1, -1, 1, -1] and list(m.c_int) == [2, -1, 0]
+    dm = np.zeros((4, 3), np.int64); np.add.at(dm, (m.rows, m.cols), m.a_int)
+    assert np.array_equal(dm, [[1, 1, 0], [-1, 0, -1], [0, 1, 1], [0, -1, -1]])
+    lp2 = lpio.parse_lp("Minimize\n obj: 2 x - y\nSubject to\n r1: x + y <= 1\n r2: x + z >= 1\n r3: y + z = 1\nBinaries\n x y z\nEnd\n")
+    for k in ("rows", "cols", "a_int", "b_int", "c_int"):
+        assert np.array_equal(getattr(lp2, k), getattr(m, k)), k
+    with pytest.raises(ValueError):
+        lpio.parse_lp("Minimize\n obj: x\nSubject to\n r: 0.5 x <= 1\nBinaries\n x\nEnd\n")
+    with pytest.raises(ValueError):
+        lpio.parse_lp("Minimize\n obj: x\nSubject to\n r: x <= 1\nGenerals\n x\nEnd\n")

@@ -334,7 +334,11 @@ def main():
                     "d2h_bytes_per_step": B * inst.n + B * 4 + B * 16, "feasible_ratio": float(cnt[1]) / total_samples},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "attn_bwd_tc_kernel<key-stationary> (decoder attention backward: dP, dV, dK; tcgen05)", "bound": "tensor", "achieved": achieved,
-                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                         # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_dkdv_summary.txt: mean of the two
+                         # decoder layers' launches at wave 37, SC shapes); algorithmic bytes of the launch are ~400 MB, i.e. no DRAM re-reads
+                         "traffic": 315.1e6 if (B == 37 and L == 2000) else None,
+                         "ceiling_note": "3 bf16 MMA passes per fp32-grade product: attainable ceiling = peak/3",
                          "peak_source": pk["src"] + ", sustained bf16", "launch_ms": avg_ms,
                          "share_of_step": dk["ms"] / total_prof_ms if total_prof_ms > 0 else None},
             "kernel_time_share": {k: (v["ms"] / total_prof_ms if total_prof_ms > 0 else 0.0) for k, v in prof.items()},

@@ -321,3 +321,29 @@ def test_toy_instance_end_to_end_known_answers(cuda):
     assert np.array_equal(X[idx], bits)
     assert np.array_equal(out["viol_int"].cpu().numpy(), viol_tab[idx]) and np.array_equal(out["obj_int"].cpu().numpy(), obj_tab[idx])
     assert np.array_equal(out["penalty"].cpu().numpy() <= 1e-5, feas_tab[idx])
+
+
+@pytest.mark.parametrize("L,n,M,B", [(130, 130, 9, 1), (130, 97, 40, 5), (65, 64, 3, 41), (200, 1, 2, 2)])
+def test_ragged_shapes_and_degenerate_rows(cuda, L, n, M, B):
+    """Edge cases around the kernels' tile sizes and the sparse passes: L not a multiple of 32/64/128, no padding and heavy padding,
+    a single integer variable, an empty constraint row, an all-zero objective, duplicate COO entries (summed like coalesce()), a wave
+    larger than the SM count / cluster size -- one guided step against the oracle, tensor-core mode."""
+    from dip_b200.engine import Engine
+    from oracle import restate
+    cs = small_case(seed=L + n, L=L, n=n, M=M, nnz=max(4, 3 * M), B=B, dup=2)
+    cs.rows[cs.rows == M - 1] = 0                      # row M-1 is empty
+    cs.c[:] = 0.0                                      # objective without any weight
+    eng = Engine()
+    Wd, Wdec = synth.denoiser_weights(1, seed=1), synth.decoder_weights(2, seed=2)
+    eng.set_denoiser(tw(Wd, cuda)); eng.set_decoder(tw(Wdec, cuda))
+    eng.set_instance(torch.from_numpy(cs.mip).to(cuda), torch.from_numpy(cs.kpm).to(cuda), cs.rows, cs.cols, cs.vals, cs.M, cs.b, cs.c)
+    S, gs, lam = 100, 1e3, 0.3
+    tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], S)
+    t = case_tensors(cs)
+    ref = restate.guided_ddim_step(tw(Wd), tw(Wdec), t["x"], S - 1, restate.ddim_step_coeffs(tab, 0), t["mipB"], t["kpmB"], coalesced(cs), t["b"], t["c"], gs, lam)
+    xg = t["x"].to(cuda).clone()
+    grad, p_full, viol, obj = eng.guidance_grad(xg, lam)
+    assert rel_l2(p_full, ref["p_full"]) < 1e-3 and rel_l2(grad[:, :n], ref["grad"][:, :n]) < 1e-3
+    assert float(obj.abs().max()) == 0.0
+    eng.guided_ddim_step(xg, coeffs(S, 0), gs, lam)
+    assert rel_l2(xg[:, :n], ref["x_prev"][:, :n]) < 1e-3

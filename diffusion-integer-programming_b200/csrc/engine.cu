@@ -135,6 +135,7 @@ struct Workspace {
     // denoiser
     float *hd, *tmp, *tmp2, *qkv1, *ao1;
     void *qkv1_hi, *qkv1_lo, *do_hi, *do_lo;
+    void *ln_hi, *ln_lo;     // bf16 planes of LayerNorm(x), the A operand of the in-projection (tensor-core mode)
     // decoder
     LayerSave ls[MAX_LAYERS];
     float *h, *h2;
@@ -155,6 +156,8 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
     w.ao1 = c.take<float>(R1 * D);
     w.qkv1_hi = c.take<uint16_t>(R1 * 3 * D);
     w.qkv1_lo = c.take<uint16_t>(R1 * 3 * D);
+    w.ln_hi = c.take<uint16_t>((R1 > R2 ? R1 : R2) * D);
+    w.ln_lo = c.take<uint16_t>((R1 > R2 ? R1 : R2) * D);
     for (int l = 0; l < e->n_dec; ++l) {
         LayerSave& s = w.ls[l];
         s.mean1 = c.take<float>(R2); s.rstd1 = c.take<float>(R2);
@@ -235,8 +238,8 @@ static void window(dip_gemm_args& g, int B, int T, int w) {
 // win > 0 (tensor-core mode only): the caller will use the output tokens t >= win only (the decoder keeps the last L of
 // its 2L tokens, model/decoder.py:45), so in the last layer just those tokens act as queries and go through the
 // out-projection and the MLP; keys and values still cover the whole sequence.
-static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, float* qkv, void* qkv_hi,
-                     void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
+static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, void* ln_hi, void* ln_lo, float* qkv,
+                     void* qkv_hi, void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
                      int B, int T, int win, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
@@ -244,8 +247,14 @@ static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float
     if (!tc) win = 0;
     // q|k|v = LN1(x) . W_in^T + b_in   (tensor-core mode: only the bf16 planes are written)
     dip_gemm_args g = gemm(nullptr, D, tc ? nullptr : qkv, 3 * D, R, 3 * D, D, w.in_b, DIP_ACT_NONE);
-    if (tc) { g.split_hi = qkv_hi; g.split_lo = qkv_lo; }
-    DIP_TRY(linear(mode, g, w.in_w, &xin, w.ln1_w, w.ln1_b, mean1, rstd1, h, st));
+    if (tc) {
+        // LayerNorm once into bf16 planes, then a TMA-fed GEMM: the three column blocks share the normalised rows
+        g.split_hi = qkv_hi; g.split_lo = qkv_lo;
+        DIP_TRY(dip_layernorm_split(ln_hi, ln_lo, mean1, rstd1, xin, w.ln1_w, w.ln1_b, R, st));
+        DIP_TRY(dip_gemm_tc_planes(&g, ln_hi, ln_lo, w.in_w.hi, w.in_w.lo, st));
+    } else {
+        DIP_TRY(linear(mode, g, w.in_w, &xin, w.ln1_w, w.ln1_b, mean1, rstd1, h, st));
+    }
     if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, win, st));
     else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
     // x_mid = x + attn . W_out^T + b_out
@@ -351,7 +360,7 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     g = gemm(w.tmp, D, w.hd, D, R1, D, D, e->b2, DIP_ACT_NONE);
     DIP_TRY(linear(e->mode, g, e->w2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     for (int l = 0; l < e->n_den; ++l)
-        DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
+        DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.ln_hi, w.ln_lo, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
                           nullptr, nullptr, nullptr, nullptr, e->mask_den, B, T1, 0, st));
     return 0;
 }
@@ -364,7 +373,7 @@ static int decode(dip_engine* e, const Workspace& w, const float* x, int B, dip_
         if (l == 0) { xin.shared = e->inst.mip; xin.batch = x; xin.T = T2; xin.split = L; }
         else xin = plain_rows(w.ls[l - 1].xout, T2);
         const LayerSave& s = w.ls[l];
-        DIP_TRY(block_fwd(e->mode, e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, s.qkv, s.qkv_hi, s.qkv_lo, s.ao, s.lse, s.mean1, s.rstd1, s.mean2,
+        DIP_TRY(block_fwd(e->mode, e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, w.ln_hi, w.ln_lo, s.qkv, s.qkv_hi, s.qkv_lo, s.ao, s.lse, s.mean1, s.rstd1, s.mean2,
                           s.rstd2, s.u, e->mask_dec, B, T2, l == e->n_dec - 1 ? L : 0, st));
     }
     DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, e->inst.kpm, st));

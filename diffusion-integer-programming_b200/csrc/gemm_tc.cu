@@ -179,9 +179,13 @@ __device__ __forceinline__ void epi_finish(const Params& P, const EpiIn& e, int 
 constexpr int N_LOADERS = 8, W_MMA = 0, W_EPI = N_LOADERS, N_EPI = 8, N_THREADS = (N_LOADERS + N_EPI) * 32;      // 16 warps: 128 registers each
 constexpr int RPW = 128 / N_LOADERS;      // rows of a tile per loader warp, loaded in batches of 16
 
-template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT>
+// APL = true: A arrives as ready-made bf16 hi/lo planes (dip_layernorm_split) and is fetched by TMA straight into the MMA layout --
+// no loader warps.  Used by the q|k|v in-projection, whose three column CTAs per row tile would otherwise each repeat the row
+// loads, the LayerNorm and the split.
+template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT, bool APL>
 __global__ void __launch_bounds__(N_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Params P) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const __grid_constant__ CUtensorMap tm_a_hi,
+               const __grid_constant__ CUtensorMap tm_a_lo, const Params P) {
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
     uint8_t* sW = sm + OFF_W;
@@ -198,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (threadIdx.x == 0) {
         mbar_init(&bars[G_WFULL], 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[G_AFULL + s], N_LOADERS * 32);
+            mbar_init(&bars[G_AFULL + s], APL ? 1 : N_LOADERS * 32);
             mbar_init(&bars[G_AEMPTY + s], 1);
             mbar_init(&bars[G_CFULL + s], 1);
             mbar_init(&bars[G_CEMPTY + s], N_EPI * 32);
@@ -261,6 +265,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             TR(12, ti);
         };
         int it = 0;
+        if (APL) {
+            if (issuer) {
+                const int n_it = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                for (int itx = 0; itx <= n_it; ++itx) {
+                    if (itx < n_it) {
+                        const int s = itx & 1, tile = blockIdx.x + itx * gridDim.x;
+                        if (itx >= 2) mbar_wait(&bars[G_AEMPTY + s], ((itx >> 1) - 1) & 1);
+                        mbar_expect_tx(&bars[G_AFULL + s], A_STAGE);
+                        for (int kb = 0; kb < 2; ++kb) {        // rows past M are zero-filled by the tensor map
+                            tma_load_2d(sm + s * A_STAGE + kb * 16384, &tm_a_hi, &bars[G_AFULL + s], kb * 64, tile * 128);
+                            tma_load_2d(sm + s * A_STAGE + A_PLANE + kb * 16384, &tm_a_lo, &bars[G_AFULL + s], kb * 64, tile * 128);
+                        }
+                    }
+                    if (itx >= 1) mma_issue(itx - 1);
+                }
+            }
+        } else {
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
 #pragma unroll 1
             for (int kc = 0; kc < KCH; ++kc, ++it) {
@@ -318,6 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             }
         }
         if (issuer && it > 0) mma_issue(it - 1);
+        }
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp % 4; the two warps of a
@@ -391,18 +413,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (warp == W_MMA) tmem_dealloc(tmem, 2 * BN);
 }
 
-template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT>
-static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const Params& P, int n_blocks_y, cudaStream_t st) {
+template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT, bool APL = false>
+static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const CUtensorMap& ahi, const CUtensorMap& alo, const Params& P, int n_blocks_y, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        DIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<KCH, BN, LN, ROWOPS, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<KCH, BN, LN, ROWOPS, ACT, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr = true;
     }
     int gx = sm_count() / n_blocks_y;
     if (gx < 1) gx = 1;
     if (gx > P.n_tiles) gx = P.n_tiles;
     dim3 grid(gx, n_blocks_y);
-    gemm_tc_kernel<KCH, BN, LN, ROWOPS, ACT><<<grid, N_THREADS, SMEM_BYTES, st>>>(whi, wlo, P);
+    gemm_tc_kernel<KCH, BN, LN, ROWOPS, ACT, APL><<<grid, N_THREADS, SMEM_BYTES, st>>>(whi, wlo, ahi, alo, P);
     return 0;
 }
 
@@ -483,7 +505,7 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     const int variant = (g.K == 128 ? (ln_gamma ? 1 : 0) : 2) * 4 + (rowops ? 2 : 0) + (act ? 1 : 0);
     const int ny = g.N / BN;
     switch (variant) {
-#define DIP_GEMM_CASE(v, KCH, BNv, LNv, RO, AC) case v: DIP_TRY((tcgemm::launch<KCH, BNv, LNv, RO, AC>(whi, wlo, P, ny, st))); break;
+#define DIP_GEMM_CASE(v, KCH, BNv, LNv, RO, AC) case v: DIP_TRY((tcgemm::launch<KCH, BNv, LNv, RO, AC>(whi, wlo, whi, wlo, P, ny, st))); break;
         DIP_GEMM_CASE(0, 1, 128, false, false, false) DIP_GEMM_CASE(1, 1, 128, false, false, true)
         DIP_GEMM_CASE(2, 1, 128, false, true, false)  DIP_GEMM_CASE(3, 1, 128, false, true, true)
         DIP_GEMM_CASE(4, 1, 128, true, false, false)  DIP_GEMM_CASE(5, 1, 128, true, false, true)
@@ -493,6 +515,37 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
 #undef DIP_GEMM_CASE
         default: DIP_FAIL("dip_gemm_tc: no kernel variant %d", variant);
     }
+    DIP_LAUNCHED();
+    return 0;
+}
+
+/* C = A . W^T + bias with A given as bf16 hi/lo planes (M,128) -- see include/dip_b200.h. */
+int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, dip_stream_t stream) {
+    DIP_REQUIRE(args && a_hi && a_lo && w_hi && w_lo, "dip_gemm_tc_planes: null argument");
+    const dip_gemm_args& g = *args;
+    DIP_REQUIRE(g.M > 0 && g.K == 128 && g.N % 128 == 0, "dip_gemm_tc_planes: needs K == 128 and N %% 128 == 0 (K=%d N=%d)", g.K, g.N);
+    DIP_REQUIRE(g.C || g.split_hi || g.preact, "dip_gemm_tc_planes: no output");
+    DIP_REQUIRE(g.ldc % 4 == 0 && (g.split_hi == nullptr) == (g.split_lo == nullptr), "dip_gemm_tc_planes: bad ldc / split planes");
+    DIP_REQUIRE(!g.row_bias_scale && !g.addmat && !g.res.batch && !g.aux && g.act == DIP_ACT_NONE && g.rows_in == 0 && g.in_T == 0,
+                "dip_gemm_tc_planes: bias-only epilogue (no row operands, activation, row maps)");
+    float* zeros = nullptr;
+    DIP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&zeros), tcgemm::g_zeros));
+    DIP_REQUIRE(g.bias || g.N <= 4 * 128, "dip_gemm_tc_planes: N too large for the zero block");
+    tcgemm::Params P;
+    memset(&P, 0, sizeof(P));
+    P.M = g.M; P.N = g.N; P.n_tiles = cdiv(g.M, 128); P.act = DIP_ACT_NONE;
+    P.a_T = tcgemm::make_fastdiv(tcgemm::BIG); P.in_rows = tcgemm::make_fastdiv(tcgemm::BIG);
+    P.rows_in = tcgemm::make_fastdiv(tcgemm::BIG); P.res_T = tcgemm::make_fastdiv(tcgemm::BIG);
+    P.bias = g.bias ? g.bias : zeros;
+    P.addmat = zeros; P.res_shared = zeros; P.res_batch = zeros; P.aux = zeros;
+    P.C = g.C; P.preact = g.preact; P.split_hi = g.split_hi; P.split_lo = g.split_lo; P.ldc = g.ldc;
+    CUtensorMap whi, wlo, ahi, alo;
+    DIP_TRY(make_tmap_bf16_2d(&whi, w_hi, g.N, 128, 128, 128, 64));
+    DIP_TRY(make_tmap_bf16_2d(&wlo, w_lo, g.N, 128, 128, 128, 64));
+    DIP_TRY(make_tmap_bf16_2d(&ahi, a_hi, g.M, 128, 128, 128, 64));
+    DIP_TRY(make_tmap_bf16_2d(&alo, a_lo, g.M, 128, 128, 128, 64));
+    DIP_PROF(DIP_PROF_GEMM, stream);
+    DIP_TRY((tcgemm::launch<1, 128, false, false, false, true>(whi, wlo, ahi, alo, P, g.N / 128, as_stream(stream))));
     DIP_LAUNCHED();
     return 0;
 }

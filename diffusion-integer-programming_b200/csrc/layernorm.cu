@@ -1,6 +1,6 @@
 // LayerNorm over 128 features (model/modules.py:280,288), forward and input-gradient backward.
 // One warp per row, one float4 per lane; HBM-bound streaming kernels.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dip {
 
@@ -60,6 +60,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(float* __restrict__ dx, con
     }
 }
 
+// y = LayerNorm(x) written as bf16 hi/lo planes (rows, 128): the A operand of dip_gemm_tc_planes
+__global__ void __launch_bounds__(256) ln_split_kernel(uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                       const dip_rows x, const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 g = reinterpret_cast<const float4*>(gamma)[lane], b = reinterpret_cast<const float4*>(beta)[lane];
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float4 v = reinterpret_cast<const float4*>(row_ptr(x, r))[lane];
+        const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);
+        const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+        const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
+        float rs = rsqrtf(var + 1e-5f);
+        rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
+        const float y0 = dx * rs * g.x + b.x, y1 = dy * rs * g.y + b.y, y2 = dz * rs * g.z + b.z, y3 = dw * rs * g.w + b.w;
+        uint32_t h0, l0, h1, l1;
+        tc::split2(y0, y1, h0, l0);
+        tc::split2(y2, y3, h1, l1);
+        hi[r * 32 + lane] = make_uint2(h0, h1);
+        lo[r * 32 + lane] = make_uint2(l0, l1);
+        if (mean_out && lane == 0) { mean_out[r] = mu; rstd_out[r] = rs; }
+    }
+}
+
 static int ln_grid(int64_t rows) {
     int64_t blocks = (rows + 7) / 8;   // 8 warps per CTA
     int64_t cap = (int64_t)sm_count() * 8;
@@ -81,6 +105,17 @@ int dip_layernorm_fwd(float* y, float* mean, float* rstd, dip_rows x, const floa
     DIP_REQUIRE(x.split == 0 || (x.shared && x.T > x.split), "dip_layernorm_fwd: bad row source");
     DIP_PROF(DIP_PROF_LN, stream);
     ln_fwd_kernel<<<ln_grid(rows), 256, 0, as_stream(stream)>>>(y, mean, rstd, x, gamma, beta, rows);
+    DIP_LAUNCHED();
+    return 0;
+}
+
+int dip_layernorm_split(void* hi, void* lo, float* mean, float* rstd, dip_rows x, const float* gamma, const float* beta, int64_t rows,
+                        dip_stream_t stream) {
+    DIP_REQUIRE(hi && lo && x.batch && gamma && beta && rows > 0, "dip_layernorm_split: bad argument");
+    DIP_REQUIRE((mean == nullptr) == (rstd == nullptr), "dip_layernorm_split: mean and rstd go together");
+    DIP_REQUIRE(x.split == 0 || (x.shared && x.T > x.split), "dip_layernorm_split: bad row source");
+    DIP_PROF(DIP_PROF_LN, stream);
+    ln_split_kernel<<<ln_grid(rows), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), mean, rstd, x, gamma, beta, rows);
     DIP_LAUNCHED();
     return 0;
 }

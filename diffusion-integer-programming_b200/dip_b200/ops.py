@@ -307,3 +307,37 @@ def block_forward(x, w, key_mask=None):
     h = layernorm_fwd(xm, w["ln_2.weight"], w["ln_2.bias"])
     g = gemm_nt(h, w["mlp.c_fc.weight"], w["mlp.c_fc.bias"], act="quickgelu")
     return gemm_nt(g, w["mlp.c_proj.weight"], w["mlp.c_proj.bias"], res=xm).view(B, T, D)
+
+
+def layernorm_split(x, gamma, beta, shared=None, T=0, split=0, rows=None, want_stats=False):
+    """LayerNorm(x) as bf16 (hi, lo) planes (rows, 128); x optionally two-source like layernorm_fwd."""
+    lib = _lib.load()
+    x = _f32(x)
+    rows = x.numel() // D if rows is None else rows
+    dev = x.device
+    hi = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+    mean = torch.empty(rows, dtype=torch.float32, device=dev) if want_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev) if want_stats else None
+    r = Rows(ptr(shared), ptr(x), int(T), int(split))
+    check(lib.dip_layernorm_split(ptr(hi), ptr(lo), ptr(mean), ptr(rstd), r, ptr(_f32(gamma)), ptr(_f32(beta)), rows, _stream()))
+    return hi, lo, mean, rstd
+
+
+def gemm_tc_planes(a_hi, a_lo, W, bias=None, want_c=True, want_split=False):
+    """tcgen05 Linear whose A operand is given as bf16 (hi, lo) planes (M, 128)."""
+    lib = _lib.load()
+    W = _f32(W, "W")
+    N, K = W.shape
+    M = a_hi.shape[0]
+    w_hi, w_lo = split_bf16(W)
+    dev = a_hi.device
+    out = torch.empty((M, N), dtype=torch.float32, device=dev) if want_c else None
+    hi = torch.empty((M, N), dtype=torch.bfloat16, device=dev) if want_split else None
+    lo = torch.empty((M, N), dtype=torch.bfloat16, device=dev) if want_split else None
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.bias, g.C, g.ldc = None, K, None, ptr(bias), ptr(out), N
+    g.M, g.N, g.K, g.act = M, N, K, ACT[None]
+    g.split_hi, g.split_lo = ptr(hi), ptr(lo)
+    check(lib.dip_gemm_tc_planes(C.byref(g), ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), _stream()))
+    return {"C": out, "hi": hi, "lo": lo}

@@ -180,6 +180,16 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
  * d_o / o / lse are never read); dq is written for t >= q_begin only (q_begin >= do_begin); dk, dv for t >= k_begin
  * only.  Unwritten rows keep their previous content. */
 
+/* LayerNorm(x) (model/modules.py:280,288) written as the bf16 (hi, lo) planes of its result, (rows,128) each: the A operand of
+ * dip_gemm_tc_planes.  The q|k|v in-projection uses this pair instead of the fused-LayerNorm dip_gemm_tc: its three 128-column
+ * blocks run on different CTAs, which would each repeat the row loads, the LayerNorm and the split. */
+int dip_layernorm_split(void* hi, void* lo, float* mean, float* rstd, dip_rows x, const float* gamma, const float* beta,
+                        int64_t rows, dip_stream_t stream);
+/* C = A . W^T + bias on tcgen05 with A given as bf16 (hi, lo) planes (M,128), fetched by TMA straight into the MMA layout.
+ * K == 128, N % 128 == 0, bias-only epilogue; outputs as in dip_gemm_args (C / preact / split planes). */
+int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                       dip_stream_t stream);
+
 /* dip_gemm_nt on tcgen05 (bf16x2-split operands): w_hi / w_lo are the bf16 planes of the (N,K) weight
  * (dip_split_bf16 of the nn.Linear weight).  K must be 128 or 384.  Extras over dip_gemm_nt:
  *   a_rows   (nullable) two-source A rows (K == 128), replaces args->A;

@@ -228,3 +228,24 @@ def test_gemm_tc_row_window(cuda):
     ref3 = (A3.double() @ W3.double().t()).view(B, T, D)
     got3 = out3.view(B, T, D)
     assert rel_l2(got3[:, w:], ref3[:, w:]) < 2e-5 and float((got3[:, :w] + 1.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,T,split,N", [(3, 70, 30, 384), (1, 129, 0, 128), (2, 1000, 500, 384)])
+def test_layernorm_split_and_planes_gemm(cuda, B, T, split, N):
+    """The in-projection path of the tensor-core mode: LayerNorm written once as bf16 planes, then the TMA-fed Linear."""
+    from dip_b200 import ops
+    shared = rnd((max(split, 1), D), 0, 2.0)
+    batch = rnd((B, T - split, D), 1, 2.0)
+    gamma, beta = 1 + 0.1 * rnd((D,), 2), 0.1 * rnd((D,), 3)
+    W, bias = rnd((N, D), 4, 0.1), rnd((N,), 5)
+    x = (torch.cat([shared[None, :split].expand(B, -1, -1), batch], dim=1) if split else batch).reshape(B * T, D).double()
+    h = F.layer_norm(x, (D,), gamma.double(), beta.double(), 1e-5)
+    hi, lo, mean, rstd = ops.layernorm_split(batch.to(cuda), gamma.to(cuda), beta.to(cuda), shared=shared.to(cuda) if split else None, T=T, split=split,
+                                             rows=B * T, want_stats=True)
+    assert rel_l2(hi.float() + lo.float(), h) < 1e-5
+    assert rel_l2(mean, x.mean(-1)) < 1e-5 and rel_l2(rstd, 1.0 / torch.sqrt(x.var(-1, unbiased=False) + 1e-5)) < 1e-5
+    out = ops.gemm_tc_planes(hi, lo, W.to(cuda), bias.to(cuda), want_split=True)
+    ref = h @ W.double().t() + bias.double()
+    assert rel_l2(out["C"], ref) < 2e-5, rel_l2(out["C"], ref)
+    assert rel_l2(out["hi"].float() + out["lo"].float(), out["C"]) < 1e-5
+    assert torch.equal(out["C"], ops.gemm_tc_planes(hi, lo, W.to(cuda), bias.to(cuda))["C"])

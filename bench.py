@@ -280,19 +280,29 @@ def main():
     host_x = [torch.empty((B, L, D), dtype=torch.float32).pin_memory() for _ in range(K)]
     for k in range(K):
         host_x[k].copy_(noise(20_000 + k).cpu())
-    host_out = {"xbits": torch.empty((B, inst.n), dtype=torch.uint8).pin_memory(), "penalty": torch.empty(B, dtype=torch.float32).pin_memory(),
+    def host_bufs():
+        return {"xbits": torch.empty((B, inst.n), dtype=torch.uint8).pin_memory(), "penalty": torch.empty(B, dtype=torch.float32).pin_memory(),
                 "viol_int": torch.empty(B, dtype=torch.int64).pin_memory(), "obj_int": torch.empty(B, dtype=torch.int64).pin_memory()}
+    host_out = [host_bufs(), host_bufs()]                 # double-buffered: wave k is read back while wave k+1 is already queued
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     n_feas_e2e = 0
+
+    def collect(k):
+        done[k & 1].synchronize()
+        return int((host_out[k & 1]["viol_int"] == 0).sum())
+
     for k in range(K):
-        xd = host_x[k].to(dev, non_blocking=True)
+        xd = host_x[k].to(dev, non_blocking=True)                         # H2D of this wave's inputs (pinned)
         o = eng.sample_guided_ddim(xd, steps, args.gs, args.lam)
-        for nm in host_out:
-            host_out[nm].copy_(o[nm], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        n_feas_e2e += int((host_out["viol_int"] == 0).sum())
+        for nm in host_out[k & 1]:
+            host_out[k & 1][nm].copy_(o[nm], non_blocking=True)           # D2H of this wave's result
+        done[k & 1].record()
+        if k >= 1:
+            n_feas_e2e += collect(k - 1)                                  # host reads wave k-1 while the GPU runs wave k
+    n_feas_e2e += collect(K - 1)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -314,9 +324,11 @@ def main():
         pk = peaks()
         den, dec_f, dec_b = step_flops(L)
         T2 = 2 * L
-        # dominant kernel: key-stationary attention backward (dK, dV, dP products): 6*T^2*D algorithmic FLOPs per sample-layer
+        # dominant kernel: key-stationary attention backward (dK, dV, dP products): 6*Tq*Tk*D algorithmic FLOPs per sample-layer.
+        # With the row windows each decoder layer's launch pairs 2L keys with the L live queries (last layer) or L keys with 2L
+        # queries (layer 0): Tq*Tk = 2L*L for both -- the dead half the reference computes is not counted as achieved work.
         dk = prof["attn_bwd_dkdv"]
-        flops_per_launch = 6.0 * T2 * T2 * D * B
+        flops_per_launch = 6.0 * T2 * L * D * B
         avg_ms = dk["ms"] / max(dk["launches"], 1)
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
         upd, gd = prof["update"], prof["guidance"]
@@ -330,6 +342,7 @@ def main():
                        "precision_mode": "attention and Linear layers on tcgen05 tensor cores with bf16x2-split fp32 operands (hi*hi + hi*lo + lo*hi, fp32 TMEM accumulation; one-step latent error ~1e-5 rel vs the fp32 reference); guidance, DDIM update, rounding and the integer feasibility check in fp32/int64 SIMT"},
             "feasible_per_s": float(cnt[0]) / (ms / 1e3), "feasible_ratio": float(cnt[0]) / total_samples,
             "tflops_effective": (den + dec_f + dec_b) * S * total_samples / (ms / 1e3) / 1e12,
+            "tflops_effective_note": "reference-equivalent FLOPs (SURVEY 8d: what the reference executes per sample-step, dead tokens included) / time",
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * L * D * 4,
                     "d2h_bytes_per_step": B * inst.n + B * 4 + B * 16, "feasible_ratio": float(cnt[1]) / total_samples},
             "gpu_launches": int(launches),
@@ -338,7 +351,8 @@ def main():
                          # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_dkdv_summary.txt: mean of the two
                          # decoder layers' launches at wave 37, SC shapes); algorithmic bytes of the launch are ~400 MB, i.e. no DRAM re-reads
                          "traffic": 315.1e6 if (B == 37 and L == 2000) else None,
-                         "ceiling_note": "3 bf16 MMA passes per fp32-grade product: attainable ceiling = peak/3",
+                         "ceiling_note": "fp32-grade products cost 3 bf16 MMA passes and the launch recomputes S (8 executed per 6 credited products): "
+                                         "attainable ceiling = peak * (1/3) * (6/8) = 0.25 of the bf16 peak",
                          "peak_source": pk["src"] + ", sustained bf16", "launch_ms": avg_ms,
                          "share_of_step": dk["ms"] / total_prof_ms if total_prof_ms > 0 else None},
             "kernel_time_share": {k: (v["ms"] / total_prof_ms if total_prof_ms > 0 else 0.0) for k, v in prof.items()},

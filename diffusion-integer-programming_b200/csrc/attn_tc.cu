@@ -873,6 +873,268 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// backward, dK / dV: key-stationary with 64-query tiles
+// =============================================================================================
+// Same idea as the dQ kernel, for the pass that needs two accumulators.  Tensor memory is the tight resource: dV and dK take 256
+// columns, the packed P / dS operands of a 64-query tile 128, which leaves 128 -- one score tile.  So S^T and dP^T share ONE
+// region and are formed one after the other; the accumulating products of the PREVIOUS tile are issued in between and keep the
+// tensor pipe busy while the row threads drain the region:
+//      S^T_j  |  dV += P_{j-1}^T dO_{j-1}  |  dK += dS_{j-1}^T Q_{j-1}  |  dP^T_j  |  S^T_{j+1} ...
+// Shared memory: K hi/lo, V hi/lo stationary (128 KB) | Q ring 2 x 32 KB (needed until dK of its tile) | dO 32 KB, single-buffered
+// (its reload hides behind the dK product).  Score MMAs are N = 128 (64 queries, hi and lo stacked): 73 cycles for twice the work
+// of the N = 64 MMAs (67 cycles) the 32-query version had to use.
+// tensor memory: [0,128) S^T / dP^T (X.U_hi | X.U_lo), [128,256) P hi, P lo, dS hi, dS lo (32 packed columns each),
+//                [256,384) dV, [384,512) dK
+constexpr uint32_t KTM_G = 0, KTM_PD = 128, KTM_ACC1 = 256, KTM_ACC2 = 384;
+enum { E_XFULL = 0, E_UFULL = 1, E_UEMPTY = 3, E_WFULL = 5, E_WEMPTY = 6, E_G1FULL = 7, E_G1FREE = 8, E_G2FULL = 9, E_G2FREE = 10, E_PFULL = 11, E_PFREE = 12,
+       E_DSFULL = 13, E_DSFREE = 14, E_DONE = 15 };
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
+                      const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64,
+                      const __grid_constant__ CUtensorMap tm_do_hi64, const __grid_constant__ CUtensorMap tm_do_lo64, float* __restrict__ dv,
+                      float* __restrict__ dk, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
+                      const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int k_begin, int q_begin) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    require_aligned_smem(sm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    volatile uint64_t* bits_ring = reinterpret_cast<volatile uint64_t*>(sm + QOFF_BITS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, r0 = k_begin + blockIdx.x * 128;      // first key of this CTA
+    const int row_base = b * T;
+    const int n_tiles = (T - q_begin + QT - 1) / QT;                // queries q_begin .. T-1 are streamed
+    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : -1);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[E_XFULL], 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars[E_UFULL + s], 1);
+            mbar_init(&bars[E_UEMPTY + s], 1);
+        }
+        mbar_init(&bars[E_WFULL], 1);
+        mbar_init(&bars[E_WEMPTY], 1);
+        mbar_init(&bars[E_G1FULL], 1);
+        mbar_init(&bars[E_G1FREE], ROW_THREADS);
+        mbar_init(&bars[E_G2FULL], 1);
+        mbar_init(&bars[E_G2FREE], ROW_THREADS);
+        mbar_init(&bars[E_PFULL], ROW_THREADS);
+        mbar_init(&bars[E_PFREE], 1);
+        mbar_init(&bars[E_DSFULL], ROW_THREADS);
+        mbar_init(&bars[E_DSFREE], 1);
+        mbar_init(&bars[E_DONE], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
+
+    if (warp == W_PRODUCER) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[E_XFULL], 4 * ST_PLANE);
+            for (int kb = 0; kb < 2; ++kb) {
+                tma_load_3d(sm + QOFF_X + kb * 16384, &tm_qkv_hi128, &bars[E_XFULL], 128 + kb * 64, r0, b);                 // K hi
+                tma_load_3d(sm + QOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[E_XFULL], 128 + kb * 64, r0, b);      // K lo
+                tma_load_3d(sm + QOFF_Y + kb * 16384, &tm_qkv_hi128, &bars[E_XFULL], 256 + kb * 64, r0, b);                 // V hi
+                tma_load_3d(sm + QOFF_Y + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[E_XFULL], 256 + kb * 64, r0, b);      // V lo
+            }
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j & 1;
+            const int q0 = q_begin + j * QT;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, q0 + lane >= T), b1 = __ballot_sync(0xffffffffu, q0 + 32 + lane >= T);
+            if (lane == 0) {
+                TR(40, j);
+                if (j >= 2) mbar_wait(&bars[E_UEMPTY + s], ((j >> 1) - 1) & 1);
+                TR(41, j);
+                bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);
+                mbar_expect_tx(&bars[E_UFULL + s], Q_TILE);
+                uint8_t* du = sm + QOFF_U + s * Q_TILE;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(du + kb * 16384, &tm_qkv_hi64, &bars[E_UFULL + s], kb * 64, q0, b);               // Q hi, d-half kb
+                    tma_load_3d(du + kb * 16384 + 8192, &tm_qkv_lo64, &bars[E_UFULL + s], kb * 64, q0, b);        // Q lo
+                }
+                TR(42, j);
+                if (j >= 1) mbar_wait(&bars[E_WEMPTY], (j - 1) & 1);
+                TR(43, j);
+                mbar_expect_tx(&bars[E_WFULL], Q_TILE);
+                uint8_t* dw = sm + QOFF_W;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(dw + kb * 16384, &tm_do_hi64, &bars[E_WFULL], kb * 64, q0, b);                    // dO hi
+                    tma_load_3d(dw + kb * 16384 + 8192, &tm_do_lo64, &bars[E_WFULL], kb * 64, q0, b);             // dO lo
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == W_MMA) {
+        if (lane == 0) {
+            const uint32_t aX = smem_u32(sm + QOFF_X), aY = smem_u32(sm + QOFF_Y), aU = smem_u32(sm + QOFF_U), aW = smem_u32(sm + QOFF_W);
+            auto issue_G = [&](uint32_t st, uint32_t tp) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            tc_mma(tmem + KTM_G, smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024), smem_desc(tp + kb * 16384 + ks * 32, 16, 1024),
+                                   IDESC_G128, acc);
+                            acc = 1;
+                        }
+            };
+            auto issue_acc = [&](uint32_t dst, uint32_t a_cols, uint32_t tile, uint32_t first) {
+                uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = tmem + KTM_PD + a_cols + (pass == 2 ? 32 : 0);       // A hi, hi, lo (32 packed columns per plane)
+                    const uint32_t bb = tile + (pass == 1 ? 8192 : 0);                      // B hi, lo, hi
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        // streamed tile as MN-major B: d-halves 16384 bytes apart, 16 queries per k-step = 2048 bytes
+                        tc_mma_ts(dst, a + ks * 8, smem_desc(bb + ks * 2048, 16384, 1024), IDESC_ACC, acc);
+                        acc = 1;
+                    }
+                }
+            };
+            mbar_wait(&bars[E_XFULL], 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j & 1;
+                TR(20, j);
+                mbar_wait(&bars[E_UFULL + s], (j >> 1) & 1);
+                if (j >= 1) mbar_wait(&bars[E_G2FREE], (j - 1) & 1);
+                TR(21, j);
+                tc_fence_after();
+                issue_G(aX, aU + s * Q_TILE);                                        // S^T_j
+                tc_commit(&bars[E_G1FULL]);
+                TR(22, j);
+                if (j >= 1) {                                                        // dK += dS_{j-1}^T Q_{j-1}
+                    mbar_wait(&bars[E_DSFULL], (j - 1) & 1);
+                    tc_fence_after();
+                    issue_acc(tmem + KTM_ACC2, 64, aU + ((j - 1) & 1) * Q_TILE, j == 1);
+                    tc_commit(&bars[E_UEMPTY + ((j - 1) & 1)]);
+                    tc_commit(&bars[E_DSFREE]);
+                    TR(23, j);
+                }
+                mbar_wait(&bars[E_WFULL], j & 1);
+                mbar_wait(&bars[E_G1FREE], j & 1);
+                TR(24, j);
+                tc_fence_after();
+                issue_G(aY, aW);                                                     // dP^T_j
+                tc_commit(&bars[E_G2FULL]);
+                TR(25, j);
+                mbar_wait(&bars[E_PFULL], j & 1);                                    // dV += P_j^T dO_j : frees the dO buffer one product early
+                tc_fence_after();
+                issue_acc(tmem + KTM_ACC1, 0, aW, j == 0);
+                tc_commit(&bars[E_WEMPTY]);
+                tc_commit(&bars[E_PFREE]);
+                TR(28, j);
+            }
+            mbar_wait(&bars[E_DSFULL], (n_tiles - 1) & 1);
+            tc_fence_after();
+            issue_acc(tmem + KTM_ACC2, 64, aU + ((n_tiles - 1) & 1) * Q_TILE, n_tiles == 1);
+            tc_commit(&bars[E_DONE]);
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------------ row warps: thread = (key row, 32 of the 64 queries)
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const int r_idx = r0 + row;
+        bool row_ok = r_idx < T;
+        if (row_ok && mrow && mrow[r_idx]) row_ok = false;          // masked key: its column of P is zero
+        for (int j = 0; j < n_tiles; ++j) {
+            // lane l fetches lse and delta of query h*32 + l of this tile; broadcast by shuffle below
+            const int cq = q_begin + j * QT + h * 32 + lane;
+            float q_lse2 = 0.f, q_delta = 0.f;
+            if (cq < T) {
+                q_lse2 = __ldg(lse + (int64_t)row_base + cq) * LOG2E;
+                q_delta = __ldg(delta + (int64_t)row_base + cq);
+            }
+            TR(30, j);
+            mbar_wait(&bars[E_G1FULL], j & 1);
+            TR(31, j);
+            tc_fence_after();
+            float pr[32];
+            uint32_t ph[16], pl[16];
+            {
+                float t[32];
+                tmem_ld32(lane_addr + KTM_G + h * 32, pr);
+                tmem_ld32(lane_addr + KTM_G + 64 + h * 32, t);
+                tc_fence_before();
+                mbar_arrive(&bars[E_G1FREE]);
+                const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float l2 = __shfl_sync(0xffffffffu, q_lse2, c);
+                    const bool ok = row_ok && !((bad >> c) & 1u);
+                    pr[c] = ok ? ex2_approx(fmaf(pr[c] + t[c], SC2, -l2)) : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) split2(pr[2 * c], pr[2 * c + 1], ph[c], pl[c]);
+            }
+            if (j >= 1) mbar_wait(&bars[E_PFREE], (j - 1) & 1);       // P_{j-1}^T dO_{j-1} has read the P columns
+            tc_fence_after();
+            tmem_st16(lane_addr + KTM_PD + h * 16, ph);
+            tmem_st16(lane_addr + KTM_PD + 32 + h * 16, pl);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[E_PFULL]);
+            TR(32, j);
+            mbar_wait(&bars[E_G2FULL], j & 1);
+            TR(33, j);
+            tc_fence_after();
+            uint32_t dh[16], dl[16];
+            {
+                float g2[32], t[32];
+                tmem_ld32(lane_addr + KTM_G + h * 32, g2);
+                tmem_ld32(lane_addr + KTM_G + 64 + h * 32, t);
+                tc_fence_before();
+                mbar_arrive(&bars[E_G2FREE]);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float dl0 = __shfl_sync(0xffffffffu, q_delta, 2 * c), dl1 = __shfl_sync(0xffffffffu, q_delta, 2 * c + 1);
+                    const float d0 = pr[2 * c] * (g2[2 * c] + t[2 * c] - dl0) * SM_SCALE;
+                    const float d1 = pr[2 * c + 1] * (g2[2 * c + 1] + t[2 * c + 1] - dl1) * SM_SCALE;
+                    split2(d0, d1, dh[c], dl[c]);
+                }
+            }
+            if (j >= 1) mbar_wait(&bars[E_DSFREE], (j - 1) & 1);      // dS_{j-1}^T Q_{j-1} has read the dS columns
+            TR(34, j);
+            tc_fence_after();
+            tmem_st16(lane_addr + KTM_PD + 64 + h * 16, dh);
+            tmem_st16(lane_addr + KTM_PD + 96 + h * 16, dl);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[E_DSFULL]);
+            TR(35, j);
+        }
+        mbar_wait(&bars[E_DONE], 0);
+        tc_fence_after();
+        const bool store_ok = r_idx < T;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float* dst = (g == 0 ? dv : dk) + ((int64_t)row_base + r_idx) * ld_d + h * 64;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float t[32];
+                tmem_ld32(lane_addr + (g == 0 ? KTM_ACC1 : KTM_ACC2) + h * 64 + ch * 32, t);
+                if (store_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // delta[row] = o[row] . dO[row] for the rows t >= begin of every sample (rows = B * (T - begin))
 __global__ void __launch_bounds__(256) delta_kernel(float* __restrict__ delta, const float* __restrict__ o, const float* __restrict__ d_o, int64_t rows,
                                                     int T, int begin) {
@@ -985,7 +1247,7 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
                 "dip_attn_bwd_tc: need 0 <= do_begin <= q_begin < T and 0 <= k_begin < T (got %d, %d, %d)", do_begin, q_begin, k_begin);
     static bool attr = false;
     if (!attr) {
-        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::BWD_SMEM));
+        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
         attr = true;
     }
@@ -1000,6 +1262,9 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     DIP_TRY(make_tmap_bf16_3d(&q_lo32, qkv_lo, B, T, 3 * D, 3 * D, 32, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_hi128, do_hi, B, T, D, D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_lo128, do_lo, B, T, D, D, 128, 64));
+    CUtensorMap d_hi64, d_lo64;
+    DIP_TRY(make_tmap_bf16_3d(&d_hi64, do_hi, B, T, D, D, 64, 64));
+    DIP_TRY(make_tmap_bf16_3d(&d_lo64, do_lo, B, T, D, D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_hi32, do_hi, B, T, D, D, 32, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_lo32, do_lo, B, T, D, D, 32, 64));
     {
@@ -1012,8 +1277,8 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     {
         dim3 grid(cdiv(T - k_begin, 128), B);      // keys k_begin.. stationary, queries do_begin.. streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DKDV, stream);
-        tcattn::attn_bwd_tc_kernel<true><<<grid, tcattn::NTHREADS, tcattn::BWD_SMEM, st>>>(q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32,
-                                                                                           d_lo32, dv, dk, ld_d, lse, delta_ws, key_mask, mask_stride, T, k_begin, do_begin);
+        tcattn::attn_bwd_kv_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, d_hi64, d_lo64, dv, dk, ld_d, lse,
+                                                                                       delta_ws, key_mask, mask_stride, T, k_begin, do_begin);
         DIP_LAUNCHED();
     }
     {

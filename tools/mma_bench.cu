@@ -7,6 +7,8 @@ namespace dip { void set_error(const char*, ...) {} std::atomic<uint64_t> g_laun
 using namespace dip::tc;
 
 // mode 0: A K-major SW128, B K-major SW128 (N rows);  mode 1: B MN-major SW128;  mode 2: A un-swizzled K-major, B MN-major
+// mode 3: A in tensor memory (TS) x MN-major B, d-halves 8192 bytes apart;  mode 4: the same with d-halves 16384 bytes apart;
+// mode 5: TS x K-major B
 template <int N, int MODE>
 __global__ void __launch_bounds__(128, 1) bench(long long* out, int n_mma, int same_acc) {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -30,6 +32,12 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int n_mma, int s
             else da = smem_desc(a0 + kb * 16384 + ks * 32, 16, 1024);
             if (MODE == 0) db = smem_desc(b0 + kb * (N * 128) + ks * 32, 16, 1024);
             else db = smem_desc(b0 + (i & 1) * 2048, 8192, 1024);
+            if (MODE >= 3) {
+                if (MODE == 3) db = smem_desc(b0 + (i & 3) * 2048, 8192, 1024);
+                if (MODE == 4) db = smem_desc(b0 + (i & 3) * 2048, 16384, 1024);
+                if (MODE == 5) db = smem_desc(b0 + kb * (N * 128) + ks * 32, 16, 1024);
+                tc_mma_ts(tmem + (same_acc ? 0 : (i & 1) * N), tmem + 256 + (i & 3) * 8, db, dip::tc::instr_desc(128, N, 0, MODE == 5 ? 0 : 1), i > 1);
+            } else
             tc_mma(tmem + (same_acc ? 0 : (i & 1) * N), da, db, idesc, i > 1);
         }
         long long t1 = clock64();
@@ -66,5 +74,10 @@ int main() {
     run<128, 1>("K-major A x MN-major B", d, 1);
     run<128, 1>("K-major A x MN-major B", d, 0);
     run<128, 2>("nosw A x MN-major B", d, 1);
+    run<128, 3>("TMEM A x MN-major B (LBO 8192)", d, 1);
+    run<128, 4>("TMEM A x MN-major B (LBO 16384)", d, 1);
+    run<128, 5>("TMEM A x K-major B", d, 1);
+    run<64, 5>("TMEM A x K-major B", d, 1);
+    run<64, 3>("TMEM A x MN-major B (LBO 8192)", d, 1);
     return 0;
 }

@@ -22,9 +22,9 @@
 //   warp 8    : TMA producer; its 32 lanes also ballot the key-padding mask of every streamed tile into a
 //               bit word, so the row warps never touch global memory inside the loop.
 //   warp 11   : (forward only) second TMA producer, for the V ring
-//   warps 9,10: one thread each issues tcgen05.mma / tcgen05.commit -- warp 9 the score GEMMs, warp 10 the
-//               accumulating GEMMs.  Issue is throttled to the tensor pipe's rate and every mbarrier wait costs
-//               ~250 cycles (measured, tools/ktrace.py); two issuers hide each other's waits.
+//   warps 9,10: MMA issue (one thread each).  Forward: warp 9 the score GEMMs, warp 10 the accumulating GEMMs -- issue is
+//               throttled to the tensor pipe's rate and an mbarrier wait costs up to ~250 cycles (tools/ktrace.py), two
+//               issuers hide each other's waits.  Backward kernels: warp 9 alone issues everything in an explicit order.
 #include <math.h>
 #include "tc_common.cuh"
 
@@ -356,284 +356,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
 // =============================================================================================
 // backward (input gradients only, deterministic: no atomics)
 // =============================================================================================
-// Two launches of one templated kernel, both with a 128-row stationary operand pair in shared memory
-// and 32-row streamed tiles (3-stage TMA ring):
-//   KS = true  (key-stationary)   rows = keys   : X = K, Y = V stationary; U = Q, W = dO streamed
-//        G1 = K Q^T (= S^T), G2 = V dO^T (= dP^T);  dV += P^T dO,  dK += dS^T Q
-//   KS = false (query-stationary) rows = queries: X = Q, Y = dO stationary; U = K, W = V streamed
-//        G1 = Q K^T (= S),   G2 = dO V^T (= dP);    dQ += dS K
-// P = exp(S/sqrt(d) - lse[query]) and dS = P (dP - delta[query]) / sqrt(d) are formed by the row warps and
-// written to tensor memory as the A operands of the accumulating GEMMs; the streamed tiles double as
-// their MN-major B operands.
-// shared memory: X hi/lo, Y hi/lo (128 KB) | ring of 3 stages x 32 KB, each U then W as [d-half][hi,lo][32 rows][64 d]
-//                (d-half kb: 64 stacked rows = B operand of a score MMA; plane p: two d-halves 8192 bytes apart = MN-major B)
-// tensor memory: [0,64) G1 (X.U_hi | X.U_lo), [64,128) G2, [128,256) acc1 (dV), [256,384) acc2 (dK / dQ),
-//                [384,512) two P/dS buffers of 64 columns: P hi, P lo, dS hi, dS lo (16 packed columns each)
-constexpr int BT = 32, TL_STAGES = 3;
+// Two kernels, each with a 128-row stationary operand pair in shared memory and 64-row streamed tiles:
+//   dQ    (query-stationary): Q, dO stationary; K, V streamed;   S = Q K^T, dP = dO V^T;       dQ += dS K
+//   dK/dV (key-stationary)  : K, V stationary; Q, dO streamed;   S^T = K Q^T, dP^T = V dO^T;   dV += P^T dO, dK += dS^T Q
+// P = exp(S/sqrt(d) - lse[query]) and dS = P (dP - delta[query]) / sqrt(d) are formed by the row warps and written to tensor memory
+// as the A operands of the accumulating GEMMs; the streamed tiles double as their MN-major B operands.  An earlier generic kernel
+// streamed 32-row tiles (score MMAs at N = 64): an MMA with N = 64 costs 67 cycles, one with N = 128 only 73 (the 128-row A operand
+// is fetched from shared memory either way), so the tensor pipe was < 50 % active (ncu) -- both kernels now use 64-row tiles.
 constexpr uint32_t ST_PLANE = 32768;           // stationary plane: [2][128][64] bf16
-constexpr uint32_t TL_HALF = 16384;            // U or W of one stage
-constexpr uint32_t TL_STAGE = 2 * TL_HALF;
-constexpr uint32_t BOFF_X = 0, BOFF_Y = 2 * ST_PLANE, BOFF_TL = 4 * ST_PLANE, BOFF_BAR = BOFF_TL + TL_STAGES * TL_STAGE, BOFF_BITS = BOFF_BAR + 192;
-constexpr uint32_t BWD_SMEM = BOFF_BAR + 256;
-static_assert(BOFF_BAR == 229376 && BWD_SMEM <= SMEM_LIMIT, "backward kernel shared memory");
-constexpr uint32_t TM_G1 = 0, TM_G2 = 64, TM_ACC1 = 128, TM_ACC2 = 256, TM_PD = 384;
-constexpr uint32_t IDESC_G = instr_desc(128, 2 * BT, 0, 0);   // X (K-major) x [U_hi;U_lo] (K-major) -> 128 x 64
-constexpr uint32_t IDESC_ACC = instr_desc(128, 128, 0, 1);    // P/dS (tensor memory) x U/W (MN-major) -> 128 x 128
-
-enum { C_XFULL = 0, C_TLFULL = 1, C_TLEMPTY = 4, C_GFULL = 7, C_GFREE = 8, C_PDFULL = 9, C_PDFREE = 11, C_DONE = 13 };
-
-template <bool KS>
-__global__ void __launch_bounds__(NTHREADS, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
-                   const __grid_constant__ CUtensorMap tm_qkv_hi32, const __grid_constant__ CUtensorMap tm_qkv_lo32,
-                   const __grid_constant__ CUtensorMap tm_do_hi128, const __grid_constant__ CUtensorMap tm_do_lo128,
-                   const __grid_constant__ CUtensorMap tm_do_hi32, const __grid_constant__ CUtensorMap tm_do_lo32,
-                   float* __restrict__ out1, float* __restrict__ out2, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
-                   const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int stat_begin, int str_begin) {
-    extern __shared__ __align__(1024) uint8_t sm[];
-    require_aligned_smem(sm);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BOFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-    volatile uint32_t* bits_ring = reinterpret_cast<volatile uint32_t*>(sm + BOFF_BITS);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // stationary rows stat_begin .. T-1 (one CTA per 128), streamed rows str_begin .. T-1: rows below the two bounds
-    // take no part (their dO is zero / their gradient is not wanted)
-    const int b = blockIdx.y, r0 = stat_begin + blockIdx.x * 128;      // first stationary row (key for KS, query otherwise)
-    const int row_base = b * T;
-    const int n_tiles = (T - str_begin + BT - 1) / BT;
-    Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[C_XFULL], 1);
-        for (int s = 0; s < TL_STAGES; ++s) { mbar_init(&bars[C_TLFULL + s], 1); mbar_init(&bars[C_TLEMPTY + s], 1); }
-        mbar_init(&bars[C_GFULL], 1);
-        mbar_init(&bars[C_GFREE], ROW_THREADS);
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars[C_PDFULL + s], ROW_THREADS); mbar_init(&bars[C_PDFREE + s], 1); }
-        mbar_init(&bars[C_DONE], 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    // column of the packed (q|k|v) planes each operand lives in
-    constexpr int COL_X = KS ? 128 : 0;      // K : Q
-    constexpr int COL_U = KS ? 0 : 128;      // Q : K
-    const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
-
-    if (warp == W_PRODUCER) {
-        const CUtensorMap* whi = KS ? &tm_do_hi32 : &tm_qkv_hi32;
-        const CUtensorMap* wlo = KS ? &tm_do_lo32 : &tm_qkv_lo32;
-        const int col_w = KS ? 0 : 256;  // dO : V
-        if (lane == 0) {
-            const CUtensorMap* yhi = KS ? &tm_qkv_hi128 : &tm_do_hi128;
-            const CUtensorMap* ylo = KS ? &tm_qkv_lo128 : &tm_do_lo128;
-            const int col_y = KS ? 256 : 0;  // V : dO
-            mbar_expect_tx(&bars[C_XFULL], 4 * ST_PLANE);
-            for (int kb = 0; kb < 2; ++kb) {
-                tma_load_3d(sm + BOFF_X + kb * 16384, &tm_qkv_hi128, &bars[C_XFULL], COL_X + kb * 64, r0, b);
-                tma_load_3d(sm + BOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[C_XFULL], COL_X + kb * 64, r0, b);
-                tma_load_3d(sm + BOFF_Y + kb * 16384, yhi, &bars[C_XFULL], col_y + kb * 64, r0, b);
-                tma_load_3d(sm + BOFF_Y + ST_PLANE + kb * 16384, ylo, &bars[C_XFULL], col_y + kb * 64, r0, b);
-            }
-        }
-        for (int j = 0; j < n_tiles; ++j) {
-            const int s = j % TL_STAGES;
-            // invalid streamed rows of this tile: beyond T, or (query-stationary: streamed rows are keys) masked keys
-            const int c = str_begin + j * BT + lane;
-            const bool bad = (c >= T) || (!KS && mrow && mrow[c]);
-            const uint32_t bits = __ballot_sync(0xffffffffu, bad);
-            if (lane == 0) {
-                TR(40, j);
-                if (j >= TL_STAGES) mbar_wait(&bars[C_TLEMPTY + s], ((j / TL_STAGES) - 1) & 1);
-                TR(41, j);
-                bits_ring[j & 7] = bits;
-                mbar_expect_tx(&bars[C_TLFULL + s], TL_STAGE);
-                uint8_t* dst = sm + BOFF_TL + s * TL_STAGE;
-                const int trow = str_begin + j * BT;
-                for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_3d(dst + kb * 8192, &tm_qkv_hi32, &bars[C_TLFULL + s], COL_U + kb * 64, trow, b);                // U hi, d-half kb
-                    tma_load_3d(dst + kb * 8192 + 4096, &tm_qkv_lo32, &bars[C_TLFULL + s], COL_U + kb * 64, trow, b);         // U lo
-                    tma_load_3d(dst + TL_HALF + kb * 8192, whi, &bars[C_TLFULL + s], col_w + kb * 64, trow, b);               // W hi
-                    tma_load_3d(dst + TL_HALF + kb * 8192 + 4096, wlo, &bars[C_TLFULL + s], col_w + kb * 64, trow, b);        // W lo
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp == W_MMA || warp == W_MMA2) {
-        if (lane == 0) {
-            const uint32_t aX = smem_u32(sm + BOFF_X), aY = smem_u32(sm + BOFF_Y), aTL = smem_u32(sm + BOFF_TL);
-            if (warp == W_MMA) mbar_wait(&bars[C_XFULL], 0);
-            auto issue_G = [&](int j) {
-                const int s = j % TL_STAGES;
-                TR(20, j);
-                mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);
-                TR(21, j);
-                if (j >= 1) mbar_wait(&bars[C_GFREE], (j - 1) & 1);
-                TR(22, j);
-                tc_fence_after();
-                const uint32_t tl = aTL + s * TL_STAGE;
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {                       // g = 0: X.[U_hi;U_lo]^T, g = 1: Y.[W_hi;W_lo]^T
-                    const uint32_t st = g == 0 ? aX : aY;
-                    const uint32_t tp = tl + g * TL_HALF;
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int pl = 0; pl < 2; ++pl)                  // A = stationary hi, then lo, into the same 64 columns
-#pragma unroll
-                        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                tc_mma(tmem + (g == 0 ? TM_G1 : TM_G2), smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024),
-                                       smem_desc(tp + kb * 8192 + ks * 32, 16, 1024), IDESC_G, acc);
-                                acc = 1;
-                            }
-                }
-                tc_commit(&bars[C_GFULL]);
-                TR(25, j);
-            };
-            auto issue_acc = [&](int j) {
-                const int s = j % TL_STAGES, pb = j & 1;
-                mbar_wait(&bars[C_TLFULL + s], (j / TL_STAGES) & 1);     // this issuer observes the TMA completion itself
-                TR(26, j);
-                mbar_wait(&bars[C_PDFULL + pb], (j >> 1) & 1);
-                TR(27, j);
-                tc_fence_after();
-                const uint32_t tl = aTL + s * TL_STAGE;
-                const uint32_t pd = tmem + TM_PD + pb * 64;
-#pragma unroll
-                for (int g = (KS ? 0 : 1); g < 2; ++g) {            // g = 0: acc1 += P.W (dV), g = 1: acc2 += dS.U (dK / dQ)
-                    const uint32_t tp = tl + (g == 0 ? TL_HALF : 0);
-                    uint32_t acc = j > 0 ? 1u : 0u;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a = pd + g * 32 + (pass == 2 ? 16 : 0);        // A hi, hi, lo (16 packed columns per plane)
-                        const uint32_t bb = tp + (pass == 1 ? 4096 : 0);              // B hi, lo, hi
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            // streamed tile as MN-major B: d-halves 8192 bytes apart, 16 rows per k-step = 2048 bytes
-                            tc_mma_ts(tmem + (g == 0 ? TM_ACC1 : TM_ACC2), a + ks * 8, smem_desc(bb + ks * 2048, 8192, 1024), IDESC_ACC, acc);
-                            acc = 1;
-                        }
-                    }
-                }
-                tc_commit(&bars[C_PDFREE + pb]);
-                tc_commit(&bars[C_TLEMPTY + s]);
-                TR(28, j);
-            };
-            if (warp == W_MMA) {
-                for (int j = 0; j < n_tiles; ++j) issue_G(j);
-            } else {
-                for (int j = 0; j < n_tiles; ++j) issue_acc(j);
-                tc_commit(&bars[C_DONE]);
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ row warps: thread = (stationary row, 16 of the 32 tile columns)
-        const int q = warp & 3, h = warp >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        const int r_idx = r0 + row;
-        bool row_ok = r_idx < T;
-        float row_lse2 = 0.f, row_delta = 0.f;
-        if (KS) {
-            if (row_ok && mrow && mrow[r_idx]) row_ok = false;      // masked key: its column of P is zero
-        } else if (row_ok) {
-            row_lse2 = lse[(int64_t)row_base + r_idx] * LOG2E;
-            row_delta = delta[(int64_t)row_base + r_idx];
-        }
-        for (int j = 0; j < n_tiles; ++j) {
-            const int pb = j & 1;
-            // key-stationary: lanes 0-15 fetch lse, lanes 16-31 delta of this thread's 16 queries; broadcast by shuffle below
-            float qstat = 0.f;
-            if (KS) {
-                const int cq = str_begin + j * BT + h * 16 + (lane & 15);
-                if (cq < T) qstat = (lane < 16) ? __ldg(lse + (int64_t)row_base + cq) * LOG2E : __ldg(delta + (int64_t)row_base + cq);
-            }
-            TR(30, j);
-            mbar_wait(&bars[C_GFULL], j & 1);
-            TR(31, j);
-            tc_fence_after();
-            float g1[16], g2[16];
-            {
-                float t1[16], t2[16];
-                tmem_ld16(lane_addr + TM_G1 + h * 16, g1);
-                tmem_ld16(lane_addr + TM_G1 + 32 + h * 16, t1);
-                tmem_ld16(lane_addr + TM_G2 + h * 16, g2);
-                tmem_ld16(lane_addr + TM_G2 + 32 + h * 16, t2);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) { g1[c] += t1[c]; g2[c] += t2[c]; }
-            }
-            tc_fence_before();
-            mbar_arrive(&bars[C_GFREE]);
-            TR(32, j);
-            const uint32_t bad = (bits_ring[j & 7] >> (16 * h)) & 0xffffu;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                float l2 = row_lse2, dl = row_delta;
-                if (KS) {
-                    l2 = __shfl_sync(0xffffffffu, qstat, c);
-                    dl = __shfl_sync(0xffffffffu, qstat, 16 + c);
-                }
-                const bool ok = row_ok && !((bad >> c) & 1u);
-                const float p = ok ? ex2_approx(fmaf(g1[c], SC2, -l2)) : 0.f;
-                g1[c] = p;
-                g2[c] = ok ? p * (g2[c] - dl) * SM_SCALE : 0.f;
-            }
-            uint32_t ph[8], pl[8], dh[8], dlw[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                split2(g1[2 * c], g1[2 * c + 1], ph[c], pl[c]);
-                split2(g2[2 * c], g2[2 * c + 1], dh[c], dlw[c]);
-            }
-            TR(33, j);
-            if (j >= 2) mbar_wait(&bars[C_PDFREE + pb], ((j >> 1) - 1) & 1);     // the accumulating MMAs of tile j-2 are done with this buffer
-            TR(34, j);
-            tc_fence_after();
-            const uint32_t pd = lane_addr + TM_PD + pb * 64 + h * 8;
-            if (KS) {
-                tmem_st8(pd, ph);
-                tmem_st8(pd + 16, pl);
-            }
-            tmem_st8(pd + 32, dh);
-            tmem_st8(pd + 48, dlw);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[C_PDFULL + pb]);
-            TR(35, j);
-        }
-        mbar_wait(&bars[C_DONE], 0);
-        tc_fence_after();
-        const bool store_ok = r_idx < T;
-#pragma unroll
-        for (int g = (KS ? 0 : 1); g < 2; ++g) {
-            float* dst = (g == 0 ? out1 : out2) + ((int64_t)row_base + r_idx) * ld_d + h * 64;
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                float t[32];
-                tmem_ld32(lane_addr + (g == 0 ? TM_ACC1 : TM_ACC2) + h * 64 + ch * 32, t);
-                if (store_ok) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
+constexpr uint32_t IDESC_ACC = instr_desc(128, 128, 0, 1);    // P/dS (tensor memory) x streamed tile (MN-major) -> 128 x 128
 
 // =============================================================================================
 // backward, dQ: query-stationary with 64-key tiles
 // =============================================================================================
-// The generic kernel above streams 32-row tiles because its two stationary operand pairs and two accumulators leave room
-// for nothing larger -- and pays for it: a score MMA with N = 64 costs 67 cycles, as much as one with N = 128 (73).  The dQ
-// pass needs neither P nor a second accumulator, and its V tile is dead as soon as dP is formed, so here the tiles are 64
-// keys: K double-buffered (it is also the B operand of dS.K), V single-buffered, score MMAs at N = 128.
+// The dQ pass needs neither P nor a second accumulator, and its V tile is dead as soon as dP is formed: K is double-buffered
+// (it is also the B operand of dS.K), V single-buffered, score MMAs at N = 128.
 //   G1 = Q.[K_hi;K_lo]^T (= S), G2 = dO.[V_hi;V_lo]^T (= dP), dS = P (dP - delta) / sqrt(d), dQ += dS.K
 // shared memory: Q hi/lo, dO hi/lo (128 KB) | K ring 2 x 32 KB | V 32 KB; a streamed tile is [d-half][hi,lo][64 keys][64 d]
 // tensor memory: [0,128) G1, [128,256) G2, [256,384) dQ, [384,512) two dS buffers of (32 hi + 32 lo) packed columns
@@ -1252,21 +989,17 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
         attr = true;
     }
     cudaStream_t st = as_stream(stream);
-    CUtensorMap q_hi128, q_lo128, q_hi32, q_lo32, d_hi128, d_lo128, d_hi32, d_lo32;
+    CUtensorMap q_hi128, q_lo128, d_hi128, d_lo128;
     DIP_TRY(make_tmap_bf16_3d(&q_hi128, qkv_hi, B, T, 3 * D, 3 * D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
     CUtensorMap q_hi64, q_lo64;
     DIP_TRY(make_tmap_bf16_3d(&q_hi64, qkv_hi, B, T, 3 * D, 3 * D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
-    DIP_TRY(make_tmap_bf16_3d(&q_hi32, qkv_hi, B, T, 3 * D, 3 * D, 32, 64));
-    DIP_TRY(make_tmap_bf16_3d(&q_lo32, qkv_lo, B, T, 3 * D, 3 * D, 32, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_hi128, do_hi, B, T, D, D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_lo128, do_lo, B, T, D, D, 128, 64));
     CUtensorMap d_hi64, d_lo64;
     DIP_TRY(make_tmap_bf16_3d(&d_hi64, do_hi, B, T, D, D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_lo64, do_lo, B, T, D, D, 64, 64));
-    DIP_TRY(make_tmap_bf16_3d(&d_hi32, do_hi, B, T, D, D, 32, 64));
-    DIP_TRY(make_tmap_bf16_3d(&d_lo32, do_lo, B, T, D, D, 32, 64));
     {
         DIP_PROF(DIP_PROF_OTHER, stream);
         const int64_t rows = (int64_t)B * (T - do_begin);

@@ -444,6 +444,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
             const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
             if (lane == 0) {
+                // V first: it is single-buffered and dP_j opens the tile; K_j is not needed before S_j, two products later
+                TR(42, j);
+                if (j >= 1) mbar_wait(&bars[D_WEMPTY], (j - 1) & 1);
+                TR(43, j);
+                mbar_expect_tx(&bars[D_WFULL], Q_TILE);
+                uint8_t* dw = sm + QOFF_W;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(dw + kb * 16384, &tm_qkv_hi64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);                // V hi
+                    tma_load_3d(dw + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);         // V lo
+                }
                 TR(40, j);
                 if (j >= 2) mbar_wait(&bars[D_UEMPTY + s], ((j >> 1) - 1) & 1);
                 TR(41, j);
@@ -454,21 +464,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                     tma_load_3d(du + kb * 16384, &tm_qkv_hi64, &bars[D_UFULL + s], 128 + kb * 64, j * QT, b);            // K hi, d-half kb
                     tma_load_3d(du + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_UFULL + s], 128 + kb * 64, j * QT, b);     // K lo
                 }
-                TR(42, j);
-                if (j >= 1) mbar_wait(&bars[D_WEMPTY], (j - 1) & 1);
-                TR(43, j);
-                mbar_expect_tx(&bars[D_WFULL], Q_TILE);
-                uint8_t* dw = sm + QOFF_W;
-                for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_3d(dw + kb * 16384, &tm_qkv_hi64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);                // V hi
-                    tma_load_3d(dw + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);         // V lo
-                }
             }
             __syncwarp();
         }
     } else if (warp == W_MMA) {
-        // One issuer, in the order  S_j , dS_{j-1}.K_{j-1} , dP_j : the accumulating product runs as soon as its dS exists instead of
-        // queueing behind a whole tile of score MMAs, which frees its K buffer one score GEMM earlier -- the K ring is only two deep.
+        // One issuer, in the order  dP_j , dS_{j-1}.K_{j-1} , S_j : the accumulating product runs before the score GEMM of the next K
+        // tile, so K_{j-1}'s buffer is free again a whole score GEMM before K_{j+1} is needed -- the K ring is only two deep.
         if (lane == 0) {
             const uint32_t aX = smem_u32(sm + QOFF_X), aY = smem_u32(sm + QOFF_Y), aU = smem_u32(sm + QOFF_U), aW = smem_u32(sm + QOFF_W);
             auto issue_G = [&](uint32_t st, uint32_t tp, uint32_t dst) {
@@ -511,21 +512,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
                 TR(20, j);
-                mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
-                if (j >= 1) mbar_wait(&bars[D_G1FREE], (j - 1) & 1);
-                TR(21, j);
-                tc_fence_after();
-                issue_G(aX, aU + s * Q_TILE, tmem + QTM_G1);
-                tc_commit(&bars[D_G1FULL]);
-                TR(22, j);
-                if (j >= 1) issue_acc(j - 1);
                 mbar_wait(&bars[D_WFULL], j & 1);
                 if (j >= 1) mbar_wait(&bars[D_G2FREE], (j - 1) & 1);
-                TR(24, j);
+                TR(21, j);
                 tc_fence_after();
-                issue_G(aY, aW, tmem + QTM_G2);
+                issue_G(aY, aW, tmem + QTM_G2);                                       // dP_j first: its V tile is single-buffered
                 tc_commit(&bars[D_G2FULL]);
                 tc_commit(&bars[D_WEMPTY]);
+                TR(22, j);
+                if (j >= 1) issue_acc(j - 1);                                         // dQ += dS_{j-1} K_{j-1}: frees K_{j-1} before S_j starts
+                mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
+                if (j >= 1) mbar_wait(&bars[D_G1FREE], (j - 1) & 1);
+                TR(24, j);
+                tc_fence_after();
+                issue_G(aX, aU + s * Q_TILE, tmem + QTM_G1);                          // S_j
+                tc_commit(&bars[D_G1FULL]);
                 TR(25, j);
             }
             issue_acc(n_tiles - 1);
@@ -546,39 +547,36 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         for (int j = 0; j < n_tiles; ++j) {
             const int pb = j & 1;
             TR(30, j);
-            mbar_wait(&bars[D_G1FULL], j & 1);
+            mbar_wait(&bars[D_G2FULL], j & 1);
             TR(31, j);
             tc_fence_after();
-            float pr[32];
+            float dp[32];
             {
                 float t[32];
-                tmem_ld32(lane_addr + QTM_G1 + h * 32, pr);
+                tmem_ld32(lane_addr + QTM_G2 + h * 32, dp);
+                tmem_ld32(lane_addr + QTM_G2 + 64 + h * 32, t);
+                tc_fence_before();
+                mbar_arrive(&bars[D_G2FREE]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) dp[c] = (dp[c] + t[c] - row_delta) * SM_SCALE;
+            }
+            TR(32, j);
+            mbar_wait(&bars[D_G1FULL], j & 1);
+            TR(33, j);
+            tc_fence_after();
+            uint32_t dh[16], dl[16];
+            {
+                float sc[32], t[32];
+                tmem_ld32(lane_addr + QTM_G1 + h * 32, sc);
                 tmem_ld32(lane_addr + QTM_G1 + 64 + h * 32, t);
                 tc_fence_before();
                 mbar_arrive(&bars[D_G1FREE]);
                 const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const bool ok = row_ok && !((bad >> c) & 1u);
-                    pr[c] = ok ? ex2_approx(fmaf(pr[c] + t[c], SC2, -row_lse2)) : 0.f;
-                }
-            }
-            TR(32, j);
-            mbar_wait(&bars[D_G2FULL], j & 1);
-            TR(33, j);
-            tc_fence_after();
-            uint32_t dh[16], dl[16];
-            {
-                float g2[32], t[32];
-                tmem_ld32(lane_addr + QTM_G2 + h * 32, g2);
-                tmem_ld32(lane_addr + QTM_G2 + 64 + h * 32, t);
-                tc_fence_before();
-                mbar_arrive(&bars[D_G2FREE]);
-#pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    const float d0 = pr[2 * c] * (g2[2 * c] + t[2 * c] - row_delta) * SM_SCALE;
-                    const float d1 = pr[2 * c + 1] * (g2[2 * c + 1] + t[2 * c + 1] - row_delta) * SM_SCALE;
-                    split2(d0, d1, dh[c], dl[c]);
+                    const bool ok0 = row_ok && !((bad >> (2 * c)) & 1u), ok1 = row_ok && !((bad >> (2 * c + 1)) & 1u);
+                    const float p0 = ex2_approx(fmaf(sc[2 * c] + t[2 * c], SC2, -row_lse2)), p1 = ex2_approx(fmaf(sc[2 * c + 1] + t[2 * c + 1], SC2, -row_lse2));
+                    split2(ok0 ? p0 * dp[2 * c] : 0.f, ok1 ? p1 * dp[2 * c + 1] : 0.f, dh[c], dl[c]);
                 }
             }
             if (j >= 2) mbar_wait(&bars[D_DSFREE + pb], ((j >> 1) - 1) & 1);     // dS.K of tile j-2 is done with this buffer

@@ -9,14 +9,16 @@ using namespace dip::tc;
 // mode 0: A K-major SW128, B K-major SW128 (N rows);  mode 1: B MN-major SW128;  mode 2: A un-swizzled K-major, B MN-major
 // mode 3: A in tensor memory (TS) x MN-major B, d-halves 8192 bytes apart;  mode 4: the same with d-halves 16384 bytes apart;
 // mode 5: TS x K-major B
-template <int N, int MODE>
-__global__ void __launch_bounds__(128, 1) bench(long long* out, int n_mma, int same_acc) {
+// NOISE: what the other warps do meanwhile -- 0 nothing, 1 tcgen05.ld loop, 2 tcgen05.st loop, 3 shared-memory load/store loop
+template <int N, int MODE, int NOISE = 0>
+__global__ void __launch_bounds__(288, 1) bench(long long* out, int n_mma, int same_acc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
+    __shared__ volatile int stop;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 196608 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int i = threadIdx.x; i < 196608 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
     if (warp == 0) tmem_alloc(&slot, 512);
     fence_proxy_async();
     tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -45,14 +47,26 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int n_mma, int s
         mbar_wait(&bar, 0);
         long long t2 = clock64();
         out[0] = t1 - t0; out[1] = t2 - t0;
+        stop = 1;
+    } else if (warp >= 1 && NOISE > 0) {
+        const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384;
+        float v[32]; uint32_t w[16];
+        for (int i = 0; i < 16; ++i) w[i] = i;
+        float accu = 0.f;
+        while (!stop) {
+            if (NOISE == 1) { tmem_ld32(la, v); accu += v[3]; }
+            if (NOISE == 2) { tmem_st16(la, w); tmem_st_wait(); }
+            if (NOISE == 3) { volatile float* ps = reinterpret_cast<volatile float*>(sm + 131072); float x = ps[threadIdx.x]; ps[4096 + threadIdx.x] = x + 1.f; accu += x; }
+        }
+        if (accu == 12345.f) out[2] = 1;
     }
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int N, int MODE>
+template <int N, int MODE, int NOISE = 0>
 void run(const char* name, long long* d, int same_acc) {
-    cudaFuncSetAttribute(bench<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704);
+    cudaFuncSetAttribute(bench<N, MODE, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704);
     const int n = 2048;
     for (int grid : {1, 148}) {
         bench<N, MODE><<<grid, 128, 200704>>>(d, n, same_acc);
@@ -65,7 +79,7 @@ void run(const char* name, long long* d, int same_acc) {
 }
 
 int main() {
-    long long* d; cudaMalloc(&d, 64);
+    long long* d; cudaMalloc(&d, 64); cudaMemset(d, 0, 64);
     run<32, 0>("K-major A x K-major B", d, 1);
     run<64, 0>("K-major A x K-major B", d, 1);
     run<64, 0>("K-major A x K-major B", d, 0);
@@ -79,5 +93,10 @@ int main() {
     run<128, 5>("TMEM A x K-major B", d, 1);
     run<64, 5>("TMEM A x K-major B", d, 1);
     run<64, 3>("TMEM A x MN-major B (LBO 8192)", d, 1);
+    run<128, 4, 1>("TMEM A x MN B + tcgen05.ld noise", d, 1);
+    run<128, 4, 2>("TMEM A x MN B + tcgen05.st noise", d, 1);
+    run<128, 4, 3>("TMEM A x MN B + smem noise", d, 1);
+    run<128, 0, 1>("SS K-major + tcgen05.ld noise", d, 1);
+    run<128, 0, 3>("SS K-major + smem noise", d, 1);
     return 0;
 }

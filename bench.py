@@ -348,9 +348,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"kernel": "attn_bwd_kv_tc_kernel (key-stationary decoder attention backward: dP, dV, dK; tcgen05)", "bound": "tensor", "achieved": achieved,
                          "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                         # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_dkdv_summary.txt, captured on the 32-query predecessor of this kernel, same operands: mean of the two
+                         # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_dkdv_summary.txt: mean of the two
                          # decoder layers' launches at wave 37, SC shapes); algorithmic bytes of the launch are ~400 MB, i.e. no DRAM re-reads
-                         "traffic": 315.1e6 if (B == 37 and L == 2000) else None,
+                         "traffic": 314.7e6 if (B == 37 and L == 2000) else None,
                          "ceiling_note": "fp32-grade products cost 3 bf16 MMA passes and the launch recomputes S (8 executed per 6 credited products): "
                                          "attainable ceiling = peak * (1/3) * (6/8) = 0.25 of the bf16 peak",
                          "peak_source": pk["src"] + ", sustained bf16", "launch_ms": avg_ms,

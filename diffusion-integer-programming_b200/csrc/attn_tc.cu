@@ -254,8 +254,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             float sv[32];
             {
                 float s_lo[32];
-                tmem_ld32(lane_addr + TM_S + s * 128 + h * 32, sv);           // Q . K_hi
-                tmem_ld32(lane_addr + TM_S + s * 128 + 64 + h * 32, s_lo);    // Q . K_lo
+                tmem_ld32x2(lane_addr + TM_S + s * 128 + h * 32, sv, lane_addr + TM_S + s * 128 + 64 + h * 32, s_lo);    // Q . K_hi, Q . K_lo
 #pragma unroll
                 for (int c = 0; c < 32; ++c) sv[c] += s_lo[c];
             }
@@ -553,8 +552,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             float dp[32];
             {
                 float t[32];
-                tmem_ld32(lane_addr + QTM_G2 + h * 32, dp);
-                tmem_ld32(lane_addr + QTM_G2 + 64 + h * 32, t);
+                tmem_ld32x2(lane_addr + QTM_G2 + h * 32, dp, lane_addr + QTM_G2 + 64 + h * 32, t);
                 tc_fence_before();
                 mbar_arrive(&bars[D_G2FREE]);
 #pragma unroll
@@ -567,8 +565,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             uint32_t dh[16], dl[16];
             {
                 float sc[32], t[32];
-                tmem_ld32(lane_addr + QTM_G1 + h * 32, sc);
-                tmem_ld32(lane_addr + QTM_G1 + 64 + h * 32, t);
+                tmem_ld32x2(lane_addr + QTM_G1 + h * 32, sc, lane_addr + QTM_G1 + 64 + h * 32, t);
                 tc_fence_before();
                 mbar_arrive(&bars[D_G1FREE]);
                 const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
@@ -798,8 +795,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             uint32_t ph[16], pl[16];
             {
                 float t[32];
-                tmem_ld32(lane_addr + KTM_G + h * 32, pr);
-                tmem_ld32(lane_addr + KTM_G + 64 + h * 32, t);
+                tmem_ld32x2(lane_addr + KTM_G + h * 32, pr, lane_addr + KTM_G + 64 + h * 32, t);
                 tc_fence_before();
                 mbar_arrive(&bars[E_G1FREE]);
                 const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
@@ -826,8 +822,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             uint32_t dh[16], dl[16];
             {
                 float g2[32], t[32];
-                tmem_ld32(lane_addr + KTM_G + h * 32, g2);
-                tmem_ld32(lane_addr + KTM_G + 64 + h * 32, t);
+                tmem_ld32x2(lane_addr + KTM_G + h * 32, g2, lane_addr + KTM_G + 64 + h * 32, t);
                 tc_fence_before();
                 mbar_arrive(&bars[E_G2FREE]);
 #pragma unroll

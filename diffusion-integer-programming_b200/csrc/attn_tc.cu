@@ -176,11 +176,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             }
         }
     } else if (warp == W_MMA || warp == W_MMA2) {
-        // ------------------------------------------------------------------ MMA issuers (one thread each)
-        if (lane == 0) {
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-            if (warp == W_MMA) mbar_wait(&bars[B_QFULL], 0);
-            auto issue_S = [&](int j) {
+        // ------------------------------------------------------------------ MMA issuers: warp-uniform loops, the elected lane issues
+        const uint64_t dQ = smem_desc(smem_u32(sQ), 16, 1024), dK = smem_desc(smem_u32(sK), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
+        if (warp == W_MMA) {
+            mbar_wait(&bars[B_QFULL], 0);
+            for (int j = 0; j < n_tiles; ++j) {
                 const int s = j % K_STAGES, sb = j & 1;
                 TR(20, j);
                 mbar_wait(&bars[B_KFULL + s], (j / K_STAGES) & 1);
@@ -188,23 +188,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 if (j >= 2) mbar_wait(&bars[B_SFREE + sb], ((j >> 1) - 1) & 1);
                 TR(22, j);
                 tc_fence_after();
-                const uint32_t kbase = aK + s * K_STAGE;
-                uint32_t acc = 0;
+                if (elect_one()) {
+                    const uint64_t kbase = desc_adv(dK, s * K_STAGE);
+                    uint32_t acc = 0;
 #pragma unroll
-                for (int pl = 0; pl < 2; ++pl)                     // A = Q_hi, then Q_lo, into the same 128 columns
+                    for (int pl = 0; pl < 2; ++pl)                     // A = Q_hi, then Q_lo, into the same 128 columns
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
+                        for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            tc_mma(tmem + TM_S + sb * 128, smem_desc(aQ + pl * 32768 + kb * 16384 + ks * 32, 16, 1024),
-                                   smem_desc(kbase + kb * 16384 + ks * 32, 16, 1024), IDESC_S, acc);
-                            acc = 1;
-                        }
-                tc_commit(&bars[B_SFULL + sb]);
-                tc_commit(&bars[B_KEMPTY + s]);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc_mma(tmem + TM_S + sb * 128, desc_adv(dQ, pl * 32768 + kb * 16384 + ks * 32), desc_adv(kbase, kb * 16384 + ks * 32), IDESC_S, acc);
+                                acc = 1;
+                            }
+                    tc_commit(&bars[B_SFULL + sb]);
+                    tc_commit(&bars[B_KEMPTY + s]);
+                }
+                __syncwarp();
                 TR(23, j);
-            };
-            auto issue_PV = [&](int j) {
+            }
+        } else {
+            for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
                 TR(24, j);
                 mbar_wait(&bars[B_VFULL + s], (j >> 1) & 1);
@@ -212,28 +215,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 mbar_wait(&bars[B_PFULL + s], (j >> 1) & 1);       // P_j stored AND the previous P.V tile folded by the row warps
                 TR(26, j);
                 tc_fence_after();
-                const uint32_t vbase = aV + s * V_STAGE;
-                const uint32_t pbase = tmem + TM_P + s * 64;
-                uint32_t acc = 0;
+                if (elect_one()) {
+                    const uint64_t vbase = desc_adv(dVmn, s * V_STAGE);
+                    const uint32_t pbase = tmem + TM_P + s * 64;
+                    uint32_t acc = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t pa = pbase + (pass == 2 ? 32 : 0);           // P hi, hi, lo
-                    const uint32_t va = vbase + (pass == 1 ? 16384 : 0);        // V hi, lo, hi
+                    for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        // V tile: two [64 keys x 64 d] blocks 8192 bytes apart (MN blocks), 16 keys per k-step = 2048 bytes
-                        tc_mma_ts(tmem + TM_PV, pa + ks * 8, smem_desc(va + ks * 2048, 8192, 1024), IDESC_PV, acc);
-                        acc = 1;
+                        for (int ks = 0; ks < 4; ++ks) {
+                            // P hi, hi, lo x V hi, lo, hi; V tile: two [64 keys x 64 d] blocks 8192 bytes apart (MN blocks), 16 keys per k-step = 2048 bytes
+                            tc_mma_ts(tmem + TM_PV, pbase + (pass == 2 ? 32 : 0) + ks * 8, desc_adv(vbase, (pass == 1 ? 16384 : 0) + ks * 2048), IDESC_PV, acc);
+                            acc = 1;
+                        }
                     }
+                    tc_commit(&bars[B_PVFULL]);
+                    tc_commit(&bars[B_VEMPTY + s]);
                 }
-                tc_commit(&bars[B_PVFULL]);
-                tc_commit(&bars[B_VEMPTY + s]);
+                __syncwarp();
                 TR(28, j);
-            };
-            if (warp == W_MMA) {
-                for (int j = 0; j < n_tiles; ++j) issue_S(j);
-            } else {
-                for (int j = 0; j < n_tiles; ++j) issue_PV(j);
             }
         }
     } else {
@@ -469,68 +468,77 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     } else if (warp == W_MMA) {
         // One issuer, in the order  dP_j , dS_{j-1}.K_{j-1} , S_j : the accumulating product runs before the score GEMM of the next K
         // tile, so K_{j-1}'s buffer is free again a whole score GEMM before K_{j+1} is needed -- the K ring is only two deep.
-        if (lane == 0) {
-            const uint32_t aX = smem_u32(sm + QOFF_X), aY = smem_u32(sm + QOFF_Y), aU = smem_u32(sm + QOFF_U), aW = smem_u32(sm + QOFF_W);
-            auto issue_G = [&](uint32_t st, uint32_t tp, uint32_t dst) {
-                uint32_t acc = 0;
+        // Warp-uniform control flow, the elected lane issues (see elect_one).
+        const uint64_t dX = smem_desc(smem_u32(sm + QOFF_X), 16, 1024), dY = smem_desc(smem_u32(sm + QOFF_Y), 16, 1024);
+        const uint64_t dU = smem_desc(smem_u32(sm + QOFF_U), 16, 1024), dW = smem_desc(smem_u32(sm + QOFF_W), 16, 1024);
+        const uint64_t dUmn = smem_desc(smem_u32(sm + QOFF_U), 16384, 1024);
+        auto issue_G = [&](uint64_t st, uint64_t tp, uint32_t dst) {
+            uint32_t acc = 0;
 #pragma unroll
-                for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
+            for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
+                for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            tc_mma(dst, smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024), smem_desc(tp + kb * 16384 + ks * 32, 16, 1024), IDESC_G128, acc);
-                            acc = 1;
-                        }
-            };
-            auto issue_acc = [&](int j) {
-                const int s = j & 1, pb = j & 1;
-                TR(26, j);
-                mbar_wait(&bars[D_DSFULL + pb], (j >> 1) & 1);
-                TR(27, j);
-                tc_fence_after();
-                const uint32_t tl = aU + s * Q_TILE;
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc_mma(dst, desc_adv(st, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
+                        acc = 1;
+                    }
+        };
+        auto issue_acc = [&](int j) {
+            const int s = j & 1, pb = j & 1;
+            TR(26, j);
+            mbar_wait(&bars[D_DSFULL + pb], (j >> 1) & 1);
+            TR(27, j);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t tl = desc_adv(dUmn, s * Q_TILE);
                 const uint32_t ds = tmem + QTM_DS + pb * 64;
                 uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t a = ds + (pass == 2 ? 32 : 0);               // dS hi, hi, lo
-                    const uint32_t bb = tl + (pass == 1 ? 8192 : 0);            // K hi, lo, hi
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        // K tile as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step = 2048 bytes
-                        tc_mma_ts(tmem + QTM_ACC, a + ks * 8, smem_desc(bb + ks * 2048, 16384, 1024), IDESC_ACC, acc);
+                        // dS hi, hi, lo (32 packed columns per plane) x K hi, lo, hi as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step
+                        tc_mma_ts(tmem + QTM_ACC, ds + (pass == 2 ? 32 : 0) + ks * 8, desc_adv(tl, (pass == 1 ? 8192 : 0) + ks * 2048), IDESC_ACC, acc);
                         acc = 1;
                     }
                 }
                 tc_commit(&bars[D_DSFREE + pb]);
                 tc_commit(&bars[D_UEMPTY + s]);
-                TR(28, j);
-            };
-            mbar_wait(&bars[D_XFULL], 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                TR(20, j);
-                mbar_wait(&bars[D_WFULL], j & 1);
-                if (j >= 1) mbar_wait(&bars[D_G2FREE], (j - 1) & 1);
-                TR(21, j);
-                tc_fence_after();
-                issue_G(aY, aW, tmem + QTM_G2);                                       // dP_j first: its V tile is single-buffered
+            }
+            __syncwarp();
+            TR(28, j);
+        };
+        mbar_wait(&bars[D_XFULL], 0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j & 1;
+            TR(20, j);
+            mbar_wait(&bars[D_WFULL], j & 1);
+            if (j >= 1) mbar_wait(&bars[D_G2FREE], (j - 1) & 1);
+            TR(21, j);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_G(dY, dW, tmem + QTM_G2);                                       // dP_j first: its V tile is single-buffered
                 tc_commit(&bars[D_G2FULL]);
                 tc_commit(&bars[D_WEMPTY]);
-                TR(22, j);
-                if (j >= 1) issue_acc(j - 1);                                         // dQ += dS_{j-1} K_{j-1}: frees K_{j-1} before S_j starts
-                mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
-                if (j >= 1) mbar_wait(&bars[D_G1FREE], (j - 1) & 1);
-                TR(24, j);
-                tc_fence_after();
-                issue_G(aX, aU + s * Q_TILE, tmem + QTM_G1);                          // S_j
-                tc_commit(&bars[D_G1FULL]);
-                TR(25, j);
             }
-            issue_acc(n_tiles - 1);
-            tc_commit(&bars[D_DONE]);
+            __syncwarp();
+            TR(22, j);
+            if (j >= 1) issue_acc(j - 1);                                             // dQ += dS_{j-1} K_{j-1}: frees K_{j-1} before S_j starts
+            mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
+            if (j >= 1) mbar_wait(&bars[D_G1FREE], (j - 1) & 1);
+            TR(24, j);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_G(dX, desc_adv(dU, s * Q_TILE), tmem + QTM_G1);                 // S_j
+                tc_commit(&bars[D_G1FULL]);
+            }
+            __syncwarp();
+            TR(25, j);
         }
+        issue_acc(n_tiles - 1);
+        if (elect_one()) tc_commit(&bars[D_DONE]);
+        __syncwarp();
     } else if (warp < 8) {
         // ------------------------------------------------------------------ row warps: thread = (query row, 32 of the 64 keys)
         const int q = warp & 3, h = warp >> 2;
@@ -609,18 +617,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
 // backward, dK / dV: key-stationary with 64-query tiles
 // =============================================================================================
 // Same idea as the dQ kernel, for the pass that needs two accumulators.  Tensor memory is the tight resource: dV and dK take 256
-// columns, the packed P / dS operands of a 64-query tile 128, which leaves 128 -- one score tile.  So S^T and dP^T share ONE
-// region and are formed one after the other; the accumulating products of the PREVIOUS tile are issued in between and keep the
-// tensor pipe busy while the row threads drain the region:
-//      S^T_j  |  dV += P_{j-1}^T dO_{j-1}  |  dK += dS_{j-1}^T Q_{j-1}  |  dP^T_j  |  S^T_{j+1} ...
-// Shared memory: K hi/lo, V hi/lo stationary (128 KB) | Q ring 2 x 32 KB (needed until dK of its tile) | dO 32 KB, single-buffered
-// (its reload hides behind the dK product).  Score MMAs are N = 128 (64 queries, hi and lo stacked): 73 cycles for twice the work
-// of the N = 64 MMAs (67 cycles) the 32-query version had to use.
-// tensor memory: [0,128) S^T / dP^T (X.U_hi | X.U_lo), [128,256) P hi, P lo, dS hi, dS lo (32 packed columns each),
-//                [256,384) dV, [384,512) dK
-constexpr uint32_t KTM_G = 0, KTM_PD = 128, KTM_ACC1 = 256, KTM_ACC2 = 384;
-enum { E_XFULL = 0, E_UFULL = 1, E_UEMPTY = 3, E_WFULL = 5, E_WEMPTY = 6, E_G1FULL = 7, E_G1FREE = 8, E_G2FULL = 9, E_G2FREE = 10, E_PFULL = 11, E_PFREE = 12,
-       E_DSFULL = 13, E_DSFREE = 14, E_DONE = 15 };
+// columns, S^T and dP^T of a 64-query tile (hi- and lo-part stacked) 128 each -- nothing is left for the packed P / dS operands.
+// They are written IN PLACE: a row thread reads its 32 + 32 score columns and stores the 16 + 16 packed columns of P (or dS) back
+// into the first half of the columns it just read, so no other thread's unread data is touched.  One thread issues everything in
+// the order
+//      S^T_j , dP^T_j , dV += P_j^T dO_j , S^T_{j+1} , dK += dS_j^T Q_j , dP^T_{j+1} , ...
+// and because the tensor pipe executes in issue order no barrier is needed between a product that reads P_j and the score GEMM that
+// overwrites its region; every wait the issuer performs (P_j stored, dS_j stored, next tile loaded) is covered by two products of
+// queued work.  Shared memory: K hi/lo, V hi/lo stationary (128 KB) | Q ring 2 x 32 KB | dO 32 KB, single-buffered.  Score MMAs are
+// N = 128: 73 cycles for twice the work of the N = 64 MMAs (67 cycles) the 32-query version had to use.
+// tensor memory: [0,128) S^T_j then P_j, [128,256) dP^T_j then dS_j, [256,384) dV, [384,512) dK
+constexpr uint32_t KTM_G1 = 0, KTM_G2 = 128, KTM_ACC1 = 256, KTM_ACC2 = 384;
+enum { E_XFULL = 0, E_UFULL = 1, E_UEMPTY = 3, E_WFULL = 5, E_WEMPTY = 6, E_G1FULL = 7, E_G2FULL = 8, E_PFULL = 9, E_DSFULL = 10, E_DONE = 11 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
@@ -631,7 +639,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     volatile uint64_t* bits_ring = reinterpret_cast<volatile uint64_t*>(sm + QOFF_BITS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -649,13 +657,9 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         mbar_init(&bars[E_WFULL], 1);
         mbar_init(&bars[E_WEMPTY], 1);
         mbar_init(&bars[E_G1FULL], 1);
-        mbar_init(&bars[E_G1FREE], ROW_THREADS);
         mbar_init(&bars[E_G2FULL], 1);
-        mbar_init(&bars[E_G2FREE], ROW_THREADS);
         mbar_init(&bars[E_PFULL], ROW_THREADS);
-        mbar_init(&bars[E_PFREE], 1);
         mbar_init(&bars[E_DSFULL], ROW_THREADS);
-        mbar_init(&bars[E_DSFREE], 1);
         mbar_init(&bars[E_DONE], 1);
         mbar_fence_init();
     }
@@ -704,73 +708,85 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             __syncwarp();
         }
     } else if (warp == W_MMA) {
-        if (lane == 0) {
-            const uint32_t aX = smem_u32(sm + QOFF_X), aY = smem_u32(sm + QOFF_Y), aU = smem_u32(sm + QOFF_U), aW = smem_u32(sm + QOFF_W);
-            auto issue_G = [&](uint32_t st, uint32_t tp) {
-                uint32_t acc = 0;
+        // warp-uniform issue loop: every lane waits, the elected lane issues (see elect_one)
+        const uint64_t dX = smem_desc(smem_u32(sm + QOFF_X), 16, 1024), dY = smem_desc(smem_u32(sm + QOFF_Y), 16, 1024);
+        const uint64_t dU = smem_desc(smem_u32(sm + QOFF_U), 16, 1024), dW = smem_desc(smem_u32(sm + QOFF_W), 16, 1024);
+        const uint64_t dUmn = smem_desc(smem_u32(sm + QOFF_U), 16384, 1024), dWmn = smem_desc(smem_u32(sm + QOFF_W), 16384, 1024);
+        auto issue_G = [&](uint64_t st, uint64_t tp, uint32_t dst) {
+            uint32_t acc = 0;
 #pragma unroll
-                for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
+            for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            tc_mma(tmem + KTM_G, smem_desc(st + pl * ST_PLANE + kb * 16384 + ks * 32, 16, 1024), smem_desc(tp + kb * 16384 + ks * 32, 16, 1024),
-                                   IDESC_G128, acc);
-                            acc = 1;
-                        }
-            };
-            auto issue_acc = [&](uint32_t dst, uint32_t a_cols, uint32_t tile, uint32_t first) {
-                uint32_t acc = first ? 0u : 1u;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t a = tmem + KTM_PD + a_cols + (pass == 2 ? 32 : 0);       // A hi, hi, lo (32 packed columns per plane)
-                    const uint32_t bb = tile + (pass == 1 ? 8192 : 0);                      // B hi, lo, hi
+                for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        // streamed tile as MN-major B: d-halves 16384 bytes apart, 16 queries per k-step = 2048 bytes
-                        tc_mma_ts(dst, a + ks * 8, smem_desc(bb + ks * 2048, 16384, 1024), IDESC_ACC, acc);
+                        tc_mma(dst, desc_adv(st, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
                         acc = 1;
                     }
+        };
+        // A operand in place of the scores: the thread that owned queries 32h .. 32h+31 left their packed hi plane in columns
+        // [32h, 32h+16) and the lo plane in [32h+16, 32h+32) of the region; k-step ks covers queries 16ks .. 16ks+15
+        auto issue_acc = [&](uint32_t dst, uint32_t region, uint64_t tile_mn, bool first) {
+            uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t a = region + (ks >> 1) * 32 + (ks & 1) * 8 + (pass == 2 ? 16 : 0);       // A hi, hi, lo
+                    // streamed tile as MN-major B (hi, lo, hi): d-halves 16384 bytes apart, 16 queries per k-step = 2048 bytes
+                    tc_mma_ts(dst, a, desc_adv(tile_mn, (pass == 1 ? 8192 : 0) + ks * 2048), IDESC_ACC, acc);
+                    acc = 1;
                 }
-            };
-            mbar_wait(&bars[E_XFULL], 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                TR(20, j);
-                mbar_wait(&bars[E_UFULL + s], (j >> 1) & 1);
-                if (j >= 1) mbar_wait(&bars[E_G2FREE], (j - 1) & 1);
-                TR(21, j);
-                tc_fence_after();
-                issue_G(aX, aU + s * Q_TILE);                                        // S^T_j
-                tc_commit(&bars[E_G1FULL]);
-                TR(22, j);
-                if (j >= 1) {                                                        // dK += dS_{j-1}^T Q_{j-1}
-                    mbar_wait(&bars[E_DSFULL], (j - 1) & 1);
-                    tc_fence_after();
-                    issue_acc(tmem + KTM_ACC2, 64, aU + ((j - 1) & 1) * Q_TILE, j == 1);
-                    tc_commit(&bars[E_UEMPTY + ((j - 1) & 1)]);
-                    tc_commit(&bars[E_DSFREE]);
-                    TR(23, j);
-                }
-                mbar_wait(&bars[E_WFULL], j & 1);
-                mbar_wait(&bars[E_G1FREE], j & 1);
-                TR(24, j);
-                tc_fence_after();
-                issue_G(aY, aW);                                                     // dP^T_j
-                tc_commit(&bars[E_G2FULL]);
-                TR(25, j);
-                mbar_wait(&bars[E_PFULL], j & 1);                                    // dV += P_j^T dO_j : frees the dO buffer one product early
-                tc_fence_after();
-                issue_acc(tmem + KTM_ACC1, 0, aW, j == 0);
-                tc_commit(&bars[E_WEMPTY]);
-                tc_commit(&bars[E_PFREE]);
-                TR(28, j);
             }
-            mbar_wait(&bars[E_DSFULL], (n_tiles - 1) & 1);
+        };
+        auto issue_scores1 = [&](int j) {                       // S^T_j
+            const int s = j & 1;
+            TR(20, j);
+            mbar_wait(&bars[E_UFULL + s], (j >> 1) & 1);
             tc_fence_after();
-            issue_acc(tmem + KTM_ACC2, 64, aU + ((n_tiles - 1) & 1) * Q_TILE, n_tiles == 1);
-            tc_commit(&bars[E_DONE]);
+            if (elect_one()) {
+                issue_G(dX, desc_adv(dU, s * Q_TILE), tmem + KTM_G1);
+                tc_commit(&bars[E_G1FULL]);
+            }
+            __syncwarp();
+            TR(22, j);
+        };
+        auto issue_scores2 = [&](int j) {                       // dP^T_j
+            mbar_wait(&bars[E_WFULL], j & 1);
+            TR(24, j);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_G(dY, dW, tmem + KTM_G2);
+                tc_commit(&bars[E_G2FULL]);
+            }
+            __syncwarp();
+            TR(25, j);
+        };
+        mbar_wait(&bars[E_XFULL], 0);
+        issue_scores1(0);
+        issue_scores2(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(&bars[E_PFULL], j & 1);                                    // dV += P_j^T dO_j
+            tc_fence_after();
+            if (elect_one()) {
+                issue_acc(tmem + KTM_ACC1, tmem + KTM_G1, dWmn, j == 0);
+                tc_commit(&bars[E_WEMPTY]);
+            }
+            __syncwarp();
+            TR(28, j);
+            if (j + 1 < n_tiles) issue_scores1(j + 1);                            // S^T_{j+1} overwrites P_j: after its product, in pipe order
+            mbar_wait(&bars[E_DSFULL], j & 1);                                   // dK += dS_j^T Q_j
+            tc_fence_after();
+            if (elect_one()) {
+                issue_acc(tmem + KTM_ACC2, tmem + KTM_G2, desc_adv(dUmn, (j & 1) * Q_TILE), j == 0);
+                tc_commit(&bars[E_UEMPTY + (j & 1)]);
+            }
+            __syncwarp();
+            TR(23, j);
+            if (j + 1 < n_tiles) issue_scores2(j + 1);                            // dP^T_{j+1} overwrites dS_j
         }
+        if (elect_one()) tc_commit(&bars[E_DONE]);
+        __syncwarp();
     } else if (warp < 8) {
         // ------------------------------------------------------------------ row warps: thread = (key row, 32 of the 64 queries)
         const int q = warp & 3, h = warp >> 2;
@@ -792,12 +808,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             TR(31, j);
             tc_fence_after();
             float pr[32];
-            uint32_t ph[16], pl[16];
             {
                 float t[32];
-                tmem_ld32x2(lane_addr + KTM_G + h * 32, pr, lane_addr + KTM_G + 64 + h * 32, t);
-                tc_fence_before();
-                mbar_arrive(&bars[E_G1FREE]);
+                uint32_t ph[16], pl[16];
+                tmem_ld32x2(lane_addr + KTM_G1 + h * 32, pr, lane_addr + KTM_G1 + 64 + h * 32, t);
                 const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -807,24 +821,21 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 }
 #pragma unroll
                 for (int c = 0; c < 16; ++c) split2(pr[2 * c], pr[2 * c + 1], ph[c], pl[c]);
+                // in place: the packed planes go into the first 32 of the 64 columns this thread has just read
+                tmem_st16(lane_addr + KTM_G1 + h * 32, ph);
+                tmem_st16(lane_addr + KTM_G1 + h * 32 + 16, pl);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[E_PFULL]);
             }
-            if (j >= 1) mbar_wait(&bars[E_PFREE], (j - 1) & 1);       // P_{j-1}^T dO_{j-1} has read the P columns
-            tc_fence_after();
-            tmem_st16(lane_addr + KTM_PD + h * 16, ph);
-            tmem_st16(lane_addr + KTM_PD + 32 + h * 16, pl);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[E_PFULL]);
             TR(32, j);
             mbar_wait(&bars[E_G2FULL], j & 1);
             TR(33, j);
             tc_fence_after();
-            uint32_t dh[16], dl[16];
             {
                 float g2[32], t[32];
-                tmem_ld32x2(lane_addr + KTM_G + h * 32, g2, lane_addr + KTM_G + 64 + h * 32, t);
-                tc_fence_before();
-                mbar_arrive(&bars[E_G2FREE]);
+                uint32_t dh[16], dl[16];
+                tmem_ld32x2(lane_addr + KTM_G2 + h * 32, g2, lane_addr + KTM_G2 + 64 + h * 32, t);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float dl0 = __shfl_sync(0xffffffffu, q_delta, 2 * c), dl1 = __shfl_sync(0xffffffffu, q_delta, 2 * c + 1);
@@ -832,15 +843,13 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                     const float d1 = pr[2 * c + 1] * (g2[2 * c + 1] + t[2 * c + 1] - dl1) * SM_SCALE;
                     split2(d0, d1, dh[c], dl[c]);
                 }
+                TR(34, j);
+                tmem_st16(lane_addr + KTM_G2 + h * 32, dh);
+                tmem_st16(lane_addr + KTM_G2 + h * 32 + 16, dl);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[E_DSFULL]);
             }
-            if (j >= 1) mbar_wait(&bars[E_DSFREE], (j - 1) & 1);      // dS_{j-1}^T Q_{j-1} has read the dS columns
-            TR(34, j);
-            tc_fence_after();
-            tmem_st16(lane_addr + KTM_PD + 64 + h * 16, dh);
-            tmem_st16(lane_addr + KTM_PD + 96 + h * 16, dl);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[E_DSFULL]);
             TR(35, j);
         }
         mbar_wait(&bars[E_DONE], 0);

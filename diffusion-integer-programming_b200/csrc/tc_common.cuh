@@ -205,6 +205,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)2 << 61;
     return d;
 }
+// descriptor of the same operand `bytes` further on (the start-address field counts 16-byte units; shared memory is < 256 KB, so the
+// field cannot overflow): lets the issue loops add compile-time constants to a precomputed descriptor instead of rebuilding it
+__device__ __forceinline__ uint64_t desc_adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+// one lane of a converged warp (the lowest): MMA issue code stays warp-uniform -- waits by all lanes, tcgen05.mma / commit by the
+// elected one -- so that addresses live in uniform registers (issuing from inside `if (lane == 0)` cost ~18 instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // Instruction descriptor: bf16 x bf16 -> fp32, dense; majors: 0 = K-major, 1 = MN-major
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |

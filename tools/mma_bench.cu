@@ -9,6 +9,8 @@ using namespace dip::tc;
 // mode 0: A K-major SW128, B K-major SW128 (N rows);  mode 1: B MN-major SW128;  mode 2: A un-swizzled K-major, B MN-major
 // mode 3: A in tensor memory (TS) x MN-major B, d-halves 8192 bytes apart;  mode 4: the same with d-halves 16384 bytes apart;
 // mode 5: TS x K-major B
+// MODE 6: the issue pattern of the dK/dV kernel -- per 'tile' 16 SS MMAs -> cols [0,128), 12 TS MMAs (A = cols [0,64)) -> [256,384),
+//         16 SS MMAs -> [128,256), 12 TS MMAs (A = cols [128,192)) -> [384,512); reports cycles per tile (n_mma = tiles)
 // NOISE: what the other warps do meanwhile -- 0 nothing, 1 tcgen05.ld loop, 2 tcgen05.st loop, 3 shared-memory load/store loop
 template <int N, int MODE, int NOISE = 0>
 __global__ void __launch_bounds__(288, 1) bench(long long* out, int n_mma, int same_acc) {
@@ -27,6 +29,20 @@ __global__ void __launch_bounds__(288, 1) bench(long long* out, int n_mma, int s
         const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm) + 65536;
         const uint32_t idesc = dip::tc::instr_desc(128, N, 0, MODE >= 1 ? 1 : 0);
         long long t0 = clock64();
+        if (MODE == 6) {
+            const uint32_t idg = dip::tc::instr_desc(128, 128, 0, 0), ida = dip::tc::instr_desc(128, 128, 0, 1);
+            for (int t = 0; t < n_mma; ++t) {
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t acc = 0;
+                    for (int pl = 0; pl < 2; ++pl) for (int kb = 0; kb < 2; ++kb) for (int ks = 0; ks < 4; ++ks) {
+                        tc_mma(tmem + g * 128, smem_desc(a0 + g * 65536 / 2 + pl * 32768 / 2 + kb * 16384 / 2 + ks * 32, 16, 1024), smem_desc(b0 + 65536 + kb * 16384 + ks * 32, 16, 1024), idg, acc);
+                        acc = 1;
+                    }
+                    for (int pass = 0; pass < 3; ++pass) for (int ks = 0; ks < 4; ++ks)
+                        tc_mma_ts(tmem + 256 + g * 128, tmem + g * 128 + (ks >> 1) * 32 + (ks & 1) * 8 + (pass == 2 ? 16 : 0), smem_desc(b0 + 65536 + (pass == 1 ? 8192 : 0) + ks * 2048, 16384, 1024), ida, t > 0 || pass > 0 || ks > 0);
+                }
+            }
+        } else
         for (int i = 0; i < n_mma; ++i) {
             const int ks = i & 3, kb = (i >> 2) & 1;
             uint64_t da, db;
@@ -93,6 +109,7 @@ int main() {
     run<128, 5>("TMEM A x K-major B", d, 1);
     run<64, 5>("TMEM A x K-major B", d, 1);
     run<64, 3>("TMEM A x MN-major B (LBO 8192)", d, 1);
+    run<128, 6>("dK/dV issue pattern: cycles per tile / 2048", d, 1);
     run<128, 4, 1>("TMEM A x MN B + tcgen05.ld noise", d, 1);
     run<128, 4, 2>("TMEM A x MN B + tcgen05.st noise", d, 1);
     run<128, 4, 3>("TMEM A x MN B + smem noise", d, 1);

@@ -238,7 +238,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 tma_load_2d(sW + W_PLANE + kb * W_BLOCK, &tm_w_lo, &bars[G_WFULL], kb * 64, n0);
             }
         }
-        auto mma_issue = [&](int itx) {                     // lane 0 of warp 0 only
+        const uint64_t dA = smem_desc(aA, 16, 1024), dWd = smem_desc(aW, 16, 1024);
+        auto mma_issue = [&](int itx) {                     // all lanes of warp 0 (uniform): they wait, the elected lane issues
             const int ti = itx / KCH, kc = itx - ti * KCH, cb = ti & 1, s = itx & 1;
             if (itx == 0) mbar_wait(&bars[G_WFULL], 0);
             if (kc == 0 && ti >= 2) mbar_wait(&bars[G_CEMPTY + cb], ((ti >> 1) - 1) & 1);
@@ -246,37 +247,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
             mbar_wait(&bars[G_AFULL + s], (itx >> 1) & 1);
             TR(11, ti);
             tc_fence_after();
-            uint32_t acc = kc > 0 ? 1u : 0u;
+            if (elect_one()) {
+                const uint64_t da = desc_adv(dA, s * A_STAGE), dw = desc_adv(dWd, kc * 2 * W_BLOCK);
+                uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t a = aA + s * A_STAGE + (pass == 2 ? A_PLANE : 0);      // hi, hi, lo
-                const uint32_t w = aW + (pass == 1 ? W_PLANE : 0);                    // hi, lo, hi
+                for (int pass = 0; pass < 3; ++pass)                                 // A hi, hi, lo x W hi, lo, hi
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+                    for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        tc_mma(tmem + cb * BN, smem_desc(a + kb * 16384 + ks * 32, 16, 1024), smem_desc(w + (kc * 2 + kb) * W_BLOCK + ks * 32, 16, 1024),
-                               IDESC, acc);
-                        acc = 1;
-                    }
+                        for (int ks = 0; ks < 4; ++ks) {
+                            tc_mma(tmem + cb * BN, desc_adv(da, (pass == 2 ? A_PLANE : 0) + kb * 16384 + ks * 32),
+                                   desc_adv(dw, (pass == 1 ? W_PLANE : 0) + kb * W_BLOCK + ks * 32), IDESC, acc);
+                            acc = 1;
+                        }
+                tc_commit(&bars[G_AEMPTY + s]);
+                if (kc == KCH - 1) tc_commit(&bars[G_CFULL + cb]);
             }
-            tc_commit(&bars[G_AEMPTY + s]);
-            if (kc == KCH - 1) tc_commit(&bars[G_CFULL + cb]);
+            __syncwarp();
             TR(12, ti);
         };
         int it = 0;
         if (APL) {
-            if (issuer) {
+            if (warp == W_MMA) {
                 const int n_it = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
                 for (int itx = 0; itx <= n_it; ++itx) {
                     if (itx < n_it) {
                         const int s = itx & 1, tile = blockIdx.x + itx * gridDim.x;
                         if (itx >= 2) mbar_wait(&bars[G_AEMPTY + s], ((itx >> 1) - 1) & 1);
-                        mbar_expect_tx(&bars[G_AFULL + s], A_STAGE);
-                        for (int kb = 0; kb < 2; ++kb) {        // rows past M are zero-filled by the tensor map
-                            tma_load_2d(sm + s * A_STAGE + kb * 16384, &tm_a_hi, &bars[G_AFULL + s], kb * 64, tile * 128);
-                            tma_load_2d(sm + s * A_STAGE + A_PLANE + kb * 16384, &tm_a_lo, &bars[G_AFULL + s], kb * 64, tile * 128);
+                        if (issuer) {
+                            mbar_expect_tx(&bars[G_AFULL + s], A_STAGE);
+                            for (int kb = 0; kb < 2; ++kb) {        // rows past M are zero-filled by the tensor map
+                                tma_load_2d(sm + s * A_STAGE + kb * 16384, &tm_a_hi, &bars[G_AFULL + s], kb * 64, tile * 128);
+                                tma_load_2d(sm + s * A_STAGE + A_PLANE + kb * 16384, &tm_a_lo, &bars[G_AFULL + s], kb * 64, tile * 128);
+                            }
                         }
+                        __syncwarp();
                     }
                     if (itx >= 1) mma_issue(itx - 1);
                 }
@@ -301,8 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                         v[u] = DBG(2) ? make_float4(1.f, 2.f, 3.f, 4.f) : reinterpret_cast<const float4*>(src)[lane];
                     }
                     if (bt == 0) {
-                        if (issuer && it > 0) mma_issue(it - 1);
-                        __syncwarp();
+                        if (warp == W_MMA && it > 0) mma_issue(it - 1);
                         if (it >= 2) mbar_wait(&bars[G_AEMPTY + s], ((it >> 1) - 1) & 1);      // the stage's previous MMAs have read it
                         TR(2, tile);
                     }
@@ -338,9 +342,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                 TR(3, tile);
             }
         }
-        if (issuer && it > 0) mma_issue(it - 1);
+        if (warp == W_MMA && it > 0) mma_issue(it - 1);
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp % 4; the two warps of a
         // quarter split the tile's 32-column chunks between them

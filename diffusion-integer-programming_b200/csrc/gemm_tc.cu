@@ -113,7 +113,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 __device__ __forceinline__ float fast_sigmoid(float z) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+// ACT (template): 0 none, 1 QuickGELU, 2 multiply by the QuickGELU derivative at aux, 3 any (selected at run time: ReLU / sigmoid / ...)
+template <int ACT>
 __device__ __forceinline__ float act_apply(float v, int act, float aux) {
+    if (ACT == 1) return v * fast_sigmoid(1.702f * v);
+    if (ACT == 2) {
+        const float sg = fast_sigmoid(1.702f * aux);
+        return v * (sg + 1.702f * aux * sg * (1.0f - sg));
+    }
     const float z = act == DIP_ACT_MUL_QUICKGELU_GRAD ? aux : v;
     const float sg = fast_sigmoid((act == DIP_ACT_SIGMOID ? 1.0f : 1.702f) * z);
     const float gelu = v * sg, grad = v * (sg + 1.702f * z * sg * (1.0f - sg));
@@ -157,14 +164,14 @@ __device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b, bo
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(a), "r"(b), "r"((uint32_t)ok) : "memory");
 }
 
-template <bool ACT>
+template <int ACT>
 __device__ __forceinline__ void epi_finish(const Params& P, const EpiIn& e, int c, float4 a4, bool ok) {
     float x[4] = {a4.x + e.ext.x, a4.y + e.ext.y, a4.z + e.ext.z, a4.w + e.ext.w};
     const size_t o = (size_t)e.out_row * P.ldc + c;
     if (P.preact) st_global_v4(P.preact + o, x[0], x[1], x[2], x[3], ok);
-    if (ACT) {          // compiled out of the variants without activation: a skipped block this size costs instruction-fetch stalls
-        x[0] = act_apply(x[0], P.act, e.aux.x); x[1] = act_apply(x[1], P.act, e.aux.y);
-        x[2] = act_apply(x[2], P.act, e.aux.z); x[3] = act_apply(x[3], P.act, e.aux.w);
+    if (ACT != 0) {     // compiled out of the variants without activation: a skipped block this size costs instruction-fetch stalls
+        x[0] = act_apply<ACT>(x[0], P.act, e.aux.x); x[1] = act_apply<ACT>(x[1], P.act, e.aux.y);
+        x[2] = act_apply<ACT>(x[2], P.act, e.aux.z); x[3] = act_apply<ACT>(x[3], P.act, e.aux.w);
     }
     if (P.C) st_global_v4(P.C + o, x[0], x[1], x[2], x[3], ok);
     if (P.split_hi) {
@@ -182,7 +189,7 @@ constexpr int RPW = 128 / N_LOADERS;      // rows of a tile per loader warp, loa
 // APL = true: A arrives as ready-made bf16 hi/lo planes (dip_layernorm_split) and is fetched by TMA straight into the MMA layout --
 // no loader warps.  Used by the q|k|v in-projection, whose three column CTAs per row tile would otherwise each repeat the row
 // loads, the LayerNorm and the split.
-template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT, bool APL>
+template <int KCH, int BN, bool LN, bool ROWOPS, int ACT, bool APL>
 __global__ void __launch_bounds__(N_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo, const Params P) {
@@ -416,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
     if (warp == W_MMA) tmem_dealloc(tmem, 2 * BN);
 }
 
-template <int KCH, int BN, bool LN, bool ROWOPS, bool ACT, bool APL = false>
+template <int KCH, int BN, bool LN, bool ROWOPS, int ACT, bool APL = false>
 static int launch(const CUtensorMap& whi, const CUtensorMap& wlo, const CUtensorMap& ahi, const CUtensorMap& alo, const Params& P, int n_blocks_y, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
@@ -504,17 +511,18 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     DIP_PROF(DIP_PROF_GEMM, stream);
     cudaStream_t st = as_stream(stream);
     const bool rowops = g.row_bias_scale || g.addmat || g.res.batch || g.aux;
-    const bool act = g.act != DIP_ACT_NONE;
-    const int variant = (g.K == 128 ? (ln_gamma ? 1 : 0) : 2) * 4 + (rowops ? 2 : 0) + (act ? 1 : 0);
+    const int actk = g.act == DIP_ACT_NONE ? 0 : g.act == DIP_ACT_QUICKGELU ? 1 : g.act == DIP_ACT_MUL_QUICKGELU_GRAD ? 2 : 3;
+    const int shape = g.K == 128 ? (ln_gamma ? 1 : 0) : 2;
+    const int variant = (shape * 2 + (rowops ? 1 : 0)) * 4 + actk;
     const int ny = g.N / BN;
     switch (variant) {
 #define DIP_GEMM_CASE(v, KCH, BNv, LNv, RO, AC) case v: DIP_TRY((tcgemm::launch<KCH, BNv, LNv, RO, AC>(whi, wlo, whi, wlo, P, ny, st))); break;
-        DIP_GEMM_CASE(0, 1, 128, false, false, false) DIP_GEMM_CASE(1, 1, 128, false, false, true)
-        DIP_GEMM_CASE(2, 1, 128, false, true, false)  DIP_GEMM_CASE(3, 1, 128, false, true, true)
-        DIP_GEMM_CASE(4, 1, 128, true, false, false)  DIP_GEMM_CASE(5, 1, 128, true, false, true)
-        DIP_GEMM_CASE(6, 1, 128, true, true, false)   DIP_GEMM_CASE(7, 1, 128, true, true, true)
-        DIP_GEMM_CASE(8, 3, 64, false, false, false)  DIP_GEMM_CASE(9, 3, 64, false, false, true)
-        DIP_GEMM_CASE(10, 3, 64, false, true, false)  DIP_GEMM_CASE(11, 3, 64, false, true, true)
+#define DIP_GEMM_ACTS(v0, KCH, BNv, LNv, RO) DIP_GEMM_CASE(v0, KCH, BNv, LNv, RO, 0) DIP_GEMM_CASE(v0 + 1, KCH, BNv, LNv, RO, 1) \
+        DIP_GEMM_CASE(v0 + 2, KCH, BNv, LNv, RO, 2) DIP_GEMM_CASE(v0 + 3, KCH, BNv, LNv, RO, 3)
+        DIP_GEMM_ACTS(0, 1, 128, false, false) DIP_GEMM_ACTS(4, 1, 128, false, true)
+        DIP_GEMM_ACTS(8, 1, 128, true, false)  DIP_GEMM_ACTS(12, 1, 128, true, true)
+        DIP_GEMM_ACTS(16, 3, 64, false, false) DIP_GEMM_ACTS(20, 3, 64, false, true)
+#undef DIP_GEMM_ACTS
 #undef DIP_GEMM_CASE
         default: DIP_FAIL("dip_gemm_tc: no kernel variant %d", variant);
     }
@@ -548,7 +556,7 @@ int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* 
     DIP_TRY(make_tmap_bf16_2d(&ahi, a_hi, g.M, 128, 128, 128, 64));
     DIP_TRY(make_tmap_bf16_2d(&alo, a_lo, g.M, 128, 128, 128, 64));
     DIP_PROF(DIP_PROF_GEMM, stream);
-    DIP_TRY((tcgemm::launch<1, 128, false, false, false, true>(whi, wlo, ahi, alo, P, g.N / 128, as_stream(stream))));
+    DIP_TRY((tcgemm::launch<1, 128, false, false, 0, true>(whi, wlo, ahi, alo, P, g.N / 128, as_stream(stream))));
     DIP_LAUNCHED();
     return 0;
 }

@@ -12,13 +12,16 @@ dev = torch.device("cuda")
 x = torch.randn(B * T, D, device=dev); W = torch.randn(D, D, device=dev) * 0.1; bias = torch.randn(D, device=dev)
 W3 = torch.randn(3 * D, D, device=dev) * 0.1; b3 = torch.randn(3 * D, device=dev)
 g, be = torch.ones(D, device=dev), torch.zeros(D, device=dev)
-out = torch.empty(B * T, D, device=dev)
+out = torch.empty(B * T, D, device=dev); pre = torch.empty(B * T, D, device=dev)
+x3 = torch.randn(B * T, 3 * D, device=dev); W384 = torch.randn(D, 3 * D, device=dev) * 0.1
 cases = {
     "plain": lambda: ops.gemm_tc(x, W, bias, out=out),
     "residual": lambda: ops.gemm_tc(x, W, bias, out=out, res=x),
     "aux": lambda: ops.gemm_tc(x, W, None, out=out, act="mul_quickgelu_grad", aux=x),
     "ln_qkv_planes": lambda: ops.gemm_tc(x, W3, b3, ln=(g, be), want_stats=True, want_split=True, want_c=False),
     "planes_out": lambda: ops.gemm_tc(x, W, None, out=out, want_split=True),
+    "ln_fc_gelu_preact": lambda: ops.gemm_tc(x, W, bias, out=out, ln=(g, be), want_stats=True, act="quickgelu", preact=pre),
+    "k384": lambda: ops.gemm_tc(x3, W384, None, out=out),
 }
 names = {1: "ld:begin", 2: "ld:stage free", 3: "ld:stored", 10: "mma:begin", 11: "mma:a_full", 12: "mma:issued", 20: "ep:begin", 21: "ep:c_full", 22: "ep:chunk", 23: "ep:tmem loaded", 24: "ep:staged", 25: "ep:batch stored"}
 fn = lib.dip_debug_set_trace_gemm; fn.restype = C.c_int; fn.argtypes = [C.c_void_p]
@@ -42,7 +45,7 @@ for name, f in cases.items():
     t0 = min(e[0] for e in evs)
     evs = sorted((((c - t0) & 0xffffffff), t, e) for c, t, e in evs)
     tiles = sorted(set(t for _, t, _ in evs))
-    show = tiles[3:5]
+    show = [3, 4, 3 * 148, 4 * 148]
     for c, t, e in evs:
         if t in show: print("   %8d  tile %5d  %s" % (c, t, names.get(e, e)))
     st = [c for c, t, e in evs if e == 3]

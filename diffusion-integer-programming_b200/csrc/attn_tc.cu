@@ -367,32 +367,37 @@ constexpr uint32_t IDESC_ACC = instr_desc(128, 128, 0, 1);    // P/dS (tensor me
 // =============================================================================================
 // backward, dQ: query-stationary with 64-key tiles
 // =============================================================================================
-// The dQ pass needs neither P nor a second accumulator, and its V tile is dead as soon as dP is formed: K is double-buffered
-// (it is also the B operand of dS.K), V single-buffered, score MMAs at N = 128.
-//   G1 = Q.[K_hi;K_lo]^T (= S), G2 = dO.[V_hi;V_lo]^T (= dP), dS = P (dP - delta) / sqrt(d), dQ += dS.K
-// shared memory: Q hi/lo, dO hi/lo (128 KB) | K ring 2 x 32 KB | V 32 KB; a streamed tile is [d-half][hi,lo][64 keys][64 d]
-// tensor memory: [0,128) G1, [128,256) G2, [256,384) dQ, [384,512) two dS buffers of (32 hi + 32 lo) packed columns
+//   S = Q.[K_hi;K_lo]^T, dP = dO.[V_hi;V_lo]^T, dS = P (dP - delta) / sqrt(d), dQ += dS K
+// The dQ pass needs neither P nor a second accumulator, which leaves tensor memory for more than accumulators: the dO planes
+// (A operand of the dP GEMM) live THERE -- loaded once per CTA by the row threads -- and dS is written in place of the dP it was
+// computed from.  That frees the 64 KB of shared memory dO would occupy: the K ring is three deep (K_j is read by S_j, issued one
+// tile early, and again by dS_j.K_j), the V ring two.  One issuer warp, in the order
+//      dP_j , S_{j+1} , dQ += dS_j K_j , dP_{j+1} , ...
+// so that the score GEMM of the next tile runs while the row threads turn (S_j, dP_j) into dS_j, and -- the tensor pipe executing
+// in issue order -- dP_{j+1} overwrites dS_j only after the product that reads it.
+// shared memory: Q hi/lo (64 KB) | K ring 3 x 32 KB | V ring 2 x 32 KB; a streamed tile is [d-half][hi,lo][64 keys][64 d]
+// tensor memory: [0,128) S, [128,256) dP then dS, [256,384) dQ, [384,512) dO hi | dO lo (64 packed columns each)
 constexpr int QT = 64;
 constexpr uint32_t Q_TILE = 32768;
-constexpr uint32_t QOFF_X = 0, QOFF_Y = 2 * ST_PLANE, QOFF_U = 4 * ST_PLANE, QOFF_W = QOFF_U + 2 * Q_TILE, QOFF_BAR = QOFF_W + Q_TILE;
+constexpr uint32_t QOFF_X = 0, QOFF_Y = 2 * ST_PLANE, QOFF_U = 4 * ST_PLANE, QOFF_W = QOFF_U + 2 * Q_TILE, QOFF_BAR = QOFF_W + Q_TILE;      // dK/dV kernel
 constexpr uint32_t QOFF_BITS = QOFF_BAR + 192;
 constexpr uint32_t DQ_SMEM = QOFF_BAR + 256;
-static_assert(QOFF_BAR == 229376 && DQ_SMEM <= SMEM_LIMIT, "dQ kernel shared memory");
-constexpr uint32_t QTM_G1 = 0, QTM_G2 = 128, QTM_ACC = 256, QTM_DS = 384;
+static_assert(QOFF_BAR == 229376 && DQ_SMEM <= SMEM_LIMIT, "backward kernels shared memory");
+constexpr uint32_t DOFF_K = 2 * ST_PLANE, DOFF_V = DOFF_K + 3 * Q_TILE;                                                                      // dQ kernel
+static_assert(DOFF_V + 2 * Q_TILE == QOFF_BAR, "dQ kernel shared memory");
+constexpr uint32_t QTM_G1 = 0, QTM_G2 = 128, QTM_ACC = 256, QTM_DO = 384;
 constexpr uint32_t IDESC_G128 = instr_desc(128, 128, 0, 0);
-enum { D_XFULL = 0, D_UFULL = 1, D_UEMPTY = 3, D_WFULL = 5, D_WEMPTY = 6, D_G1FULL = 7, D_G1FREE = 8, D_G2FULL = 9, D_G2FREE = 10, D_DSFULL = 11, D_DSFREE = 13,
-       D_DONE = 15 };
+enum { D_XFULL = 0, D_DOFULL = 1, D_KFULL = 2, D_KEMPTY = 5, D_VFULL = 8, D_VEMPTY = 10, D_SFULL = 12, D_SFREE = 13, D_DPFULL = 14, D_DSFULL = 15, D_DONE = 16 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
-                      const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64,
-                      const __grid_constant__ CUtensorMap tm_do_hi128, const __grid_constant__ CUtensorMap tm_do_lo128, float* __restrict__ dq, int ld_d,
-                      const float* __restrict__ lse, const float* __restrict__ delta, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T,
-                      int q_begin) {
+                      const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64, const uint4* __restrict__ do_hi,
+                      const uint4* __restrict__ do_lo, float* __restrict__ dq, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
+                      const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin) {
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
     volatile uint64_t* bits_ring = reinterpret_cast<volatile uint64_t*>(sm + QOFF_BITS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -403,18 +408,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[D_XFULL], 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[D_UFULL + s], 1);
-            mbar_init(&bars[D_UEMPTY + s], 1);
-            mbar_init(&bars[D_DSFULL + s], ROW_THREADS);
-            mbar_init(&bars[D_DSFREE + s], 1);
-        }
-        mbar_init(&bars[D_WFULL], 1);
-        mbar_init(&bars[D_WEMPTY], 1);
-        mbar_init(&bars[D_G1FULL], 1);
-        mbar_init(&bars[D_G1FREE], ROW_THREADS);
-        mbar_init(&bars[D_G2FULL], 1);
-        mbar_init(&bars[D_G2FREE], ROW_THREADS);
+        mbar_init(&bars[D_DOFULL], ROW_THREADS);
+        for (int s = 0; s < 3; ++s) { mbar_init(&bars[D_KFULL + s], 1); mbar_init(&bars[D_KEMPTY + s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[D_VFULL + s], 1); mbar_init(&bars[D_VEMPTY + s], 1); }
+        mbar_init(&bars[D_SFULL], 1);
+        mbar_init(&bars[D_SFREE], ROW_THREADS);
+        mbar_init(&bars[D_DPFULL], 1);
+        mbar_init(&bars[D_DSFULL], ROW_THREADS);
         mbar_init(&bars[D_DONE], 1);
         mbar_fence_init();
     }
@@ -427,116 +427,118 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
 
     if (warp == W_PRODUCER) {
         if (lane == 0) {
-            mbar_expect_tx(&bars[D_XFULL], 4 * ST_PLANE);
+            mbar_expect_tx(&bars[D_XFULL], 2 * ST_PLANE);
             for (int kb = 0; kb < 2; ++kb) {
                 tma_load_3d(sm + QOFF_X + kb * 16384, &tm_qkv_hi128, &bars[D_XFULL], kb * 64, r0, b);
                 tma_load_3d(sm + QOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[D_XFULL], kb * 64, r0, b);
-                tma_load_3d(sm + QOFF_Y + kb * 16384, &tm_do_hi128, &bars[D_XFULL], kb * 64, r0, b);
-                tma_load_3d(sm + QOFF_Y + ST_PLANE + kb * 16384, &tm_do_lo128, &bars[D_XFULL], kb * 64, r0, b);
             }
         }
         for (int j = 0; j < n_tiles; ++j) {
-            const int s = j & 1;
+            const int sk = j % 3, sv = j & 1;
             const int k0 = j * QT + lane, k1 = k0 + 32;
             const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
             const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
             const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
             if (lane == 0) {
-                // V first: it is single-buffered and dP_j opens the tile; K_j is not needed before S_j, two products later
-                TR(42, j);
-                if (j >= 1) mbar_wait(&bars[D_WEMPTY], (j - 1) & 1);
-                TR(43, j);
-                mbar_expect_tx(&bars[D_WFULL], Q_TILE);
-                uint8_t* dw = sm + QOFF_W;
-                for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_3d(dw + kb * 16384, &tm_qkv_hi64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);                // V hi
-                    tma_load_3d(dw + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_WFULL], 256 + kb * 64, j * QT, b);         // V lo
-                }
                 TR(40, j);
-                if (j >= 2) mbar_wait(&bars[D_UEMPTY + s], ((j >> 1) - 1) & 1);
+                if (j >= 3) mbar_wait(&bars[D_KEMPTY + sk], ((j / 3) - 1) & 1);
                 TR(41, j);
                 bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);
-                mbar_expect_tx(&bars[D_UFULL + s], Q_TILE);
-                uint8_t* du = sm + QOFF_U + s * Q_TILE;
+                mbar_expect_tx(&bars[D_KFULL + sk], Q_TILE);
+                uint8_t* du = sm + DOFF_K + sk * Q_TILE;
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_3d(du + kb * 16384, &tm_qkv_hi64, &bars[D_UFULL + s], 128 + kb * 64, j * QT, b);            // K hi, d-half kb
-                    tma_load_3d(du + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_UFULL + s], 128 + kb * 64, j * QT, b);     // K lo
+                    tma_load_3d(du + kb * 16384, &tm_qkv_hi64, &bars[D_KFULL + sk], 128 + kb * 64, j * QT, b);            // K hi, d-half kb
+                    tma_load_3d(du + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_KFULL + sk], 128 + kb * 64, j * QT, b);     // K lo
+                }
+                TR(42, j);
+                if (j >= 2) mbar_wait(&bars[D_VEMPTY + sv], ((j >> 1) - 1) & 1);
+                TR(43, j);
+                mbar_expect_tx(&bars[D_VFULL + sv], Q_TILE);
+                uint8_t* dw = sm + DOFF_V + sv * Q_TILE;
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(dw + kb * 16384, &tm_qkv_hi64, &bars[D_VFULL + sv], 256 + kb * 64, j * QT, b);            // V hi
+                    tma_load_3d(dw + kb * 16384 + 8192, &tm_qkv_lo64, &bars[D_VFULL + sv], 256 + kb * 64, j * QT, b);     // V lo
                 }
             }
             __syncwarp();
         }
     } else if (warp == W_MMA) {
-        // One issuer, in the order  dP_j , dS_{j-1}.K_{j-1} , S_j : the accumulating product runs before the score GEMM of the next K
-        // tile, so K_{j-1}'s buffer is free again a whole score GEMM before K_{j+1} is needed -- the K ring is only two deep.
-        // Warp-uniform control flow, the elected lane issues (see elect_one).
-        const uint64_t dX = smem_desc(smem_u32(sm + QOFF_X), 16, 1024), dY = smem_desc(smem_u32(sm + QOFF_Y), 16, 1024);
-        const uint64_t dU = smem_desc(smem_u32(sm + QOFF_U), 16, 1024), dW = smem_desc(smem_u32(sm + QOFF_W), 16, 1024);
-        const uint64_t dUmn = smem_desc(smem_u32(sm + QOFF_U), 16384, 1024);
-        auto issue_G = [&](uint64_t st, uint64_t tp, uint32_t dst) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int pl = 0; pl < 2; ++pl)                      // A = stationary hi, then lo, into the same 128 columns
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        tc_mma(dst, desc_adv(st, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
-                        acc = 1;
-                    }
-        };
-        auto issue_acc = [&](int j) {
-            const int s = j & 1, pb = j & 1;
-            TR(26, j);
-            mbar_wait(&bars[D_DSFULL + pb], (j >> 1) & 1);
-            TR(27, j);
+        // warp-uniform control flow, the elected lane issues (see elect_one)
+        const uint64_t dX = smem_desc(smem_u32(sm + QOFF_X), 16, 1024);
+        const uint64_t dK = smem_desc(smem_u32(sm + DOFF_K), 16, 1024), dKmn = smem_desc(smem_u32(sm + DOFF_K), 16384, 1024);
+        const uint64_t dV = smem_desc(smem_u32(sm + DOFF_V), 16, 1024);
+        auto issue_S = [&](int j) {                             // S_j = Q . [K_hi;K_lo]^T, both operands in shared memory
+            const int sk = j % 3;
+            TR(24, j);
+            mbar_wait(&bars[D_KFULL + sk], (j / 3) & 1);
+            if (j >= 1) mbar_wait(&bars[D_SFREE], (j - 1) & 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint64_t tl = desc_adv(dUmn, s * Q_TILE);
-                const uint32_t ds = tmem + QTM_DS + pb * 64;
+                const uint64_t tp = desc_adv(dK, sk * Q_TILE);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            tc_mma(tmem + QTM_G1, desc_adv(dX, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
+                            acc = 1;
+                        }
+                tc_commit(&bars[D_SFULL]);
+            }
+            __syncwarp();
+            TR(25, j);
+        };
+        mbar_wait(&bars[D_XFULL], 0);
+        mbar_wait(&bars[D_DOFULL], 0);
+        issue_S(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int sk = j % 3, sv = j & 1;
+            TR(20, j);
+            mbar_wait(&bars[D_VFULL + sv], (j >> 1) & 1);
+            TR(21, j);
+            tc_fence_after();
+            if (elect_one()) {                                      // dP_j = dO (tensor memory) . [V_hi;V_lo]^T
+                const uint64_t tp = desc_adv(dV, sv * Q_TILE);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            tc_mma_ts(tmem + QTM_G2, tmem + QTM_DO + pl * 64 + (kb * 4 + ks) * 8, desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
+                            acc = 1;
+                        }
+                tc_commit(&bars[D_DPFULL]);
+                tc_commit(&bars[D_VEMPTY + sv]);
+            }
+            __syncwarp();
+            TR(22, j);
+            if (j + 1 < n_tiles) issue_S(j + 1);
+            TR(26, j);
+            mbar_wait(&bars[D_DSFULL], j & 1);
+            TR(27, j);
+            tc_fence_after();
+            if (elect_one()) {                                      // dQ += dS_j K_j ; dS_j sits in the dP region (see the row threads)
+                const uint64_t tl = desc_adv(dKmn, sk * Q_TILE);
                 uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        // dS hi, hi, lo (32 packed columns per plane) x K hi, lo, hi as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step
-                        tc_mma_ts(tmem + QTM_ACC, ds + (pass == 2 ? 32 : 0) + ks * 8, desc_adv(tl, (pass == 1 ? 8192 : 0) + ks * 2048), IDESC_ACC, acc);
+                        // dS hi, hi, lo x K hi, lo, hi as MN-major B: d-halves 16384 bytes apart, 16 keys per k-step
+                        tc_mma_ts(tmem + QTM_ACC, tmem + QTM_G2 + (ks >> 1) * 32 + (ks & 1) * 8 + (pass == 2 ? 16 : 0),
+                                  desc_adv(tl, (pass == 1 ? 8192 : 0) + ks * 2048), IDESC_ACC, acc);
                         acc = 1;
                     }
                 }
-                tc_commit(&bars[D_DSFREE + pb]);
-                tc_commit(&bars[D_UEMPTY + s]);
+                tc_commit(&bars[D_KEMPTY + sk]);
             }
             __syncwarp();
             TR(28, j);
-        };
-        mbar_wait(&bars[D_XFULL], 0);
-        for (int j = 0; j < n_tiles; ++j) {
-            const int s = j & 1;
-            TR(20, j);
-            mbar_wait(&bars[D_WFULL], j & 1);
-            if (j >= 1) mbar_wait(&bars[D_G2FREE], (j - 1) & 1);
-            TR(21, j);
-            tc_fence_after();
-            if (elect_one()) {
-                issue_G(dY, dW, tmem + QTM_G2);                                       // dP_j first: its V tile is single-buffered
-                tc_commit(&bars[D_G2FULL]);
-                tc_commit(&bars[D_WEMPTY]);
-            }
-            __syncwarp();
-            TR(22, j);
-            if (j >= 1) issue_acc(j - 1);                                             // dQ += dS_{j-1} K_{j-1}: frees K_{j-1} before S_j starts
-            mbar_wait(&bars[D_UFULL + s], (j >> 1) & 1);
-            if (j >= 1) mbar_wait(&bars[D_G1FREE], (j - 1) & 1);
-            TR(24, j);
-            tc_fence_after();
-            if (elect_one()) {
-                issue_G(dX, desc_adv(dU, s * Q_TILE), tmem + QTM_G1);                 // S_j
-                tc_commit(&bars[D_G1FULL]);
-            }
-            __syncwarp();
-            TR(25, j);
         }
-        issue_acc(n_tiles - 1);
         if (elect_one()) tc_commit(&bars[D_DONE]);
         __syncwarp();
     } else if (warp < 8) {
@@ -551,48 +553,60 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             row_lse2 = lse[(int64_t)row_base + r_idx] * LOG2E;
             row_delta = delta[(int64_t)row_base + r_idx];
         }
-        for (int j = 0; j < n_tiles; ++j) {
-            const int pb = j & 1;
-            TR(30, j);
-            mbar_wait(&bars[D_G2FULL], j & 1);
-            TR(31, j);
-            tc_fence_after();
-            float dp[32];
-            {
-                float t[32];
-                tmem_ld32x2(lane_addr + QTM_G2 + h * 32, dp, lane_addr + QTM_G2 + 64 + h * 32, t);
-                tc_fence_before();
-                mbar_arrive(&bars[D_G2FREE]);
+        {
+            // this thread's dO plane (h = 0: hi, h = 1: lo) of its query row -> tensor memory: 128 bf16 = 64 packed columns
+            const uint4* src = (h == 0 ? do_hi : do_lo) + ((int64_t)row_base + r_idx) * 16;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) dp[c] = (dp[c] + t[c] - row_delta) * SM_SCALE;
-            }
-            TR(32, j);
-            mbar_wait(&bars[D_G1FULL], j & 1);
-            TR(33, j);
-            tc_fence_after();
-            uint32_t dh[16], dl[16];
-            {
-                float sc[32], t[32];
-                tmem_ld32x2(lane_addr + QTM_G1 + h * 32, sc, lane_addr + QTM_G1 + 64 + h * 32, t);
-                tc_fence_before();
-                mbar_arrive(&bars[D_G1FREE]);
-                const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const bool ok0 = row_ok && !((bad >> (2 * c)) & 1u), ok1 = row_ok && !((bad >> (2 * c + 1)) & 1u);
-                    const float p0 = ex2_approx(fmaf(sc[2 * c] + t[2 * c], SC2, -row_lse2)), p1 = ex2_approx(fmaf(sc[2 * c + 1] + t[2 * c + 1], SC2, -row_lse2));
-                    split2(ok0 ? p0 * dp[2 * c] : 0.f, ok1 ? p1 * dp[2 * c + 1] : 0.f, dh[c], dl[c]);
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = row_ok ? __ldg(src + c * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
+                    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
                 }
+                tmem_st16(lane_addr + QTM_DO + h * 64 + c * 16, w);
             }
-            if (j >= 2) mbar_wait(&bars[D_DSFREE + pb], ((j >> 1) - 1) & 1);     // dS.K of tile j-2 is done with this buffer
-            TR(34, j);
-            tc_fence_after();
-            const uint32_t pd = lane_addr + QTM_DS + pb * 64 + h * 16;
-            tmem_st16(pd, dh);
-            tmem_st16(pd + 32, dl);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars[D_DSFULL + pb]);
+            mbar_arrive(&bars[D_DOFULL]);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            TR(30, j);
+            mbar_wait(&bars[D_SFULL], j & 1);
+            TR(31, j);
+            tc_fence_after();
+            float pr[32];
+            {
+                float t[32];
+                tmem_ld32x2(lane_addr + QTM_G1 + h * 32, pr, lane_addr + QTM_G1 + 64 + h * 32, t);
+                tc_fence_before();
+                mbar_arrive(&bars[D_SFREE]);
+                const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const bool ok = row_ok && !((bad >> c) & 1u);
+                    pr[c] = ok ? ex2_approx(fmaf(pr[c] + t[c], SC2, -row_lse2)) * SM_SCALE : 0.f;
+                }
+            }
+            TR(32, j);
+            mbar_wait(&bars[D_DPFULL], j & 1);
+            TR(33, j);
+            tc_fence_after();
+            {
+                float dp[32], t[32];
+                uint32_t dh[16], dl[16];
+                tmem_ld32x2(lane_addr + QTM_G2 + h * 32, dp, lane_addr + QTM_G2 + 64 + h * 32, t);
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    split2(pr[2 * c] * (dp[2 * c] + t[2 * c] - row_delta), pr[2 * c + 1] * (dp[2 * c + 1] + t[2 * c + 1] - row_delta), dh[c], dl[c]);
+                TR(34, j);
+                // in place: the packed planes go into the first 32 of the 64 dP columns this thread has just read
+                tmem_st16(lane_addr + QTM_G2 + h * 32, dh);
+                tmem_st16(lane_addr + QTM_G2 + h * 32 + 16, dl);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[D_DSFULL]);
+            }
             TR(35, j);
         }
         mbar_wait(&bars[D_DONE], 0);
@@ -991,14 +1005,12 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
         attr = true;
     }
     cudaStream_t st = as_stream(stream);
-    CUtensorMap q_hi128, q_lo128, d_hi128, d_lo128;
+    CUtensorMap q_hi128, q_lo128;
     DIP_TRY(make_tmap_bf16_3d(&q_hi128, qkv_hi, B, T, 3 * D, 3 * D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
     CUtensorMap q_hi64, q_lo64;
     DIP_TRY(make_tmap_bf16_3d(&q_hi64, qkv_hi, B, T, 3 * D, 3 * D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&q_lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
-    DIP_TRY(make_tmap_bf16_3d(&d_hi128, do_hi, B, T, D, D, 128, 64));
-    DIP_TRY(make_tmap_bf16_3d(&d_lo128, do_lo, B, T, D, D, 128, 64));
     CUtensorMap d_hi64, d_lo64;
     DIP_TRY(make_tmap_bf16_3d(&d_hi64, do_hi, B, T, D, D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&d_lo64, do_lo, B, T, D, D, 64, 64));
@@ -1019,8 +1031,9 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     {
         dim3 grid(cdiv(T - q_begin, 128), B);      // queries q_begin.. stationary, all keys streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
-        tcattn::attn_bwd_dq_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, d_hi128, d_lo128, dq, ld_d, lse,
-                                                                                       delta_ws, key_mask, mask_stride, T, q_begin);
+        tcattn::attn_bwd_dq_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, reinterpret_cast<const uint4*>(do_hi),
+                                                                                       reinterpret_cast<const uint4*>(do_lo), dq, ld_d, lse, delta_ws, key_mask,
+                                                                                       mask_stride, T, q_begin);
         DIP_LAUNCHED();
     }
     return 0;

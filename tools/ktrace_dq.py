@@ -21,7 +21,7 @@ ops.attn_bwd_tc(hi, lo, o, d_o, lse, B, T, q_begin=2000, do_begin=2000)
 torch.cuda.synchronize(); fn(None)
 a = buf.cpu().numpy().astype(np.uint64)
 names_ks = {20: "mma:S begin", 22: "mma:S issued", 24: "mma:w_full", 25: "mma:dP issued", 23: "mma:dK issued", 28: "mma:dV issued", 30: "row:iter", 31: "row:g1_full", 32: "row:P stored", 33: "row:g2_full", 34: "row:dS ready+ds_free", 35: "row:dS stored", 40: "prod:U begin", 41: "prod:U issue", 42: "prod:W begin", 43: "prod:W issue"}
-names = {20: "mma:begin", 21: "mma:w_full+g2_free", 22: "mma:dP issued", 24: "mma:u_full+g1_free", 25: "mma:S issued", 26: "mma:acc begin", 27: "mma:ds_full", 28: "mma:acc issued",
+names = {20: "mma:begin", 21: "mma:v_full", 22: "mma:dP issued", 24: "mma:S begin", 25: "mma:S issued", 26: "mma:acc begin", 27: "mma:ds_full", 28: "mma:acc issued",
          30: "row:iter", 31: "row:dP full", 32: "row:dP loaded", 33: "row:S full", 34: "row:dS ready+ds_free", 35: "row:dS stored",
          40: "prod:U begin", 41: "prod:U issue", 42: "prod:W begin", 43: "prod:W issue"}
 # the dK/dV kernel logs into regions 0-3, the dQ kernel into regions 5-8

@@ -63,7 +63,12 @@ class NoisePredictV2(torch.nn.Module):
         if x_features.requires_grad:
             raise NotImplementedError("training / autograd through the denoiser is out of scope")
         if not bool((t == t[0]).all()):
-            raise NotImplementedError("per-sample timesteps are a training feature; the samplers use one t per call")
+            # per-sample timesteps (the loss evaluation of DDPMTrainer.forward): one engine call per distinct t
+            out = torch.empty_like(x_features, dtype=torch.float32)
+            for tv in torch.unique(t).tolist():
+                idx = torch.nonzero(t == tv).flatten()
+                out[idx] = self.forward(x_features[idx], t[idx], mip_features[idx], key_padding_mask[idx])
+            return out
         eng = default_engine()
         self.sync_engine(eng)
         x = x_features.detach().to(torch.float32).contiguous()
@@ -85,7 +90,8 @@ class NoisePredictV2(torch.nn.Module):
 
 class DDPMTrainer(torch.nn.Module):
     """Owner of the denoiser weights and of the beta schedule buffers (reference: diffusion.py:232-273,
-    334-335); same state_dict layout.  The training methods (forward / q_sample / p_losses) are out of scope."""
+    334-335); same state_dict layout.  forward / q_sample / p_losses evaluate the training loss (diffusion.py:275-332)
+    without gradients -- validation and monitoring; optimisation (dW kernels) is out of scope and nothing here is differentiable."""
 
     def __init__(self, attn_dim, n_heads, n_layers, device, timesteps=1000, loss_type="l2", beta_schedule="linear",
                  parameterization="x0"):
@@ -111,8 +117,48 @@ class DDPMTrainer(torch.nn.Module):
                           ("sqrt_recipm1_alphas_cumprod", np.sqrt(1. / ac - 1))):
             self.register_buffer(name, to_torch(val).to(self.device))
 
+    @torch.no_grad()
     def forward(self, x, condition, key_padding_mask):
-        raise NotImplementedError("DDPMTrainer.forward is the training loss (diffusion.py:275-279): out of scope")
+        """Loss evaluation at random timesteps (reference: diffusion.py:275-279); returns (pred_x_start, loss), no autograd graph."""
+        t = torch.randint(0, self.num_timesteps, (x.shape[0],), device=x.device).long()
+        return self.p_losses(x, t, condition, key_padding_mask)
+
+    def q_sample(self, x_start, t, noise=None):
+        """x_t = sqrt(abar_t) x_0 + sqrt(1 - abar_t) eps (reference: diffusion.py:281-284)."""
+        noise = default(noise, lambda: torch.randn_like(x_start))
+        return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start +
+                extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return (extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t -
+                extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+
+    @torch.no_grad()
+    def p_losses(self, x_start, t, condition, key_padding_mask, noise=None):
+        """reference: diffusion.py:292-308 (note its 'eps' branch reconstructs x_0 from the TRUE noise, kept)."""
+        noise = default(noise, lambda: torch.randn_like(x_start))
+        x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
+        model_out = self.predict_model(x_noisy, t, condition, key_padding_mask)
+        if self.parameterization == "eps":
+            target, pred_x_start = noise, self.predict_start_from_noise(x_noisy, t, noise)
+        elif self.parameterization == "x0":
+            target, pred_x_start = x_start, model_out
+        else:
+            raise NotImplementedError("unknown parameterization '%s'" % self.parameterization)
+        return pred_x_start, self.get_loss(model_out.squeeze(), target.squeeze(), key_padding_mask, mean=True)
+
+    def get_loss(self, pred, target, key_padding_mask, mean=True):
+        """reference: diffusion.py:310-332 (masked mean over the integer-variable tokens for 'l2')."""
+        if self.loss_type == "l1":
+            loss = (target - pred).abs()
+            return loss.mean() if mean else loss
+        if self.loss_type == "l2":
+            loss = torch.nn.functional.mse_loss(target, pred, reduction="none")
+            if not mean:
+                return loss
+            loss = loss.mean(dim=-1) * ~key_padding_mask
+            return (loss.sum(dim=-1) / (~key_padding_mask).sum(dim=-1)).mean()
+        raise NotImplementedError("unknown loss type '%s'" % self.loss_type)
 
     def get_predict_model(self):
         return self.predict_model

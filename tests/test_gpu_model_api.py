@@ -110,3 +110,35 @@ def test_no_cpu_path():
     s = md.DDIMSampler(tr, None, 1e3, 0.0, "cpu")
     with pytest.raises(_lib.DipError):
         s.sample(torch.zeros(1, 4, 128), torch.zeros(1, 4, dtype=torch.bool), S=5)
+
+
+@pytest.mark.parametrize("param", ["x0", "eps"])
+def test_trainer_loss_evaluation_matches_oracle(cuda, param):
+    """DDPMTrainer.p_losses / forward (reference: diffusion.py:275-332) as a forward-only loss evaluation with per-sample
+    timesteps: q_sample, the denoiser at each sample's own t (one engine call per distinct t), the masked l2 loss."""
+    from model.diffusion import DDPMTrainer
+    from oracle import restate
+    cs = small_case(B=4)
+    Wd = synth.denoiser_weights(1, seed=1)
+    tr = DDPMTrainer(128, 1, 1, cuda, parameterization=param)
+    tr.load_state_dict(tw(Wd), strict=False)
+    t = case_tensors(cs, cuda)
+    x0 = t["x"]
+    ts = torch.tensor([3, 977, 3, 500], device=cuda)
+    noise = torch.from_numpy(np.random.default_rng(4).standard_normal(tuple(x0.shape)).astype(np.float32)).to(cuda)
+    pred, loss = tr.p_losses(x0, ts, t["mipB"], t["kpmB"], noise=noise)
+    # oracle: same arithmetic on the CPU, sample by sample
+    buf = restate.trainer_buffers()
+    tc_ = case_tensors(cs)
+    x_noisy = torch.stack([float(np.sqrt(buf["alphas_cumprod"][k])) * tc_["x"][i] + float(np.sqrt(1.0 - buf["alphas_cumprod"][k])) * noise[i].cpu()
+                           for i, k in enumerate(ts.tolist())])
+    out = torch.cat([restate.denoiser_fwd(tw(Wd), x_noisy[i:i + 1], torch.tensor([k]), tc_["mipB"][i:i + 1], tc_["kpmB"][i:i + 1]) for i, k in enumerate(ts.tolist())])
+    target = tc_["x"] if param == "x0" else noise.cpu()
+    per_tok = ((target - out) ** 2).mean(-1) * ~tc_["kpmB"]
+    ref_loss = (per_tok.sum(-1) / (~tc_["kpmB"]).sum(-1)).mean()
+    assert abs(float(loss) - float(ref_loss)) < 1e-3 * abs(float(ref_loss))
+    if param == "x0":
+        assert rel_l2(pred, out) < 1e-3
+    torch.manual_seed(0)
+    p2, l2 = tr(x0, t["mipB"], t["kpmB"])                       # random timesteps: finite, right shapes, no autograd graph
+    assert p2.shape == x0.shape and torch.isfinite(l2) and not l2.requires_grad

@@ -99,6 +99,8 @@ PROTOTYPES = {
     "dip_conv_reduce": (i32, [vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, vp]),
     "dip_spmm_csr": (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
     "dip_gather_pad": (i32, [vp, vp, vp, i32, i32, vp]),
+    "dip_partial_select": (i32, [vp, vp, vp, i32, i32, i32, u64, u64, i32, i32, vp]),
+    "dip_axpby": (i32, [vp, vp, vp, f32, f32, i64, vp]),
     "dip_engine_create": (i32, [C.POINTER(vp)]),
     "dip_engine_destroy": (None, [vp]),
     "dip_engine_set_denoiser": (i32, [vp, vp, vp, vp, vp, C.POINTER(BlockWeights), i32, vp]),

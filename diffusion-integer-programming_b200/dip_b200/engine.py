@@ -21,8 +21,8 @@ BLOCK_KEYS = [
 ]
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _dev(t, dtype=torch.float32, device=None):
@@ -33,6 +33,19 @@ def _dev(t, dtype=torch.float32, device=None):
     if device is None:
         device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
     return t.to(device=device, dtype=dtype).contiguous()
+
+
+def _on_device(fn):
+    """Run an Engine method with the engine's device current (kernels launch on the current device's stream)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 def require_cuda():
@@ -69,6 +82,8 @@ class Engine:
         require_cuda()
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):
             h = C.c_void_p()
             check(self.lib.dip_engine_create(C.byref(h)))
@@ -78,6 +93,11 @@ class Engine:
         self.inst = None
         self.n_den = self.n_dec = 0
         self.precision = "tc"
+        # which module's weights the engine holds (set by the model.* mirrors' sync_engine): ownership lives HERE, so two model
+        # objects sharing the engine re-upload when they alternate
+        self.den_sig = None
+        self.dec_sig = None
+        self._current_key = None      # identity of the current instance as the model.* mirrors key it (reset by use_instance)
 
     def __del__(self):
         try:
@@ -123,6 +143,7 @@ class Engine:
             check(self.lib.dip_engine_set_denoiser(self.h, ptr(w1), ptr(b1), ptr(w2), ptr(b2), arr, n, _stream()))
             torch.cuda.current_stream().synchronize()   # weights were copied; sources may go away
         self.n_den = n
+        self.den_sig = None
 
     def set_decoder(self, sd):
         keep = []
@@ -136,12 +157,14 @@ class Engine:
             check(self.lib.dip_engine_set_decoder(self.h, arr, n, ptr(pw), ptr(pb), _stream()))
             torch.cuda.current_stream().synchronize()
         self.n_dec = n
+        self.dec_sig = None
 
     # ---- instance ------------------------------------------------------------------------------
-    def set_instance(self, mip, kpm, rows, cols, vals, M, b, c, a_int=None, b_int=None, c_int=None):
-        """mip (L,128) conditions of ONE instance; kpm (L,) bool; A as COO (rows, cols, vals) of shape
-        (M, n) with n = number of unmasked positions; b (M,), c (n,).  Optional exact-integer twin
-        a_int (aligned with rows/cols/vals, duplicates not allowed then), b_int, c_int."""
+    def prepare_instance(self, mip, kpm, rows, cols, vals, M, b, c, a_int=None, b_int=None, c_int=None):
+        """Build the device-side form of one instance ONCE (host CSR/CSC build by the library's deterministic coalescing sort, uploads,
+        the dip_instance struct): mip (L,128) conditions of ONE instance; kpm (L,) bool; A as COO (rows, cols, vals) of shape
+        (M, n) with n = number of unmasked positions; b (M,), c (n,).  Optional exact-integer twin a_int (aligned with
+        rows/cols/vals, duplicates not allowed then), b_int, c_int.  Returns a handle for use_instance()."""
         dev = self.device
         mip = _dev(mip, device=dev)
         L = mip.shape[0]
@@ -176,21 +199,35 @@ class Engine:
                      ("csr_val", "csr_val"), ("csc_colptr", "csc_colptr"), ("csc_row", "csc_row"), ("csc_val", "csc_val"),
                      ("b", "b"), ("c", "c"), ("csr_val_int", "csr_val_int"), ("b_int", "b_int"), ("c_int", "c_int")):
             setattr(inst, f, keep[k].data_ptr() if k in keep else None)
-        with torch.cuda.device(dev):
-            check(self.lib.dip_engine_set_instance(self.h, C.byref(inst), _stream()))
-        self._keep["inst"] = keep
-        self.inst = {"L": L, "n": n, "M": int(M), "nnz": int(csr["nnz"]), "has_int": a_int is not None}
+        return {"struct": inst, "keep": keep,
+                "info": {"L": L, "n": n, "M": int(M), "nnz": int(csr["nnz"]), "has_int": a_int is not None}}
+
+    def use_instance(self, prepared):
+        """Make a prepared instance the engine's current one (no host work beyond one library call)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.dip_engine_set_instance(self.h, C.byref(prepared["struct"]), _stream(self.device)))
+        self._current_key = None
+        self._keep["inst"] = prepared            # the library borrows the device arrays: keep them alive
+        self.inst = prepared["info"]
         return self.inst
 
-    def set_conditions(self, mip, kpm):
+    def set_instance(self, mip, kpm, rows, cols, vals, M, b, c, a_int=None, b_int=None, c_int=None):
+        """prepare_instance + use_instance."""
+        return self.use_instance(self.prepare_instance(mip, kpm, rows, cols, vals, M, b, c, a_int=a_int, b_int=b_int, c_int=c_int))
+
+    def prepare_conditions(self, mip, kpm):
         """Instance without constraints (unguided sampling / plain decoding): an empty 1-row system."""
         kpm = kpm.view(-1)
         n = int((~kpm.to(torch.bool)).sum())
         z = np.zeros(0, dtype=np.int64)
-        return self.set_instance(mip, kpm, z, z, np.zeros(0, dtype=np.float32), 1, np.zeros(1, dtype=np.float32),
-                                 np.zeros(n, dtype=np.float32))
+        return self.prepare_instance(mip, kpm, z, z, np.zeros(0, dtype=np.float32), 1, np.zeros(1, dtype=np.float32),
+                                     np.zeros(n, dtype=np.float32))
+
+    def set_conditions(self, mip, kpm):
+        return self.use_instance(self.prepare_conditions(mip, kpm))
 
     # ---- workspace -----------------------------------------------------------------------------
+    @_on_device
     def workspace(self, B):
         need = self.lib.dip_engine_workspace_bytes(self.h, int(B))
         if need == 0:
@@ -205,11 +242,14 @@ class Engine:
     def _x(self, x):
         if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
             raise _lib.DipError("latents must be a contiguous fp32 CUDA tensor")
+        if x.device != self.device:
+            raise _lib.DipError("latents live on %s but this engine was created on %s" % (x.device, self.device))
         if x.dim() != 3 or x.shape[1] != self.inst["L"] or x.shape[2] != D:
             raise _lib.DipError("latents must be (B, %d, 128), got %s" % (self.inst["L"], tuple(x.shape)))
         return x
 
     # ---- networks ------------------------------------------------------------------------------
+    @_on_device
     def denoise(self, x, t):
         x = self._x(x)
         out = torch.empty_like(x)
@@ -217,6 +257,7 @@ class Engine:
         check(self.lib.dip_engine_denoise(self.h, ptr(out), ptr(x), x.shape[0], float(t), ws, nb, _stream()))
         return out
 
+    @_on_device
     def decode(self, x, want_hidden=False):
         x = self._x(x)
         B = x.shape[0]
@@ -226,6 +267,7 @@ class Engine:
         check(self.lib.dip_engine_decode(self.h, ptr(p), ptr(y), ptr(x), B, ws, nb, _stream()))
         return (p, y) if want_hidden else p
 
+    @_on_device
     def guidance_grad(self, x, lam):
         x = self._x(x)
         B = x.shape[0]
@@ -242,6 +284,7 @@ class Engine:
     def ddim_coeffs(t, sqrt_at, s1m, c_dir, sqrt_aprev, sigma):
         return _lib.DdimCoeffs(float(t), float(sqrt_at), float(s1m), float(c_dir), float(sqrt_aprev), float(sigma))
 
+    @_on_device
     def guided_ddim_step(self, x, co, gs, lam, eps_param=False, noise=None, x0_out=None):
         x = self._x(x)
         ws, nb = self.workspace(x.shape[0])
@@ -249,12 +292,14 @@ class Engine:
                                                    int(eps_param), ptr(noise), ws, nb, _stream()))
         return x
 
+    @_on_device
     def ddim_step(self, x, co, eps_param=False, noise=None, x0_out=None):
         x = self._x(x)
         ws, nb = self.workspace(x.shape[0])
         check(self.lib.dip_engine_ddim_step(self.h, ptr(x), ptr(x0_out), x.shape[0], C.byref(co), int(eps_param), ptr(noise), ws, nb, _stream()))
         return x
 
+    @_on_device
     def guided_ddpm_step(self, x, co, gs, lam, eps_param=False, noise=None):
         x = self._x(x)
         ws, nb = self.workspace(x.shape[0])
@@ -262,12 +307,14 @@ class Engine:
                                                    ptr(noise), ws, nb, _stream()))
         return x
 
+    @_on_device
     def ddpm_step(self, x, co, eps_param=False, noise=None):
         x = self._x(x)
         ws, nb = self.workspace(x.shape[0])
         check(self.lib.dip_engine_ddpm_step(self.h, ptr(x), x.shape[0], C.byref(co), int(eps_param), ptr(noise), ws, nb, _stream()))
         return x
 
+    @_on_device
     def final_decode(self, x, want_p=True):
         """Decode + round + feasibility (sample.py:162-174).  Returns dict of device tensors."""
         x = self._x(x)
@@ -285,6 +332,7 @@ class Engine:
                                                ptr(out["viol_int"]), ptr(out["obj_int"]), ws, nb, _stream()))
         return out
 
+    @_on_device
     def sample_guided_ddim(self, x, steps, gs, lam, eps_param=False):
         """Whole S-step loop + final decode in ONE library call (in place on x)."""
         x = self._x(x)
@@ -305,15 +353,18 @@ class Engine:
         return out
 
 
-_default = None
+_default = {}
 
 
-def default_engine():
-    """Process-wide engine shared by the drop-in ``model.*`` classes."""
-    global _default
-    if _default is None:
-        _default = Engine()
-    return _default
+def default_engine(device=None):
+    """Per-device engine shared by the drop-in ``model.*`` classes (device: the tensors' CUDA device; default: the current one)."""
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if dev not in _default:
+        _default[dev] = Engine(dev)
+    return _default[dev]
 
 
 def randn(shape, seed, subseq, device=None):

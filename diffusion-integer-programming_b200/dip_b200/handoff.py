@@ -52,3 +52,27 @@ def unpack(values, mask, n):
     v = np.unpackbits(values, axis=1)[:, :n]
     m = np.unpackbits(mask, axis=1)[:, :n]
     return [{int(k): int(v[j, k]) for k in np.flatnonzero(m[j])} for j in range(v.shape[0])]
+
+
+# ---- device-side path ---------------------------------------------------------------------------
+def select_gpu(xbits, coverage, seed=0, instance_id=0, sample_base=0, reference_quirk=True):
+    """Selection + bit-packing on the GPU (dip_partial_select): xbits (B, n) uint8 CUDA tensor as returned by Engine.final_decode /
+    sample_guided_ddim.  Returns (values, mask) device tensors in the format of `pack`.  The subset of sample j is a pure function of
+    (seed, instance_id, sample_base + j) -- any sharding of samples over ranks selects the same variables -- and has exactly
+    int(n * coverage) members like the reference's `random.sample(range(n), num_vars)` (sample_partialsol.py:171,190)."""
+    from . import ops
+    n = xbits.shape[1]
+    return ops.partial_select(xbits, int(n * coverage), seed, instance_id, sample_base, first_sample_values=reference_quirk)
+
+
+def to_sol_text(var_names, values_row, mask_row, objective=None):
+    """One sample's partial solution in SCIP's .sol text format (name value per line, only the selected variables, in the column
+    order of A), ready for `readSolFile` / `scip -c "read x.sol"`; values_row / mask_row: one row of the packed form."""
+    n = len(var_names)
+    v = np.unpackbits(np.asarray(values_row, dtype=np.uint8))[:n]
+    m = np.unpackbits(np.asarray(mask_row, dtype=np.uint8))[:n]
+    lines = ["solution status: unknown"]
+    if objective is not None:
+        lines.append("objective value: %s" % objective)
+    lines += ["%s %d" % (var_names[k], int(v[k])) for k in np.flatnonzero(m)]
+    return "\n".join(lines) + "\n"

@@ -341,3 +341,32 @@ def gemm_tc_planes(a_hi, a_lo, W, bias=None, want_c=True, want_split=False):
     g.split_hi, g.split_lo = ptr(hi), ptr(lo)
     check(lib.dip_gemm_tc_planes(C.byref(g), ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), _stream()))
     return {"C": out, "hi": hi, "lo": lo}
+
+
+def axpby(x, y=None, a=1.0, b=1.0):
+    """a*x + b*y (y optional) on fp32 tensors of the same shape."""
+    lib = _lib.load()
+    x = _f32(x)
+    out = torch.empty_like(x)
+    check(lib.dip_axpby(ptr(out), ptr(x), ptr(_f32(y)) if y is not None else None, float(a), float(b), x.numel(), _stream()))
+    return out
+
+
+def embedding_rows(weight, tokens):
+    """weight (V,128) fp32, tokens (L,) int64 -> (L,128): torch.nn.Embedding lookup (model/encoder.py:33) as a row gather."""
+    return gather_pad(weight, tokens, tokens.numel())
+
+
+def partial_select(xbits, k, seed, instance_id, sample_base=0, first_sample_values=True):
+    """Device-side partial-solution selection (sample_partialsol.py:172-199): xbits (B,n) uint8 0/1 ->
+    (value_bits, mask_bits), each (B, ceil(n/8)) uint8 in numpy.packbits order."""
+    lib = _lib.load()
+    if xbits.dtype != torch.uint8 or not xbits.is_cuda or not xbits.is_contiguous():
+        raise _lib.DipError("xbits must be a contiguous uint8 CUDA tensor")
+    B, n = xbits.shape
+    nb = (n + 7) // 8
+    mask = torch.empty((B, nb), dtype=torch.uint8, device=xbits.device)
+    vals = torch.empty((B, nb), dtype=torch.uint8, device=xbits.device)
+    check(lib.dip_partial_select(ptr(mask), ptr(vals), ptr(xbits), B, n, int(k), int(seed), int(instance_id), int(sample_base),
+                                 1 if first_sample_values else 0, _stream()))
+    return vals, mask

@@ -20,11 +20,29 @@ class CMSP(torch.nn.Module):
 
     def get_features(self, mip, x=None):
         """-> (mip_features (G,L,128), x_features | None, key_padding_mask (G,L) bool), cmsp.py:35-42."""
-        if x is not None:
-            raise NotImplementedError("encoding solutions (x is not None) belongs to training; out of scope")
         with torch.no_grad():
             mip_features, key_padding_mask = self.encode_mip(mip, mip.n_int_vars)
-        return mip_features, None, key_padding_mask
+            x_features = None
+            if x is not None:
+                x_features, key_padding_mask = self.encode_solution(x, mip.n_int_vars)
+        return mip_features, x_features, key_padding_mask
+
+    def encode_solution(self, x, n_int_vars):
+        """Pad each instance's 0/1 solution with token 2 to padding_len, then SolutionEncoder (cmsp.py:65-69, utils.get_padding)."""
+        sizes = [int(n_int_vars)] if isinstance(n_int_vars, int) else [int(v) for v in n_int_vars.tolist()]
+        if sum(sizes) != x.numel():
+            raise ValueError("n_int_vars does not add up to len(x)")
+        L = self.padding_len
+        tok = torch.full((len(sizes), L), 2, dtype=torch.int64, device=x.device)
+        mask = torch.ones((len(sizes), L), dtype=torch.bool, device=x.device)
+        off = 0
+        for g, n in enumerate(sizes):
+            if n > L:
+                raise ValueError("instance has %d integer variables but padding_len is %d" % (n, L))
+            tok[g, :n] = x[off:off + n].to(torch.int64)
+            mask[g, :n] = False
+            off += n
+        return self.sol_encoder(tok, mask), mask
 
     def encode_mip(self, mip, n_int_vars):
         """GNN -> gather int_indices -> zero pad to padding_len (cmsp.py:53-63, utils.get_padding)."""

@@ -14,7 +14,7 @@ import torch
 
 from dip_b200 import _lib
 from dip_b200.engine import Engine, default_engine
-from model.decoder import same_rows, weights_signature
+from model.decoder import _module_uid, same_rows, tensor_key, use_conditions, weights_signature
 from model.modules import QuickGELU, ResidualAttentionBlock
 from model.utils import (default, exists, extract_into_tensor, make_beta_schedule, make_ddim_sampling_parameters,
                          make_ddim_timesteps, noise_like, to_torch)
@@ -49,15 +49,17 @@ class NoisePredictV2(torch.nn.Module):
         self.mlp_xt = torch.nn.Sequential(OrderedDict([
             ("linear_1", torch.nn.Linear(2 * attn_dim, attn_dim)), ("geru", QuickGELU()),
             ("linear_2", torch.nn.Linear(attn_dim, attn_dim)), ("geru", QuickGELU())]))
-        self._sig = None
+        self._uid = next(_module_uid)
 
     def sync_engine(self, engine):
+        """Upload the weights unless the ENGINE already holds exactly these (the engine, not the module, remembers whose weights it
+        has: two trainers sharing one engine re-upload when they alternate)."""
         for blk in self.resblocks:
             blk.check_supported()
-        sig = (id(engine), weights_signature(self))
-        if sig != self._sig:
+        sig = (self._uid, weights_signature(self))
+        if engine.den_sig != sig:
             engine.set_denoiser({"predict_model." + k: v.detach() for k, v in self.state_dict().items()})
-            self._sig = sig
+            engine.den_sig = sig
 
     def forward(self, x_features, t, mip_features, key_padding_mask):
         if x_features.requires_grad:
@@ -69,16 +71,16 @@ class NoisePredictV2(torch.nn.Module):
                 idx = torch.nonzero(t == tv).flatten()
                 out[idx] = self.forward(x_features[idx], t[idx], mip_features[idx], key_padding_mask[idx])
             return out
-        eng = default_engine()
+        eng = default_engine(x_features.device)
         self.sync_engine(eng)
         x = x_features.detach().to(torch.float32).contiguous()
         tt = float(t[0])
         if same_rows(mip_features) and same_rows(key_padding_mask):
-            eng.set_conditions(mip_features[0], key_padding_mask[0])
+            use_conditions(eng, mip_features[0], key_padding_mask[0])
             return eng.denoise(x, tt)
         outs = []
         for i in range(x.shape[0]):
-            eng.set_conditions(mip_features[i], key_padding_mask[i])
+            use_conditions(eng, mip_features[i], key_padding_mask[i])
             outs.append(eng.denoise(x[i:i + 1], tt))
         return torch.cat(outs)
 
@@ -169,8 +171,8 @@ class _SamplerBase(torch.nn.Module):
     """Wave management shared by both samplers: one engine instance per distinct (conditions, mask) row
     group; in the reference's scripts every row is the same instance (sample.py:151-152)."""
 
-    def _engine(self):
-        eng = default_engine()
+    def _engine(self, device=None):
+        eng = default_engine(device)
         self.predict_model = self.model.predict_model
         self.predict_model.sync_engine(eng)
         return eng
@@ -188,19 +190,46 @@ class _SamplerBase(torch.nn.Module):
             return [slice(0, conditions.shape[0])]
         return [slice(i, i + 1) for i in range(conditions.shape[0])]
 
-    @staticmethod
-    def _coo(A):
-        if A.layout != torch.sparse_coo:
-            A = A.to_sparse()
-        idx = A._indices().detach().cpu().numpy()
-        return idx[0], idx[1], A._values().detach().to(torch.float32).cpu().numpy(), int(A.shape[0])
+    def _prepare(self, eng, conditions, key_padding_mask, waves, A, b, c):
+        """One prepared engine instance per wave, built BEFORE the step loop (host CSR/CSC sort + uploads happen here, never inside
+        it) and cached by the identity of A / b / c / the wave's conditions and mask rows ('the CSR cache keyed by the A
+        tensor identity'): a second call with the same tensors does no host work at all."""
+        cache = self.__dict__.setdefault("_inst_cache", OrderedDict())
+        coo, akey = None, None
+        if A is not None:
+            if A.layout != torch.sparse_coo:
+                A = A.to_sparse()
+            akey = (tensor_key(A._indices()), tensor_key(A._values()), tuple(A.shape))
+        out = []
+        for sl in waves:
+            crow, mrow = conditions[sl.start], key_padding_mask[sl.start]
+            key = (id(eng), akey, tensor_key(b), tensor_key(c), tensor_key(crow), tensor_key(mrow))
+            prep = cache.get(key)
+            if prep is None:
+                if A is None:
+                    prep = eng.prepare_conditions(crow, mrow)
+                else:
+                    if coo is None:
+                        idx = A._indices().detach().cpu().numpy()
+                        coo = (idx[0], idx[1], A._values().detach().to(torch.float32).cpu().numpy(), int(A.shape[0]))
+                    prep = eng.prepare_instance(crow, mrow, coo[0], coo[1], coo[2], coo[3], b, c)
+                # the entry keeps the keyed tensors alive: a freed tensor's address (and version 0) could otherwise be recycled by a
+                # different tensor and hit this entry
+                cache[key] = (prep, (A, b, c, conditions, key_padding_mask))
+                while len(cache) > 8:
+                    cache.popitem(last=False)
+            else:
+                cache.move_to_end(key)
+                prep = prep[0]
+            out.append((key, prep))
+        return out
 
-    def _set_instance(self, eng, conditions, key_padding_mask, sl, coo, b, c):
-        if coo is None:
-            eng.set_conditions(conditions[sl.start], key_padding_mask[sl.start])
-        else:
-            rows, cols, vals, M = coo
-            eng.set_instance(conditions[sl.start], key_padding_mask[sl.start], rows, cols, vals, M, b, c)
+    @staticmethod
+    def _use(eng, keyed):
+        key, prep = keyed
+        if getattr(eng, "_current_key", None) != key:
+            eng.use_instance(prep)
+            eng._current_key = key
 
 
 class DDPMSampler(_SamplerBase):
@@ -247,24 +276,24 @@ class DDPMSampler(_SamplerBase):
         return _lib.DdpmCoeffs(float(i), float(h["posterior_mean_coef1"][i]), float(h["posterior_mean_coef2"][i]), float(std),
                                0.0 if i == 0 else 1.0, float(h["sqrt_recip_alphas_cumprod"][i]), float(h["sqrt_recipm1_alphas_cumprod"][i]))
 
-    def _loop(self, conditions, key_padding_mask, coo, b, c):
+    def _loop(self, conditions, key_padding_mask, A, b, c):
         self._check(conditions, key_padding_mask)
-        eng = self._engine()
-        guided = coo is not None
+        eng = self._engine(conditions.device)
+        guided = A is not None
         if guided:
+            if self.decoder is None:
+                raise _lib.DipError("guided sampling needs a decoder")
             self.decoder.sync_engine(eng)
         self.conditions, self.batch_size, self.key_padding_mask = conditions, conditions.shape[0], key_padding_mask
         x = torch.randn_like(conditions).contiguous()
         eps = self.parameterization == "eps"
         waves = self._waves(conditions, key_padding_mask)
-        if len(waves) == 1:
-            self._set_instance(eng, conditions, key_padding_mask, waves[0], coo, b, c)
+        prepared = self._prepare(eng, conditions, key_padding_mask, waves, A, b, c)
         for i in reversed(range(self.num_timesteps)):
             co = self._coeffs(i)
             noise = noise_like(x.shape, x.device)          # drawn every step, like the reference (:447, :458)
-            for sl in waves:
-                if len(waves) > 1:
-                    self._set_instance(eng, conditions, key_padding_mask, sl, coo, b, c)
+            for sl, prep in zip(waves, prepared):
+                self._use(eng, prep)
                 if guided:
                     eng.guided_ddpm_step(x[sl], co, self.gradient_scale, self.obj_guided_coef, eps, noise[sl])
                 else:
@@ -277,7 +306,7 @@ class DDPMSampler(_SamplerBase):
 
     @torch.no_grad()
     def constraint_guided_sample(self, conditions, key_padding_mask, A, b, c):
-        return self._loop(conditions, key_padding_mask, self._coo(A), b, c)
+        return self._loop(conditions, key_padding_mask, A, b, c)
 
 
 class DDIMSampler(_SamplerBase):
@@ -324,11 +353,11 @@ class DDIMSampler(_SamplerBase):
         s1m = self.ddim_sqrt_one_minus_alphas[index].float()
         return Engine.ddim_coeffs(step, a_t.sqrt(), s1m, (1. - a_prev - sigma ** 2).sqrt(), a_prev.sqrt(), sigma)
 
-    def _loop(self, conditions, key_padding_mask, S, coo, b, c):
+    def _loop(self, conditions, key_padding_mask, S, A, b, c):
         self._check(conditions, key_padding_mask)
         self.make_schedule(ddim_num_steps=S)
-        eng = self._engine()
-        guided = coo is not None
+        eng = self._engine(conditions.device)
+        guided = A is not None
         if guided:
             if self.decoder is None:
                 raise _lib.DipError("guided sampling needs a decoder")
@@ -342,17 +371,15 @@ class DDIMSampler(_SamplerBase):
         x = x.detach().to(torch.float32).clone().contiguous()
         eps = self.parameterization == "eps"
         waves = self._waves(conditions, key_padding_mask)
-        if len(waves) == 1:
-            self._set_instance(eng, conditions, key_padding_mask, waves[0], coo, b, c)
+        prepared = self._prepare(eng, conditions, key_padding_mask, waves, A, b, c)
         for step in reversed(range(S)):
             index = S - step - 1
             co = self._coeffs(step, index)
             noise = None
             if co.sigma != 0.0 or self.strict_rng:
                 noise = noise_like(x.shape, x.device)
-            for sl in waves:
-                if len(waves) > 1:
-                    self._set_instance(eng, conditions, key_padding_mask, sl, coo, b, c)
+            for sl, prep in zip(waves, prepared):
+                self._use(eng, prep)
                 nz = noise[sl] if (noise is not None and co.sigma != 0.0) else None
                 if guided:
                     eng.guided_ddim_step(x[sl], co, self.gradient_scale, self.obj_guided_coef, eps, nz)
@@ -366,7 +393,7 @@ class DDIMSampler(_SamplerBase):
 
     @torch.no_grad()
     def constraint_guided_sample(self, conditions, key_padding_mask, A, b, c, S=100):
-        return self._loop(conditions, key_padding_mask, S, self._coo(A), b, c)
+        return self._loop(conditions, key_padding_mask, S, A, b, c)
 
     @torch.no_grad()
     def sample(self, conditions, key_padding_mask, S=100):

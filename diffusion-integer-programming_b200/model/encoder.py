@@ -18,8 +18,9 @@ class MIPEncoder(torch.nn.Module):
 
 
 class SolutionEncoder(torch.nn.Module):
-    """Parameter container for checkpoint compatibility (reference: encoder.py:24-36).  Encoding
-    solutions is part of contrastive training, not of reverse sampling: out of scope."""
+    """Token embedding of a (padded) 0/1/2 solution + attention blocks (reference: encoder.py:24-36), forward only: the x-side
+    features of CMSP.get_features(mip, x) -- the latents the diffusion model is trained to reproduce (train_diffusion.py).  The
+    reference adds the block's output to its input although the block is residual already (`x = x + module(x, mask)`): kept."""
 
     def __init__(self, emb_num: int, attn_dim: int, num_heads: int, layers: int, attn_mask: torch.Tensor = None):
         super().__init__()
@@ -28,5 +29,17 @@ class SolutionEncoder(torch.nn.Module):
         self.layers = layers
         self.resblocks = torch.nn.ModuleList([ResidualAttentionBlock(attn_dim, num_heads, attn_mask) for _ in range(layers)])
 
+    @torch.no_grad()
     def forward(self, x, key_padding_mask=None):
-        raise NotImplementedError("SolutionEncoder.forward belongs to CMSP training (out of scope of the sampling path)")
+        from dip_b200 import ops
+        if x.dim() != 2:
+            raise ValueError("solutions must be (G, L) integer tokens")
+        G, L = x.shape
+        emb = self.embedding.weight.detach().contiguous()
+        tok = x.to(torch.int64)
+        if int(tok.min()) < 0 or int(tok.max()) >= emb.shape[0]:
+            raise IndexError("solution token outside the embedding table")
+        h = torch.stack([ops.embedding_rows(emb, tok[g].contiguous()) for g in range(G)])          # (G, L, 128)
+        for module in self.resblocks:
+            h = ops.axpby(h, module(h, key_padding_mask))                                        # x + module(x): encoder.py:35
+        return h

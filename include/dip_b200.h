@@ -353,6 +353,19 @@ int dip_engine_guided_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_c
 int dip_engine_ddpm_step(dip_engine* e, float* x, int B, const dip_ddpm_coeffs* co, int eps_param,
                          const float* noise, void* workspace, size_t workspace_bytes, dip_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* partial-solution hand-off (sample_partialsol.py:172-199) and a residual add                  */
+/* ------------------------------------------------------------------------------------------ */
+/* For each of B decoded samples (xbits (B,n) bytes 0/1, as written by dip_round_feasibility) choose k = int(n * coverage) variables
+ * uniformly without replacement -- the `random.sample(range(n), num_vars)` of sample_partialsol.py:190, drawn here from a Philox
+ * counter keyed by (seed, instance_id, sample_base + b) so the choice does not depend on how samples are sharded -- and write the
+ * selection mask and the selected values as packed bits, (B, ceil(n/8)) bytes each, numpy.packbits order.  first_sample_values != 0
+ * keeps the reference's quirk (values are read from sample 0 for every sample, sample_partialsol.py:179). */
+int dip_partial_select(uint8_t* mask_bits, uint8_t* value_bits, const uint8_t* xbits, int B, int n, int k,
+                       uint64_t seed, uint64_t instance_id, int sample_base, int first_sample_values, dip_stream_t stream);
+/* out = a*x + b*y (y nullable), n % 4 == 0: the extra residual of SolutionEncoder.forward, `x = x + module(x)` (model/encoder.py:35). */
+int dip_axpby(float* out, const float* x, const float* y, float a, float b, int64_t n, dip_stream_t stream);
+
 /* Number of kernel launches the library has issued since load (bench.py reports the delta). */
 uint64_t dip_launch_count(void);
 

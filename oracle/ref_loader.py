@@ -13,11 +13,48 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DIP_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_model.zip")
+_unpacked = None
+
+
+def _unpack():
+    """oracle/_ref/reference_model.zip (byte copies staged by oracle/stage_ref.py) -> a temporary directory, once per process."""
+    global _unpacked
+    if _unpacked is None:
+        import atexit
+        import shutil
+        import tempfile
+        import zipfile
+        _unpacked = tempfile.mkdtemp(prefix="dip_ref_")
+        atexit.register(shutil.rmtree, _unpacked, ignore_errors=True)
+        with zipfile.ZipFile(_STAGED) as z:
+            z.extractall(_unpacked)
+    return _unpacked
+
+
+def _root():
+    """/root/reference in the build container; on the GPU box the staged archive (oracle/_ref/)."""
+    env = os.environ.get("DIP_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference"]:
+        if env == "staged":           # force the staged archive (what the GPU box sees)
+            break
+        if os.path.isfile(os.path.join(cand, "model", "diffusion.py")):
+            return cand
+    if os.path.isfile(_STAGED):
+        return _unpack()
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _root()
 
 
 def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "diffusion.py"))
+
+
+def kind():
+    """'reference' when the unmodified files are importable (in place or staged), else None."""
+    return "reference" if available() else None
 
 
 _cache = None

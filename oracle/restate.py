@@ -461,3 +461,33 @@ def get_features(W, cons, edge_index, edge_attr, var, int_indices, padding_len):
         kpm = torch.zeros((1, padding_len), dtype=torch.bool)
         kpm[:, n:] = True
     return mip, kpm
+
+
+# ----------------------------------------------------------------------------------------------
+# section 8f rows: Neural-Diving head and the solution encoder
+# ----------------------------------------------------------------------------------------------
+def neural_diving_fwd(W, cons, edge_index, edge_attr, var):
+    """NeuralDiving.forward, gnn_model/gnn_model.py:81-86: shared GNN (prefix ``gnn_model.``) -> output_module
+    (Linear, ReLU, Linear(128,1), Sigmoid) and SelectiveNet (Linear, ReLU, Linear(128,1,bias=False), Sigmoid; basic_module.py:109-125)."""
+    with torch.no_grad():
+        v = encoder_fwd(W, cons, edge_index, edge_attr, var, prefix="gnn_model.")
+        g = lambda k: W[k].to(v.dtype)
+        h = torch.relu(v @ g("output_module.0.weight").t() + g("output_module.0.bias"))
+        out = torch.sigmoid(h @ g("output_module.2.weight").t() + g("output_module.2.bias")).squeeze(-1)
+        hs = torch.relu(v @ g("select_net.select_module.0.weight").t() + g("select_net.select_module.0.bias"))
+        sel = torch.sigmoid(hs @ g("select_net.select_module.2.weight").t()).squeeze(-1)
+    return out, sel
+
+
+def solution_encoder_fwd(W, sol, padding_len, prefix="sol_encoder."):
+    """CMSP.encode_solution (model/cmsp.py:65-69): pad the 0/1 solution with token 2 (model/utils.py:105), then
+    SolutionEncoder.forward (model/encoder.py:32-36): embedding, and per block ``x = x + block(x)`` (the block is itself residual)."""
+    with torch.no_grad():
+        n = sol.shape[0]
+        tok = F.pad(sol, (0, padding_len - n), value=2).unsqueeze(0)
+        kpm = torch.zeros((1, padding_len), dtype=torch.bool)
+        kpm[:, n:] = True
+        x = W[prefix + "embedding.weight"][tok]
+        for i in range(n_blocks(W, prefix + "resblocks.")):
+            x = x + block_fwd(x, W, prefix + "resblocks.%d." % i, kpm)
+    return x, kpm

@@ -93,24 +93,29 @@ merged = dd.all_gather_records(rec)
 out = [dd.decode_record(merged[i], n) for i in range(3)]
 assert [o["n_samples"] for o in out] == [4, 4, 4], out
 assert [o["n_feasible"] for o in out] == [4, 4, 4], out
-print("RANK", rank, [o["best_obj"] for o in out], [int(o["best_x"].sum()) for o in out])
+# one file per rank: two processes printing to one pipe can interleave within a line
+with open(os.path.join(%(out)r, "rank%%d.txt" %% rank), "w") as f:
+    f.write(repr(([int(o["best_obj"]) for o in out], [int(o["best_x"].sum()) for o in out])))
 dist.destroy_process_group()
 '''
 
 
 def test_all_gather_world2_gloo(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % {"root": ROOT})
+    script.write_text(WORKER % {"root": ROOT, "out": str(tmp_path)})
     import socket
-    with socket.socket() as sk:
-        sk.bind(("127.0.0.1", 0))
-        port = str(sk.getsockname()[1])
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", port, str(script)], capture_output=True, text=True, env=env, timeout=300)
+    for attempt in range(3):        # the probed port can be taken by someone else before torchrun binds it: retry on another one
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = str(sk.getsockname()[1])
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", port, str(script)], capture_output=True, text=True, env=env, timeout=300)
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout + r.stderr
-    lines = sorted(l for l in r.stdout.splitlines() if l.startswith("RANK"))
-    assert len(lines) == 2 and lines[0].split(" ", 2)[2] == lines[1].split(" ", 2)[2]       # both ranks hold the same merged result
+    res = [(tmp_path / ("rank%d.txt" % k)).read_text() for k in range(2)]
+    assert res[0] == res[1] and res[0].startswith("([")                                     # both ranks hold the same merged result
 
 
 def test_synth_generators():

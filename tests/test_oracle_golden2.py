@@ -1,0 +1,118 @@
+"""CPU: the restatement (oracle/restate.py) against the round-2 fixtures of the UNMODIFIED reference (oracle/gen_golden2.py):
+the shipped Independent-Set checkpoints at config shapes, the CF-length step, and the P4 distribution fixtures' internal
+consistency (feasibility flags of the stored assignments re-derived by the integer check)."""
+import os
+
+import numpy as np
+import torch
+
+from dip_b200 import synth
+from oracle import restate
+from helpers import GOLDEN, golden, tw, rel_l2
+
+TOL = 2e-5
+
+
+def _ckpt(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=True)
+
+
+def _A(inst):
+    return (torch.from_numpy(inst.rows), torch.from_numpy(inst.cols), torch.from_numpy(inst.a_val), inst.M)
+
+
+def test_shipped_checkpoints_have_the_reference_layout():
+    sd_t, sd_d = _ckpt("ddpm_independent_set.pth"), _ckpt("decoder_independent_set.pth")
+    assert restate.n_blocks(sd_t, "predict_model.resblocks.") == 2 and restate.n_blocks(sd_d, "resblocks.") == 2
+    assert "select_net.0.weight" in sd_d and tuple(sd_d["select_net.2.weight"].shape) == (1, 128)
+    # mirror classes load them with every key matched
+    from model.diffusion import DDPMTrainer
+    from model.decoder import MipConditionalDecorder
+    tr = DDPMTrainer(128, 1, 2, "cpu")
+    dec = MipConditionalDecorder(128, 1, 2, use_select_net=True)
+    assert not any(tr.load_state_dict(sd_t, strict=True)) and not any(dec.load_state_dict(sd_d, strict=True))
+
+
+def test_is_checkpoint_step_restatement_vs_reference():
+    g = golden("is_ckpt")
+    n = L = 1500
+    inst = synth.independent_set(n_nodes=n, n_edges=4860, n_single=n, seed=7)
+    mip = synth.mip_features(L, n, seed=17)
+    kpm = np.zeros(L, dtype=bool)
+    B, S, stride = 2, int(g["S"]), int(g["stride"])
+    x = torch.from_numpy(synth.initial_noise(7, range(B), L))
+    Wd, Wdec = _ckpt("ddpm_independent_set.pth"), _ckpt("decoder_independent_set.pth")
+    mipB, kpmB = torch.from_numpy(mip)[None].repeat(B, 1, 1), torch.from_numpy(kpm)[None].repeat(B, 1)
+    tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], S)
+    index = 50
+    out = restate.guided_ddim_step(Wd, Wdec, x, S - 1 - index, restate.ddim_step_coeffs(tab, index), mipB, kpmB, _A(inst),
+                                   torch.from_numpy(inst.b), torch.from_numpy(inst.c), float(g["gs"]), float(g["lam"]))
+    assert rel_l2(out["p"], g["tf50_p"]) < TOL
+    assert rel_l2(out["x0"][:, ::stride], g["tf50_x0"]) < TOL
+    assert rel_l2(out["grad"][:, ::stride], g["tf50_grad"]) < 1e-4
+    assert rel_l2(out["x_prev"][:, ::stride], g["tf50_xprev"]) < 1e-4
+    sols, sel = restate.decoder_fwd(Wdec, mipB, torch.from_numpy(g["xprev_full"]), kpmB)
+    assert rel_l2(sols.view(B, n), g["dec_xprev_p"]) < TOL and rel_l2(sel.view(B, n), g["dec_xprev_sel"]) < TOL
+    fd = restate.final_decode(Wdec, mipB, torch.from_numpy(g["xprev_full"]), kpmB, _A(inst), torch.from_numpy(inst.b))
+    assert np.array_equal(fd["x_int"].numpy(), g["final_x"]) and np.allclose(fd["penalty"].numpy(), g["final_penalty"], rtol=1e-6, atol=1e-6)
+
+
+def test_cf_length_step_restatement_vs_reference():
+    g = golden("cf_step")
+    inst = synth.facility_location(100, 50, seed=9)
+    n = L = inst.n
+    mip = synth.mip_features(L, n, seed=19)
+    kpm = np.zeros(L, dtype=bool)
+    S, stride = int(g["S"]), int(g["stride"])
+    x = torch.from_numpy(synth.initial_noise(9, range(1), L))
+    Wd, Wdec = tw(synth.denoiser_weights(1, seed=1)), tw(synth.decoder_weights(2, seed=2))
+    tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], S)
+    out = restate.guided_ddim_step(Wd, Wdec, x, S - 1, restate.ddim_step_coeffs(tab, 0), torch.from_numpy(mip)[None], torch.from_numpy(kpm)[None],
+                                   _A(inst), torch.from_numpy(inst.b), torch.from_numpy(inst.c), float(g["gs"]), float(g["lam"]))
+    assert rel_l2(out["p"], g["tf0_p"]) < TOL
+    assert rel_l2(out["x0"][:, ::stride], g["tf0_x0"]) < TOL
+    assert rel_l2(out["grad"][:, ::stride], g["tf0_grad"]) < 1e-4
+    assert rel_l2(out["x_prev"][:, ::stride], g["tf0_xprev"]) < 1e-4
+
+
+def test_p4_fixtures_are_consistent_and_restatement_follows_the_first_steps():
+    from oracle.gen_golden2 import p4_cases, P4
+    for kind in ("sc", "is"):
+        g = golden("p4_%s_small" % kind)
+        cfg = P4[kind]
+        cases = p4_cases(kind)
+        for i, (inst, mip, kpm, L) in enumerate(cases):
+            bits = np.unpackbits(g["i%d_bits" % i], axis=1)[:, :inst.n]
+            feas, obj, _ = restate.feasibility_int(bits, inst.rows, inst.cols, inst.a_int, inst.M, inst.b_int, inst.c_int)
+            # the reference's fp32 test `penalty > 1e-5` (sample.py:174) and the exact integer check agree on every stored sample
+            assert np.array_equal(feas, g["i%d_feasible" % i]) and np.array_equal(obj, g["i%d_obj_int" % i])
+        # restatement, first 5 free-running steps of 4 samples of instance 0 (P2)
+        inst, mip, kpm, L = cases[0]
+        if kind == "sc":
+            Wd, Wdec = tw(synth.denoiser_weights(1, seed=1)), tw(synth.decoder_weights(2, seed=2))
+        else:
+            Wd, Wdec = _ckpt("ddpm_independent_set.pth"), _ckpt("decoder_independent_set.pth")
+        B = 4
+        x = torch.from_numpy(synth.initial_noise(cfg["inst_base"], range(B), L))
+        mipB, kpmB = torch.from_numpy(mip)[None].repeat(B, 1, 1), torch.from_numpy(kpm)[None].repeat(B, 1)
+        tab = restate.ddim_tables(restate.trainer_buffers()["alphas_cumprod"], cfg["S"])
+        for k in range(5):
+            x = restate.guided_ddim_step(Wd, Wdec, x, cfg["S"] - 1 - k, restate.ddim_step_coeffs(tab, k), mipB, kpmB, _A(inst),
+                                         torch.from_numpy(inst.b), torch.from_numpy(inst.c), cfg["gs"], cfg["lam"])["x_prev"]
+            if k + 1 in (1, 2, 5):
+                assert rel_l2(x[:, :inst.n], g["i0_x_after%d" % (k + 1)][:B, :inst.n]) < 1e-4 * (k + 1), (kind, k)
+
+
+def test_neural_diving_and_solution_encoder_restatement_vs_reference():
+    from helpers import small_graph
+    g = golden("ndiving_small")
+    gr = small_graph(seed=6, M=18, N=30, E=90)
+    W = tw(synth.neural_diving_weights(seed=8))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    out, sel = restate.neural_diving_fwd(W, T(gr.cons), T(gr.edge_index), T(gr.edge_attr), T(gr.var))
+    assert rel_l2(out, g["output"]) < TOL and rel_l2(sel, g["select"]) < TOL
+    g = golden("solenc_small")
+    W = tw(synth.solution_encoder_weights(n_layers=2, seed=12))
+    xf, kpm = restate.solution_encoder_fwd(W, T(g["sol"]), 24)
+    n = int((~kpm).sum())
+    assert np.array_equal(kpm.numpy(), g["kpm"]) and rel_l2(xf[:, :n], g["x_features"][:, :n]) < TOL

@@ -62,7 +62,7 @@ __device__ __forceinline__ const float* row_ptr(const dip_rows& s, int64_t r) {
     if (s.split == 0) return s.batch + r * D;
     int64_t b = r / s.T;
     int t = (int)(r - b * s.T);
-    return t < s.split ? s.shared + (int64_t)t * D : s.batch + (b * (s.T - s.split) + (t - s.split)) * D;
+    return t < s.split ? s.shared + b * s.shared_stride + (int64_t)t * D : s.batch + (b * (s.T - s.split) + (t - s.split)) * D;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128) time_token_kernel(float* __restrict__ out
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_fwd_kernel(float* __restrict__ p_full, const float* __restrict__ y, int B, int T,
                                                        int L, const float* __restrict__ w, const float* __restrict__ beta,
-                                                       const uint8_t* __restrict__ kpm) {
+                                                       const uint8_t* __restrict__ kpm, int64_t kpm_stride) {
     int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(float* __restrict__ p_ful
         float4 yv = reinterpret_cast<const float4*>(y + (b * T + (T - L) + t) * D)[lane];
         float s = yv.x * wv.x + yv.y * wv.y + yv.z * wv.z + yv.w * wv.w;
         s = warp_sum(s);
-        if (lane == 0) p_full[r] = kpm[t] ? 0.0f : sigmoidf_(s + bb);
+        if (lane == 0) p_full[r] = kpm[b * kpm_stride + t] ? 0.0f : sigmoidf_(s + bb);
     }
 }
 
@@ -398,10 +398,10 @@ int dip_time_token(float* out, int B, int T, float t, const float* W1, const flo
 }
 
 int dip_decoder_head_fwd(float* p_full, const float* y, int B, int T, int L, const float* w, const float* beta,
-                         const uint8_t* kpm, dip_stream_t stream) {
-    DIP_REQUIRE(p_full && y && w && beta && kpm && B > 0 && L > 0 && T >= L, "dip_decoder_head_fwd: bad argument");
+                         const uint8_t* kpm, int64_t kpm_stride, dip_stream_t stream) {
+    DIP_REQUIRE(p_full && y && w && beta && kpm && B > 0 && L > 0 && T >= L && kpm_stride >= 0, "dip_decoder_head_fwd: bad argument");
     DIP_PROF(DIP_PROF_HEAD, stream);
-    head_fwd_kernel<<<ew_grid((int64_t)B * L * 32), 256, 0, as_stream(stream)>>>(p_full, y, B, T, L, w, beta, kpm);
+    head_fwd_kernel<<<ew_grid((int64_t)B * L * 32), 256, 0, as_stream(stream)>>>(p_full, y, B, T, L, w, beta, kpm, kpm_stride);
     DIP_LAUNCHED();
     return 0;
 }

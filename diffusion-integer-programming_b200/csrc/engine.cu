@@ -58,11 +58,26 @@ struct dip_engine {
     float *proj_w = nullptr, *proj_b = nullptr;
     Pool den_pool, dec_pool, inst_pool;
     bool has_den = false, has_dec = false, has_inst = false, mproj_valid = false;
-    dip_instance inst;
+    dip_instance inst;                      // instance 0 (the only one unless dip_engine_set_instances was given several)
     float* mproj = nullptr;
     uint8_t *mask_den = nullptr, *mask_dec = nullptr;
     int inst_cap_L = 0;
     int mode = DIP_PRECISION_TC_SPLIT;
+    // decoder layer 0, tensor-core mode: the q|k|v planes of the L mip tokens are constants of the wave (they depend on the instance and
+    // the decoder weights only); they are written by the first decode into a given workspace and kept -- later steps normalise and
+    // project the x tokens only.  Valid for (workspace, B) below; reset by anything that changes the instance, the map or the weights.
+    const void* dec0_ws = nullptr;
+    int dec0_B = 0;
+    // ---- waves that mix instances (dip_engine_set_instances + dip_engine_set_wave_map) ----
+    std::vector<dip_instance> insts;        // host copies of the resident instances
+    dip_instance* table = nullptr;          // device copy (guidance / rounding kernels index it by inst_of)
+    int table_cap = 0;
+    int n_max = 0, M_max = 0;
+    Pool wave_pool;                         // per-sample gathers for the current map
+    int wave_B = 0, wave_cap = 0;           // wave_B > 0: a map is set
+    int32_t* inst_of = nullptr;             // device (wave_B)
+    float *wave_mip = nullptr, *wave_mproj = nullptr;      // (B, L, 128) each
+    uint8_t *wave_kpm = nullptr, *wave_mask_den = nullptr, *wave_mask_dec = nullptr;     // (B, L), (B, L+1), (B, 2L)
 };
 
 namespace dip {
@@ -202,7 +217,7 @@ static dip_gemm_args gemm(const float* A, int lda, float* C, int ldc, int64_t M,
 
 static dip_rows plain_rows(const float* p, int T) {
     dip_rows r;
-    r.shared = nullptr; r.batch = p; r.T = T; r.split = 0;
+    r.shared = nullptr; r.batch = p; r.T = T; r.split = 0; r.shared_stride = 0;
     return r;
 }
 
@@ -240,23 +255,25 @@ static void window(dip_gemm_args& g, int B, int T, int w) {
 // out-projection and the MLP; keys and values still cover the whole sequence.
 static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, void* ln_hi, void* ln_lo, float* qkv,
                      void* qkv_hi, void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
-                     int B, int T, int win, dip_stream_t st) {
+                     int64_t mask_stride, int B, int T, int win, int in_begin, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     DIP_REQUIRE(R < (1ll << 31), "wave too large: B*T = %lld rows", (long long)R);
-    if (!tc) win = 0;
+    if (!tc) { win = 0; in_begin = 0; }
     // q|k|v = LN1(x) . W_in^T + b_in   (tensor-core mode: only the bf16 planes are written)
     dip_gemm_args g = gemm(nullptr, D, tc ? nullptr : qkv, 3 * D, R, 3 * D, D, w.in_b, DIP_ACT_NONE);
     if (tc) {
         // LayerNorm once into bf16 planes, then a TMA-fed GEMM: the three column blocks share the normalised rows
+        // in_begin > 0: the q|k|v planes of the tokens t < in_begin are already in place (constants of the wave, see dip_engine::dec0_ws)
         g.split_hi = qkv_hi; g.split_lo = qkv_lo;
-        DIP_TRY(dip_layernorm_split(ln_hi, ln_lo, mean1, rstd1, xin, w.ln1_w, w.ln1_b, R, st));
+        if (in_begin > 0) { g.M = B * (T - in_begin); g.rows_in = T - in_begin; g.rows_out = T; g.row_off = in_begin; }
+        DIP_TRY(dip_layernorm_split(ln_hi, ln_lo, mean1, rstd1, xin, w.ln1_w, w.ln1_b, R, in_begin, st));
         DIP_TRY(dip_gemm_tc_planes(&g, ln_hi, ln_lo, w.in_w.hi, w.in_w.lo, st));
     } else {
         DIP_TRY(linear(mode, g, w.in_w, &xin, w.ln1_w, w.ln1_b, mean1, rstd1, h, st));
     }
-    if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, 0, B, T, win, st));
-    else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, 0, B, T, st));
+    if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, mask_stride, B, T, win, st));
+    else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, mask_stride, B, T, st));
     // x_mid = x + attn . W_out^T + b_out
     g = gemm(ao, D, xmid, D, R, D, D, w.out_b, DIP_ACT_NONE);
     g.res = xin;
@@ -283,7 +300,7 @@ static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float
 // Tokens outside these windows are skipped by every kernel that does not need them: the row-wise chain (MLP, LN2,
 // out-projection) runs on t >= do_begin, the attention backward streams queries t >= do_begin only and produces
 // dK, dV for t >= t_min and dQ for t >= max(t_min, do_begin), the in-projection backward runs on t >= t_min.
-static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int B, int T, float* dt1,
+static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int64_t mask_stride, int B, int T, float* dt1,
                      float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, float* dxin, int t_min, int do_begin,
                      dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
@@ -313,10 +330,10 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
             DIP_CUDA(cudaMemset2DAsync(dqkv, 3 * D * sizeof(float), 0, D * sizeof(float), (size_t)R, cs));
             DIP_CUDA(cudaMemset2DAsync(dxm, (size_t)T * D * sizeof(float), 0, (size_t)do_begin * D * sizeof(float), (size_t)B, cs));
         }
-        DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, 0, delta, B, T,
+        DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, mask_stride, delta, B, T,
                                 do_begin, q_begin, t_min, st));
     } else {
-        DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, 0, delta, B, T, st));
+        DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, mask_stride, delta, B, T, st));
     }
     // dH1 = dQKV . W_in
     g = gemm(dqkv, 3 * D, dt1, D, R, D, 3 * D, nullptr, DIP_ACT_NONE);
@@ -327,9 +344,48 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
     return 0;
 }
 
+// ---- how the kernels see the instance(s) of the current wave: one shared block (stride 0) or per-sample gathers ----------------
+struct WaveView {
+    const float* mip; int64_t mip_stride;           // shared source of the decoder rows / residual
+    const float* mproj; int64_t mproj_stride;       // hoisted mip half of mlp_xt.linear_1
+    const uint8_t *kpm; int64_t kpm_stride;
+    const uint8_t *mask_den; int64_t mask_den_stride;
+    const uint8_t *mask_dec; int64_t mask_dec_stride;
+    const dip_instance* table; const int32_t* inst_of;
+};
+
+static WaveView view(const dip_engine* e) {
+    WaveView v;
+    const int64_t L = e->inst.L;
+    if (e->wave_B > 0) {
+        v.mip = e->wave_mip; v.mip_stride = L * D;
+        v.mproj = e->wave_mproj; v.mproj_stride = L * D;
+        v.kpm = e->wave_kpm; v.kpm_stride = L;
+        v.mask_den = e->wave_mask_den; v.mask_den_stride = L + 1;
+        v.mask_dec = e->wave_mask_dec; v.mask_dec_stride = 2 * L;
+        v.table = e->table; v.inst_of = e->inst_of;
+    } else {
+        v.mip = e->inst.mip; v.mip_stride = 0;
+        v.mproj = e->mproj; v.mproj_stride = 0;
+        v.kpm = e->inst.kpm; v.kpm_stride = 0;
+        v.mask_den = e->mask_den; v.mask_den_stride = 0;
+        v.mask_dec = e->mask_dec; v.mask_dec_stride = 0;
+        v.table = nullptr; v.inst_of = nullptr;
+    }
+    return v;
+}
+
+static dip_rows mip_rows(const WaveView& v, const float* x, int T2, int L) {
+    dip_rows r;
+    r.shared = v.mip; r.batch = x; r.T = T2; r.split = L; r.shared_stride = v.mip_stride;
+    return r;
+}
+
 static int check_ready(const dip_engine* e, bool need_den, bool need_dec, int B, size_t ws_bytes, void* ws) {
     DIP_REQUIRE(e, "null engine");
     DIP_REQUIRE(e->has_inst, "dip_engine_set_instance has not been called");
+    DIP_REQUIRE(e->wave_B == 0 || e->wave_B == B, "the wave map was set for %d samples, this call has %d", e->wave_B, B);
+    DIP_REQUIRE(e->insts.size() <= 1 || e->wave_B > 0, "several instances are resident: dip_engine_set_wave_map first");
     DIP_REQUIRE(!need_den || e->has_den, "dip_engine_set_denoiser has not been called");
     DIP_REQUIRE(!need_dec || e->has_dec, "dip_engine_set_decoder has not been called");
     DIP_REQUIRE(B > 0, "empty wave");
@@ -344,16 +400,18 @@ static int check_ready(const dip_engine* e, bool need_den, bool need_dec, int B,
 static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, float t, dip_stream_t st) {
     const int L = e->inst.L, T1 = L + 1;
     const int64_t R1 = (int64_t)B * T1;
+    const WaveView v = view(e);
     if (!e->mproj_valid) {
-        // mip . W1[:, :128]^T + b1 -- constant over samples and steps, hoisted out of the loop
-        dip_gemm_args g = gemm(e->inst.mip, D, e->mproj, D, L, D, D, e->b1, DIP_ACT_NONE);
+        // mip . W1[:, :128]^T + b1 -- constant over samples and steps, hoisted out of the loop (per sample of the map when instances mix)
+        const int64_t rows = e->wave_B > 0 ? (int64_t)e->wave_B * L : L;
+        dip_gemm_args g = gemm(v.mip, D, const_cast<float*>(v.mproj), D, rows, D, D, e->b1, DIP_ACT_NONE);
         g.W = e->w1m;
         DIP_TRY(dip_gemm_nt(&g, st));
         e->mproj_valid = true;
     }
     DIP_TRY(dip_time_token(w.tmp, B, T1, t, e->w1, e->b1, st));
     dip_gemm_args g = gemm(x, D, w.tmp, D, (int64_t)B * L, D, D, nullptr, DIP_ACT_QUICKGELU);
-    g.rows_in = L; g.rows_out = T1; g.row_off = 1; g.addmat = e->mproj;
+    g.rows_in = L; g.rows_out = T1; g.row_off = 1; g.addmat = v.mproj; g.addmat_stride = v.mproj_stride;
     DIP_TRY(linear(e->mode, g, e->w1x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // NO activation after linear_2: the reference's OrderedDict names both QuickGELUs "geru", so the
     // second entry replaces the first and mlp_xt is linear_1 -> QuickGELU -> linear_2 (diffusion.py:145-150)
@@ -361,22 +419,24 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     DIP_TRY(linear(e->mode, g, e->w2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     for (int l = 0; l < e->n_den; ++l)
         DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.ln_hi, w.ln_lo, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
-                          nullptr, nullptr, nullptr, nullptr, e->mask_den, B, T1, 0, st));
+                          nullptr, nullptr, nullptr, nullptr, v.mask_den, v.mask_den_stride, B, T1, 0, 0, st));
     return 0;
 }
 
 // decoder forward with saved activations; final hidden state in ws.ls[n_dec-1].xout, p in ws.p_full
 static int decode(dip_engine* e, const Workspace& w, const float* x, int B, dip_stream_t st) {
     const int L = e->inst.L, T2 = 2 * L;
+    const WaveView v = view(e);
     for (int l = 0; l < e->n_dec; ++l) {
-        dip_rows xin;
-        if (l == 0) { xin.shared = e->inst.mip; xin.batch = x; xin.T = T2; xin.split = L; }
-        else xin = plain_rows(w.ls[l - 1].xout, T2);
+        const dip_rows xin = l == 0 ? mip_rows(v, x, T2, L) : plain_rows(w.ls[l - 1].xout, T2);
         const LayerSave& s = w.ls[l];
+        // layer 0: the mip tokens' planes are in place after the first decode into this workspace
+        const bool hoisted = l == 0 && e->mode == DIP_PRECISION_TC_SPLIT && e->dec0_ws == (const void*)s.qkv_hi && e->dec0_B == B;
         DIP_TRY(block_fwd(e->mode, e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, w.ln_hi, w.ln_lo, s.qkv, s.qkv_hi, s.qkv_lo, s.ao, s.lse, s.mean1, s.rstd1, s.mean2,
-                          s.rstd2, s.u, e->mask_dec, B, T2, l == e->n_dec - 1 ? L : 0, st));
+                          s.rstd2, s.u, v.mask_dec, v.mask_dec_stride, B, T2, l == e->n_dec - 1 ? L : 0, hoisted ? L : 0, st));
+        if (l == 0 && e->mode == DIP_PRECISION_TC_SPLIT) { e->dec0_ws = s.qkv_hi; e->dec0_B = B; }
     }
-    DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, e->inst.kpm, st));
+    DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, v.kpm, v.kpm_stride, st));
     return 0;
 }
 
@@ -386,18 +446,20 @@ static int guidance_grad(dip_engine* e, const Workspace& w, const float* x, int 
     const int L = e->inst.L, T2 = 2 * L;
     DIP_TRY(decode(e, w, x, B, st));
     const dip_instance& in = e->inst;
-    DIP_TRY(dip_guidance(w.dz, w.viol, w.obj, nullptr, nullptr, w.p_full, in.pos_of_col, in.csr_rowptr, in.csr_col, in.csr_val, in.csc_colptr,
-                         in.csc_row, in.csc_val, in.b, in.c, lam, B, L, in.n, in.M, in.nnz, st));
+    const WaveView v = view(e);
+    if (v.table)
+        DIP_TRY(dip_guidance_multi(w.dz, w.viol, w.obj, w.p_full, v.table, v.inst_of, lam, B, L, e->n_max, e->M_max, st));
+    else
+        DIP_TRY(dip_guidance(w.dz, w.viol, w.obj, nullptr, nullptr, w.p_full, in.pos_of_col, in.csr_rowptr, in.csr_col, in.csr_val, in.csc_colptr,
+                             in.csc_row, in.csc_val, in.b, in.c, lam, B, L, in.n, in.M, in.nnz, st));
     float* dcur = w.dxa;
     float* dnext = w.dxb;
     DIP_TRY(dip_decoder_head_bwd(dcur, w.dz, B, T2, L, e->proj_w, st));
     for (int l = e->n_dec - 1; l >= 0; --l) {
-        dip_rows xin;
-        if (l == 0) { xin.shared = in.mip; xin.batch = x; xin.T = T2; xin.split = L; }
-        else xin = plain_rows(w.ls[l - 1].xout, T2);
+        const dip_rows xin = l == 0 ? mip_rows(v, x, T2, L) : plain_rows(w.ls[l - 1].xout, T2);
         // the gradient w.r.t. the (constant) mip tokens of layer 0 is never used, and only the last L tokens of the last
         // layer's output carry a gradient (head_bwd writes zeros elsewhere; in tensor-core mode those rows are not even read)
-        DIP_TRY(block_bwd(e->mode, e->dec[l], dcur, xin, w.ls[l], e->mask_dec, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.do_hi, w.do_lo, w.dqkv, w.delta,
+        DIP_TRY(block_bwd(e->mode, e->dec[l], dcur, xin, w.ls[l], v.mask_dec, v.mask_dec_stride, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.do_hi, w.do_lo, w.dqkv, w.delta,
                           dnext, l == 0 ? L : 0, l == e->n_dec - 1 ? L : 0, st));
         float* t = dcur; dcur = dnext; dnext = t;
     }
@@ -411,9 +473,14 @@ static int final_decode(dip_engine* e, const Workspace& w, const float* x, int B
     const dip_instance& in = e->inst;
     DIP_TRY(decode(e, w, x, B, st));
     if (p_full) DIP_CUDA(cudaMemcpyAsync(p_full, w.p_full, (size_t)B * in.L * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(st)));
-    if (xbits || penalty || viol_int || obj_int)
-        DIP_TRY(dip_round_feasibility(xbits, penalty, viol_int, obj_int, w.p_full, in.pos_of_col, in.csr_rowptr, in.csr_col, in.csr_val,
-                                      in.csr_val_int, in.b, in.b_int, in.c_int, B, in.L, in.n, in.M, in.nnz, st));
+    if (xbits || penalty || viol_int || obj_int) {
+        const WaveView v = view(e);
+        if (v.table)
+            DIP_TRY(dip_round_feasibility_multi(xbits, penalty, viol_int, obj_int, w.p_full, v.table, v.inst_of, B, in.L, e->n_max, st));
+        else
+            DIP_TRY(dip_round_feasibility(xbits, penalty, viol_int, obj_int, w.p_full, in.pos_of_col, in.csr_rowptr, in.csr_col, in.csr_val,
+                                          in.csr_val_int, in.b, in.b_int, in.c_int, B, in.L, in.n, in.M, in.nnz, st));
+    }
     return 0;
 }
 
@@ -436,6 +503,8 @@ void dip_engine_destroy(dip_engine* e) {
     e->den_pool.release();
     e->dec_pool.release();
     e->inst_pool.release();
+    e->wave_pool.release();
+    if (e->table) cudaFree(e->table);
     delete e;
 }
 
@@ -475,6 +544,7 @@ int dip_engine_set_decoder(dip_engine* e, const dip_block_weights* blocks, int n
     DIP_CUDA(cudaStreamSynchronize(st));
     e->dec_pool.release();
     e->has_dec = false;
+    e->dec0_ws = nullptr;
     DIP_TRY(e->dec_pool.alloc(&e->proj_w, D));
     DIP_TRY(e->dec_pool.alloc(&e->proj_b, 1));
     DIP_CUDA(cudaMemcpyAsync(e->proj_w, proj_w, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -485,13 +555,22 @@ int dip_engine_set_decoder(dip_engine* e, const dip_block_weights* blocks, int n
     return 0;
 }
 
-int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_t stream) {
-    DIP_REQUIRE(e && inst, "dip_engine_set_instance: null argument");
+static int validate_instance(const dip_instance* inst) {
     DIP_REQUIRE(inst->L > 0 && inst->n > 0 && inst->n <= inst->L && inst->M > 0 && inst->nnz >= 0, "dip_engine_set_instance: bad sizes L=%d n=%d M=%d",
                 inst->L, inst->n, inst->M);
     DIP_REQUIRE(inst->mip && inst->kpm && inst->pos_of_col && inst->csr_rowptr && inst->csr_col && inst->csr_val && inst->csc_colptr &&
                     inst->csc_row && inst->csc_val && inst->b && inst->c,
                 "dip_engine_set_instance: null array");
+    return 0;
+}
+
+int dip_engine_set_instances(dip_engine* e, const dip_instance* insts, int n_inst, dip_stream_t stream) {
+    DIP_REQUIRE(e && insts && n_inst >= 1, "dip_engine_set_instances: null / empty argument");
+    for (int i = 0; i < n_inst; ++i) {
+        DIP_TRY(validate_instance(&insts[i]));
+        DIP_REQUIRE(insts[i].L == insts[0].L, "dip_engine_set_instances: instance %d has padding_len %d, instance 0 has %d", i, insts[i].L, insts[0].L);
+    }
+    const dip_instance* inst = &insts[0];
     cudaStream_t st = as_stream(stream);
     if (inst->L > e->inst_cap_L) {
         DIP_CUDA(cudaStreamSynchronize(st));
@@ -505,20 +584,104 @@ int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_
         e->inst_cap_L = inst->L;
     }
     e->inst = *inst;
+    e->insts.assign(insts, insts + n_inst);
+    e->n_max = 0; e->M_max = 0;
+    for (int i = 0; i < n_inst; ++i) {
+        e->n_max = insts[i].n > e->n_max ? insts[i].n : e->n_max;
+        e->M_max = insts[i].M > e->M_max ? insts[i].M : e->M_max;
+    }
     // key masks: denoiser [False | kpm] (diffusion.py:162-165), decoder [kpm | kpm] (decoder.py:42)
     DIP_CUDA(cudaMemsetAsync(e->mask_den, 0, 1, st));
     DIP_CUDA(cudaMemcpyAsync(e->mask_den + 1, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
     DIP_CUDA(cudaMemcpyAsync(e->mask_dec, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
     DIP_CUDA(cudaMemcpyAsync(e->mask_dec + inst->L, inst->kpm, inst->L, cudaMemcpyDeviceToDevice, st));
+    if (n_inst > 1) {
+        if (n_inst > e->table_cap) {
+            DIP_CUDA(cudaStreamSynchronize(st));
+            if (e->table) cudaFree(e->table);
+            e->table = nullptr;
+            DIP_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->table), (size_t)n_inst * sizeof(dip_instance)));
+            e->table_cap = n_inst;
+        }
+        // pageable host source: the copy is staged before the call returns, the vector may change afterwards
+        DIP_CUDA(cudaMemcpyAsync(e->table, e->insts.data(), (size_t)n_inst * sizeof(dip_instance), cudaMemcpyHostToDevice, st));
+    }
+    e->wave_B = 0;                          // a map refers to the previous set of instances
     e->has_inst = true;
     e->mproj_valid = false;
+    e->dec0_ws = nullptr;
     return 0;
 }
+
+int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_t stream) {
+    DIP_REQUIRE(e && inst, "dip_engine_set_instance: null argument");
+    return dip_engine_set_instances(e, inst, 1, stream);
+}
+
+int dip_engine_set_wave_map(dip_engine* e, const int32_t* inst_of, int B, dip_stream_t stream) {
+    DIP_REQUIRE(e && e->has_inst, "dip_engine_set_wave_map: set the instances first");
+    cudaStream_t st = as_stream(stream);
+    if (inst_of == nullptr || B <= 0) {
+        DIP_REQUIRE(e->insts.size() == 1, "dip_engine_set_wave_map: several instances are resident, a map is required");
+        e->wave_B = 0;
+        e->mproj_valid = false;
+        e->dec0_ws = nullptr;
+        return 0;
+    }
+    const int n_inst = (int)e->insts.size();
+    for (int s = 0; s < B; ++s) DIP_REQUIRE(inst_of[s] >= 0 && inst_of[s] < n_inst, "dip_engine_set_wave_map: sample %d -> instance %d of %d", s, inst_of[s], n_inst);
+    const int64_t L = e->inst.L;
+    if (B > e->wave_cap) {
+        DIP_CUDA(cudaStreamSynchronize(st));
+        e->wave_pool.release();
+        float *io = nullptr, *k = nullptr, *m1 = nullptr, *m2 = nullptr;
+        DIP_TRY(e->wave_pool.alloc(&e->wave_mip, (size_t)B * L * D));
+        DIP_TRY(e->wave_pool.alloc(&e->wave_mproj, (size_t)B * L * D));
+        DIP_TRY(e->wave_pool.alloc(&io, (size_t)B));
+        DIP_TRY(e->wave_pool.alloc(&k, (size_t)B * L / 4 + 64));
+        DIP_TRY(e->wave_pool.alloc(&m1, (size_t)B * (L + 1) / 4 + 64));
+        DIP_TRY(e->wave_pool.alloc(&m2, (size_t)B * 2 * L / 4 + 64));
+        e->inst_of = reinterpret_cast<int32_t*>(io);
+        e->wave_kpm = reinterpret_cast<uint8_t*>(k);
+        e->wave_mask_den = reinterpret_cast<uint8_t*>(m1);
+        e->wave_mask_dec = reinterpret_cast<uint8_t*>(m2);
+        e->wave_cap = B;
+    }
+    if (e->table == nullptr) {              // one resident instance used through a map: still needs the device table
+        DIP_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->table), sizeof(dip_instance)));
+        e->table_cap = 1;
+    }
+    if (n_inst == 1) DIP_CUDA(cudaMemcpyAsync(e->table, e->insts.data(), sizeof(dip_instance), cudaMemcpyHostToDevice, st));
+    DIP_CUDA(cudaMemcpyAsync(e->inst_of, inst_of, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // per-sample gathers, once per map (the step loop then reads plain strided tensors; the reference builds the same with .repeat())
+    DIP_CUDA(cudaMemsetAsync(e->wave_mask_den, 0, (size_t)B * (L + 1), st));
+    for (int s = 0; s < B; ++s) {
+        const dip_instance& in = e->insts[inst_of[s]];
+        DIP_CUDA(cudaMemcpyAsync(e->wave_mip + (size_t)s * L * D, in.mip, (size_t)L * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        DIP_CUDA(cudaMemcpyAsync(e->wave_kpm + (size_t)s * L, in.kpm, (size_t)L, cudaMemcpyDeviceToDevice, st));
+        DIP_CUDA(cudaMemcpyAsync(e->wave_mask_den + (size_t)s * (L + 1) + 1, in.kpm, (size_t)L, cudaMemcpyDeviceToDevice, st));
+        DIP_CUDA(cudaMemcpyAsync(e->wave_mask_dec + (size_t)s * 2 * L, in.kpm, (size_t)L, cudaMemcpyDeviceToDevice, st));
+        DIP_CUDA(cudaMemcpyAsync(e->wave_mask_dec + (size_t)s * 2 * L + L, in.kpm, (size_t)L, cudaMemcpyDeviceToDevice, st));
+    }
+    e->wave_B = B;
+    e->mproj_valid = false;
+    e->dec0_ws = nullptr;
+    return 0;
+}
+
+int dip_engine_n_max(const dip_engine* e) { return e && e->has_inst ? e->n_max : 0; }
 
 int dip_engine_set_precision(dip_engine* e, int mode) {
     DIP_REQUIRE(e, "null engine");
     DIP_REQUIRE(mode == DIP_PRECISION_FP32_SIMT || mode == DIP_PRECISION_TC_SPLIT, "unknown precision mode %d", mode);
     e->mode = mode;
+    e->dec0_ws = nullptr;
+    return 0;
+}
+
+int dip_engine_reset_cache(dip_engine* e) {
+    DIP_REQUIRE(e, "null engine");
+    e->dec0_ws = nullptr;
     return 0;
 }
 

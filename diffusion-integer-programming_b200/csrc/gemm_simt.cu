@@ -76,12 +76,13 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmParams P) {
     for (int i = 0; i < 8; ++i) {
         int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (r >= g.M) continue;
-        int64_t out_row = r;
+        int64_t out_row = r, b_in = 0;
         int t_in = 0;
         if (g.rows_in > 0) {
             int64_t b = r / g.rows_in;
             t_in = (int)(r - b * g.rows_in);
             out_row = b * g.rows_out + g.row_off + t_in;
+            b_in = b;
         }
         float rbs = g.row_bias_scale ? g.row_bias_scale[r] : 1.0f;
         const float* resp = g.res.batch ? row_ptr(g.res, out_row) : nullptr;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmParams P) {
                 v[0] += bb.x * rbs; v[1] += bb.y * rbs; v[2] += bb.z * rbs; v[3] += bb.w * rbs;
             }
             if (g.addmat) {
-                float4 am = *reinterpret_cast<const float4*>(g.addmat + (int64_t)t_in * g.N + c);
+                float4 am = *reinterpret_cast<const float4*>(g.addmat + b_in * g.addmat_stride + (int64_t)t_in * g.N + c);
                 v[0] += am.x; v[1] += am.y; v[2] += am.z; v[3] += am.w;
             }
             if (resp) {

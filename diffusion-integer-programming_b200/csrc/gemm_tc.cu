@@ -83,6 +83,7 @@ struct Params {
     //    row windows: GEMM row r reads input row (r / in_rows) * in_T + in_off + r % in_rows (identity: in_rows = BIG, in_T = in_off = 0)
     const float *a_shared, *a_batch;
     FastDiv a_T; uint32_t a_split;
+    int64_t a_sstride, res_sstride, add_bstride;    // per-sample strides of the shared A / residual blocks and of addmat (0: one block for the wave)
     FastDiv in_rows; uint32_t in_T, in_off;
     int lda;
     const float *ln_gamma, *ln_beta;
@@ -98,10 +99,10 @@ struct Params {
     int ldc;
 };
 
-__device__ __forceinline__ const float* src_row(const float* shared, const float* batch, const FastDiv& T, uint32_t split, uint32_t r) {
+__device__ __forceinline__ const float* src_row(const float* shared, const float* batch, const FastDiv& T, uint32_t split, int64_t sstride, uint32_t r) {
     const uint32_t b = T.div(r), t = r - b * T.d;
     const bool sh = t < split;
-    const float* base = sh ? shared : batch;
+    const float* base = sh ? shared + (int64_t)b * sstride : batch;
     const uint32_t idx = sh ? t : b * (T.d - split) + (t - split);
     return base + (size_t)idx * D;
 }
@@ -143,8 +144,8 @@ __device__ __forceinline__ EpiIn epi_load(const Params& P, uint32_t row, int c, 
     if (ROWOPS) {
         float rbs = 1.0f;
         if (P.row_bias_scale) rbs = P.row_bias_scale[row];
-        const float4 am = *reinterpret_cast<const float4*>(P.addmat + (size_t)t_in * P.add_ld + c);
-        const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, e.out_row * P.res_mul) + c);
+        const float4 am = *reinterpret_cast<const float4*>(P.addmat + (int64_t)b * P.add_bstride + (size_t)t_in * P.add_ld + c);
+        const float4 rv = *reinterpret_cast<const float4*>(src_row(P.res_shared, P.res_batch, P.res_T, P.res_split, P.res_sstride, e.out_row * P.res_mul) + c);
         e.aux = *reinterpret_cast<const float4*>(P.aux + (size_t)e.out_row * P.aux_ld + c);
         e.ext = make_float4(bv.x * rbs + am.x + rv.x, bv.y * rbs + am.y + rv.y, bv.z * rbs + am.z + rv.z, bv.w * rbs + am.w + rv.w);
     } else {
@@ -309,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constan
                         const uint32_t gr = min((uint32_t)tile * 128u + warp * RPW + bt + u, (uint32_t)P.M - 1u);
                         const uint32_t gb = P.in_rows.div(gr);
                         const uint32_t row = gb * P.in_T + P.in_off + (gr - gb * P.in_rows.d);
-                        const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
+                        const float* src = KCH == 1 ? src_row(P.a_shared, P.a_batch, P.a_T, P.a_split, P.a_sstride, row) : P.a_batch + (size_t)row * P.lda + kc * 128;
                         v[u] = DBG(2) ? make_float4(1.f, 2.f, 3.f, 4.f) : reinterpret_cast<const float4*>(src)[lane];
                     }
                     if (bt == 0) {
@@ -484,6 +485,7 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     if (rows_a) {
         P.a_shared = a_rows->shared ? a_rows->shared : a_rows->batch; P.a_batch = a_rows->batch;
         P.a_split = (uint32_t)a_rows->split;
+        P.a_sstride = a_rows->shared ? a_rows->shared_stride : 0;
         P.a_T = tcgemm::make_fastdiv(a_rows->split > 0 ? (uint32_t)a_rows->T : tcgemm::BIG);
     } else {
         P.a_shared = g.A; P.a_batch = g.A; P.a_T = tcgemm::make_fastdiv(tcgemm::BIG); P.a_split = 0;
@@ -496,10 +498,11 @@ int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, c
     else { P.rows_in = tcgemm::make_fastdiv(tcgemm::BIG); P.rows_out = 0; P.row_off = 0; }
     P.bias = g.bias ? g.bias : zeros;
     P.row_bias_scale = g.row_bias_scale;
-    P.addmat = g.addmat ? g.addmat : zeros; P.add_ld = g.addmat ? (uint32_t)g.N : 0u;
+    P.addmat = g.addmat ? g.addmat : zeros; P.add_ld = g.addmat ? (uint32_t)g.N : 0u; P.add_bstride = g.addmat ? g.addmat_stride : 0;
     if (g.res.batch) {
         P.res_shared = g.res.shared ? g.res.shared : g.res.batch; P.res_batch = g.res.batch;
         P.res_split = (uint32_t)g.res.split; P.res_T = tcgemm::make_fastdiv(g.res.split > 0 ? (uint32_t)g.res.T : tcgemm::BIG); P.res_mul = 1;
+        P.res_sstride = g.res.shared ? g.res.shared_stride : 0;
     } else {
         P.res_shared = zeros; P.res_batch = zeros; P.res_split = 0; P.res_T = tcgemm::make_fastdiv(tcgemm::BIG); P.res_mul = 0;
     }
@@ -537,8 +540,9 @@ int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* 
     DIP_REQUIRE(g.M > 0 && g.K == 128 && g.N % 128 == 0, "dip_gemm_tc_planes: needs K == 128 and N %% 128 == 0 (K=%d N=%d)", g.K, g.N);
     DIP_REQUIRE(g.C || g.split_hi || g.preact, "dip_gemm_tc_planes: no output");
     DIP_REQUIRE(g.ldc % 4 == 0 && (g.split_hi == nullptr) == (g.split_lo == nullptr), "dip_gemm_tc_planes: bad ldc / split planes");
-    DIP_REQUIRE(!g.row_bias_scale && !g.addmat && !g.res.batch && !g.aux && g.act == DIP_ACT_NONE && g.rows_in == 0 && g.in_T == 0,
-                "dip_gemm_tc_planes: bias-only epilogue (no row operands, activation, row maps)");
+    DIP_REQUIRE(!g.row_bias_scale && !g.addmat && !g.res.batch && !g.aux && g.act == DIP_ACT_NONE && g.in_T == 0,
+                "dip_gemm_tc_planes: bias-only epilogue (no row operands, activation, input windows)");
+    DIP_REQUIRE(g.rows_in == 0 || (g.rows_out >= g.rows_in + g.row_off), "dip_gemm_tc_planes: bad row remap");
     float* zeros = nullptr;
     DIP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&zeros), tcgemm::g_zeros));
     DIP_REQUIRE(g.bias || g.N <= 4 * 128, "dip_gemm_tc_planes: N too large for the zero block");
@@ -547,6 +551,7 @@ int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* 
     P.M = g.M; P.N = g.N; P.n_tiles = cdiv(g.M, 128); P.act = DIP_ACT_NONE;
     P.a_T = tcgemm::make_fastdiv(tcgemm::BIG); P.in_rows = tcgemm::make_fastdiv(tcgemm::BIG);
     P.rows_in = tcgemm::make_fastdiv(tcgemm::BIG); P.res_T = tcgemm::make_fastdiv(tcgemm::BIG);
+    if (g.rows_in > 0) { P.rows_in = tcgemm::make_fastdiv((uint32_t)g.rows_in); P.rows_out = (uint32_t)g.rows_out; P.row_off = (uint32_t)g.row_off; }
     P.bias = g.bias ? g.bias : zeros;
     P.addmat = zeros; P.res_shared = zeros; P.res_batch = zeros; P.aux = zeros;
     P.C = g.C; P.preact = g.preact; P.split_hi = g.split_hi; P.split_lo = g.split_lo; P.ldc = g.ldc;

@@ -41,20 +41,34 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 // barrier, and the per-CTA partial sums of viol / obj are added by rank 0 in rank order (fixed order -> deterministic).
 constexpr int GCL = 4, GTHREADS = 512;
 
+// lane-group width for a segment pass: the power of two (<= 32) next to the average segment length
+__host__ __device__ inline int pick_group(int64_t nnz, int segments) {
+    int64_t avg = segments > 0 ? (nnz + segments - 1) / segments : 1;
+    int g = 1;
+    while (g < 32 && g < avg) g <<= 1;
+    return g;
+}
+
+// The instance of sample b: `single` (one instance for the whole wave, passed by value) or table[inst_of[b]] (a wave mixing instances).
 __global__ void __launch_bounds__(GTHREADS) guidance_kernel(
     float* __restrict__ dz, float* __restrict__ viol, float* __restrict__ obj, float* __restrict__ r_out, float* __restrict__ dp_out,
-    const float* __restrict__ p_full, const int32_t* __restrict__ pos_of_col, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ col, const float* __restrict__ val, const int32_t* __restrict__ colptr,
-    const int32_t* __restrict__ crow, const float* __restrict__ cval, const float* __restrict__ bvec, const float* __restrict__ cvec,
-    float one_minus_lam, float lam, int L, int n, int M, int Gr, int Gc) {
+    const float* __restrict__ p_full, const __grid_constant__ dip_instance single, const dip_instance* __restrict__ table,
+    const int32_t* __restrict__ inst_of, float one_minus_lam, float lam, int L, int n_max) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) float sm[];
     float* p_s = sm;
-    float* h_s = sm + n;
+    float* h_s = sm + n_max;
     __shared__ float red[GTHREADS / 32];
     __shared__ float part[2];                       // this CTA's share of viol and obj
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / GCL, tid = threadIdx.x;
+    const dip_instance& in = table ? table[inst_of[b]] : single;
+    const int n = in.n, M = in.M;
+    const int32_t* __restrict__ pos_of_col = in.pos_of_col;
+    const int32_t* __restrict__ rowptr = in.csr_rowptr; const int32_t* __restrict__ col = in.csr_col; const float* __restrict__ val = in.csr_val;
+    const int32_t* __restrict__ colptr = in.csc_colptr; const int32_t* __restrict__ crow = in.csc_row; const float* __restrict__ cval = in.csc_val;
+    const float* __restrict__ bvec = in.b; const float* __restrict__ cvec = in.c;
+    const int Gr = pick_group(in.nnz, M), Gc = pick_group(in.nnz, n);
     const int Mq = (M + GCL - 1) / GCL, nq = (n + GCL - 1) / GCL, Lq = (L + GCL - 1) / GCL;
     const int i_lo = rank * Mq, i_hi = min(M, i_lo + Mq);
     const int j_lo = rank * nq, j_hi = min(n, j_lo + nq);
@@ -128,20 +142,29 @@ __global__ void __launch_bounds__(GTHREADS) guidance_kernel(
 
 __global__ void __launch_bounds__(256) round_feas_kernel(
     uint8_t* __restrict__ xbits, float* __restrict__ penalty, long long* __restrict__ viol_int, long long* __restrict__ obj_int,
-    const float* __restrict__ p_full, const int32_t* __restrict__ pos_of_col, const int32_t* __restrict__ rowptr,
-    const int32_t* __restrict__ col, const float* __restrict__ val, const int32_t* __restrict__ val_int,
-    const float* __restrict__ bvec, const int32_t* __restrict__ b_int, const int32_t* __restrict__ c_int, int L, int n, int M, int Gr) {
+    const float* __restrict__ p_full, const __grid_constant__ dip_instance single, const dip_instance* __restrict__ table,
+    const int32_t* __restrict__ inst_of, int L, int n_max) {
     extern __shared__ __align__(16) float sm[];
     float* x_s = sm;
     __shared__ float redf[8];
     __shared__ long long redi[8];
     const int b = blockIdx.x, tid = threadIdx.x;
+    const dip_instance& in = table ? table[inst_of[b]] : single;
+    const int n = in.n, M = in.M;
+    const int32_t* __restrict__ pos_of_col = in.pos_of_col;
+    const int32_t* __restrict__ rowptr = in.csr_rowptr; const int32_t* __restrict__ col = in.csr_col; const float* __restrict__ val = in.csr_val;
+    const int32_t* __restrict__ val_int = in.csr_val_int; const float* __restrict__ bvec = in.b;
+    const int32_t* __restrict__ b_int = in.b_int; const int32_t* __restrict__ c_int = in.c_int;
+    const int Gr = pick_group(in.nnz, M);
     long long o_part = 0;
-    for (int j = tid; j < n; j += blockDim.x) {
-        float x = rintf(p_full[(int64_t)b * L + pos_of_col[j]]);   // torch.round: half to even (sample.py:164)
-        x_s[j] = x;
-        if (xbits) xbits[(int64_t)b * n + j] = (uint8_t)x;
-        if (c_int) o_part += (long long)c_int[j] * (long long)x;
+    for (int j = tid; j < n_max; j += blockDim.x) {
+        float x = 0.f;
+        if (j < n) {
+            x = rintf(p_full[(int64_t)b * L + pos_of_col[j]]);     // torch.round: half to even (sample.py:164)
+            x_s[j] = x;
+            if (c_int) o_part += (long long)c_int[j] * (long long)x;
+        }
+        if (xbits) xbits[(int64_t)b * n_max + j] = (uint8_t)x;       // rows are n_max wide, zero-padded past the instance's n
     }
     __syncthreads();
     float pen = 0.f;
@@ -177,11 +200,47 @@ __global__ void __launch_bounds__(256) round_feas_kernel(
     }
 }
 
-static int pick_group(int64_t nnz, int segments) {
-    int64_t avg = segments > 0 ? (nnz + segments - 1) / segments : 1;
-    int g = 1;
-    while (g < 32 && g < avg) g <<= 1;
-    return g;
+static int launch_guidance(float* dz, float* viol, float* obj, float* r_out, float* dp_out, const float* p_full, const dip_instance& single,
+                           const dip_instance* table, const int32_t* inst_of, float lam, int B, int L, int n_max, int M_max, dip_stream_t stream) {
+    size_t smem = (size_t)(n_max + M_max) * sizeof(float);
+    DIP_REQUIRE(smem <= 200 * 1024, "dip_guidance: n + M = %d exceeds the shared-memory staging limit", n_max + M_max);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DIP_CUDA(cudaFuncSetAttribute(guidance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    // (1 - lam) is formed in double like the reference's Python float and rounded once (diffusion.py:633)
+    float oml = (float)(1.0 - (double)lam);
+    DIP_PROF(DIP_PROF_GUIDANCE, stream);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)B * GCL);
+    cfg.blockDim = dim3(GTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DIP_CUDA(cudaLaunchKernelEx(&cfg, guidance_kernel, dz, viol, obj, r_out, dp_out, p_full, single, table, inst_of, oml, lam, L, n_max));
+    DIP_LAUNCHED();
+    return 0;
+}
+
+static int launch_round_feas(uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int, const float* p_full, const dip_instance& single,
+                             const dip_instance* table, const int32_t* inst_of, int B, int L, int n_max, dip_stream_t stream) {
+    size_t smem = (size_t)n_max * sizeof(float);
+    DIP_REQUIRE(smem <= 200 * 1024, "dip_round_feasibility: n too large");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DIP_CUDA(cudaFuncSetAttribute(round_feas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    DIP_PROF(DIP_PROF_GUIDANCE, stream);
+    round_feas_kernel<<<B, 256, smem, as_stream(stream)>>>(xbits, penalty, reinterpret_cast<long long*>(viol_int),
+                                                           reinterpret_cast<long long*>(obj_int), p_full, single, table, inst_of, L, n_max);
+    DIP_LAUNCHED();
+    return 0;
 }
 
 }  // namespace dip
@@ -197,31 +256,21 @@ int dip_guidance(float* dz, float* viol, float* obj, float* r_out, float* dp_out
     DIP_REQUIRE(dz && p_full && pos_of_col && csr_rowptr && csr_col && csr_val && csc_colptr && csc_row && csc_val && b && c,
                 "dip_guidance: null argument");
     DIP_REQUIRE(B > 0 && L > 0 && n > 0 && n <= L && M > 0, "dip_guidance: bad sizes B=%d L=%d n=%d M=%d", B, L, n, M);
-    size_t smem = (size_t)(n + M) * sizeof(float);
-    DIP_REQUIRE(smem <= 200 * 1024, "dip_guidance: n + M = %d exceeds the shared-memory staging limit", n + M);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        DIP_CUDA(cudaFuncSetAttribute(guidance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
-    int Gr = pick_group(nnz, M), Gc = pick_group(nnz, n);
-    // (1 - lam) is formed in double like the reference's Python float and rounded once (diffusion.py:633)
-    float oml = (float)(1.0 - (double)lam);
-    DIP_PROF(DIP_PROF_GUIDANCE, stream);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)B * GCL);
-    cfg.blockDim = dim3(GTHREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = GCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    DIP_CUDA(cudaLaunchKernelEx(&cfg, guidance_kernel, dz, viol, obj, r_out, dp_out, p_full, pos_of_col, csr_rowptr, csr_col, csr_val, csc_colptr,
-                                csc_row, csc_val, b, c, oml, lam, L, n, M, Gr, Gc));
-    DIP_LAUNCHED();
-    return 0;
+    dip_instance in;
+    memset(&in, 0, sizeof(in));
+    in.L = L; in.n = n; in.M = M; in.nnz = nnz; in.pos_of_col = pos_of_col;
+    in.csr_rowptr = csr_rowptr; in.csr_col = csr_col; in.csr_val = csr_val;
+    in.csc_colptr = csc_colptr; in.csc_row = csc_row; in.csc_val = csc_val; in.b = b; in.c = c;
+    return launch_guidance(dz, viol, obj, r_out, dp_out, p_full, in, nullptr, nullptr, lam, B, L, n, M, stream);
+}
+
+int dip_guidance_multi(float* dz, float* viol, float* obj, const float* p_full, const dip_instance* table, const int32_t* inst_of, float lam,
+                       int B, int L, int n_max, int M_max, dip_stream_t stream) {
+    DIP_REQUIRE(dz && p_full && table && inst_of, "dip_guidance_multi: null argument");
+    DIP_REQUIRE(B > 0 && L > 0 && n_max > 0 && n_max <= L && M_max > 0, "dip_guidance_multi: bad sizes");
+    dip_instance none;
+    memset(&none, 0, sizeof(none));
+    return launch_guidance(dz, viol, obj, nullptr, nullptr, p_full, none, table, inst_of, lam, B, L, n_max, M_max, stream);
 }
 
 int dip_round_feasibility(uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int, const float* p_full,
@@ -231,19 +280,21 @@ int dip_round_feasibility(uint8_t* xbits, float* penalty, int64_t* viol_int, int
     DIP_REQUIRE(p_full && pos_of_col && csr_rowptr && csr_col && csr_val && b, "dip_round_feasibility: null argument");
     DIP_REQUIRE(B > 0 && L > 0 && n > 0 && n <= L && M > 0, "dip_round_feasibility: bad sizes");
     DIP_REQUIRE((csr_val_int == nullptr) == (b_int == nullptr), "dip_round_feasibility: csr_val_int and b_int go together");
-    size_t smem = (size_t)n * sizeof(float);
-    DIP_REQUIRE(smem <= 200 * 1024, "dip_round_feasibility: n too large");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        DIP_CUDA(cudaFuncSetAttribute(round_feas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
-    DIP_PROF(DIP_PROF_GUIDANCE, stream);
-    round_feas_kernel<<<B, 256, smem, as_stream(stream)>>>(xbits, penalty, reinterpret_cast<long long*>(viol_int),
-                                                           reinterpret_cast<long long*>(obj_int), p_full, pos_of_col, csr_rowptr, csr_col,
-                                                           csr_val, csr_val_int, b, b_int, c_int, L, n, M, pick_group(nnz, M));
-    DIP_LAUNCHED();
-    return 0;
+    dip_instance in;
+    memset(&in, 0, sizeof(in));
+    in.L = L; in.n = n; in.M = M; in.nnz = nnz; in.pos_of_col = pos_of_col;
+    in.csr_rowptr = csr_rowptr; in.csr_col = csr_col; in.csr_val = csr_val; in.b = b;
+    in.csr_val_int = csr_val_int; in.b_int = b_int; in.c_int = c_int;
+    return launch_round_feas(xbits, penalty, viol_int, obj_int, p_full, in, nullptr, nullptr, B, L, n, stream);
+}
+
+int dip_round_feasibility_multi(uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int, const float* p_full,
+                                const dip_instance* table, const int32_t* inst_of, int B, int L, int n_max, dip_stream_t stream) {
+    DIP_REQUIRE(p_full && table && inst_of, "dip_round_feasibility_multi: null argument");
+    DIP_REQUIRE(B > 0 && L > 0 && n_max > 0 && n_max <= L, "dip_round_feasibility_multi: bad sizes");
+    dip_instance none;
+    memset(&none, 0, sizeof(none));
+    return launch_round_feas(xbits, penalty, viol_int, obj_int, p_full, none, table, inst_of, B, L, n_max, stream);
 }
 
 int dip_coo_to_csr_csc_host(int64_t nnz, const int64_t* rows, const int64_t* cols, const float* vals, int M, int n,

@@ -62,12 +62,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(float* __restrict__ dx, con
 
 // y = LayerNorm(x) written as bf16 hi/lo planes (rows, 128): the A operand of dip_gemm_tc_planes
 __global__ void __launch_bounds__(256) ln_split_kernel(uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                       const dip_rows x, const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows) {
+                                                       const dip_rows x, const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows,
+                                                       int T, int t_begin) {
     int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float4 g = reinterpret_cast<const float4*>(gamma)[lane], b = reinterpret_cast<const float4*>(beta)[lane];
-    for (int64_t r = warp; r < rows; r += nwarps) {
+    const int w = T - t_begin;
+    // `rows` counts the live rows (t >= t_begin of every sample); the planes are compact over them, the statistics keep the
+    // input's row numbering b*T + t
+    for (int64_t i = warp; i < rows; i += nwarps) {
+        const int64_t r = t_begin > 0 ? (i / w) * T + t_begin + (i % w) : i;
         const float4 v = reinterpret_cast<const float4*>(row_ptr(x, r))[lane];
         const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);
         const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
@@ -78,8 +83,8 @@ __global__ void __launch_bounds__(256) ln_split_kernel(uint2* __restrict__ hi, u
         uint32_t h0, l0, h1, l1;
         tc::split2(y0, y1, h0, l0);
         tc::split2(y2, y3, h1, l1);
-        hi[r * 32 + lane] = make_uint2(h0, h1);
-        lo[r * 32 + lane] = make_uint2(l0, l1);
+        hi[i * 32 + lane] = make_uint2(h0, h1);
+        lo[i * 32 + lane] = make_uint2(l0, l1);
         if (mean_out && lane == 0) { mean_out[r] = mu; rstd_out[r] = rs; }
     }
 }
@@ -110,12 +115,15 @@ int dip_layernorm_fwd(float* y, float* mean, float* rstd, dip_rows x, const floa
 }
 
 int dip_layernorm_split(void* hi, void* lo, float* mean, float* rstd, dip_rows x, const float* gamma, const float* beta, int64_t rows,
-                        dip_stream_t stream) {
+                        int t_begin, dip_stream_t stream) {
     DIP_REQUIRE(hi && lo && x.batch && gamma && beta && rows > 0, "dip_layernorm_split: bad argument");
     DIP_REQUIRE((mean == nullptr) == (rstd == nullptr), "dip_layernorm_split: mean and rstd go together");
     DIP_REQUIRE(x.split == 0 || (x.shared && x.T > x.split), "dip_layernorm_split: bad row source");
+    DIP_REQUIRE(t_begin == 0 || (x.T > t_begin && t_begin > 0 && rows % x.T == 0), "dip_layernorm_split: t_begin needs whole samples of T rows");
     DIP_PROF(DIP_PROF_LN, stream);
-    ln_split_kernel<<<ln_grid(rows), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), mean, rstd, x, gamma, beta, rows);
+    const int64_t live = t_begin > 0 ? rows / x.T * (x.T - t_begin) : rows;
+    ln_split_kernel<<<ln_grid(live), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), mean, rstd, x, gamma, beta, live,
+                                                                  x.T > 0 ? x.T : 1, t_begin);
     DIP_LAUNCHED();
     return 0;
 }

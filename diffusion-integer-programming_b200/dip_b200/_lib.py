@@ -19,7 +19,7 @@ class DipError(RuntimeError):
 
 
 class Rows(C.Structure):
-    _fields_ = [("shared", vp), ("batch", vp), ("T", C.c_int), ("split", C.c_int)]
+    _fields_ = [("shared", vp), ("batch", vp), ("T", C.c_int), ("split", C.c_int), ("shared_stride", C.c_int64)]
 
 
 class GemmArgs(C.Structure):
@@ -39,6 +39,7 @@ class GemmArgs(C.Structure):
         ("split_hi", vp),
         ("split_lo", vp),
         ("in_T", C.c_int), ("in_off", C.c_int),
+        ("addmat_stride", C.c_int64),
     ]
 
 
@@ -87,11 +88,11 @@ PROTOTYPES = {
     "dip_split_bf16": (i32, [vp, vp, vp, i64, vp]),
     "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "dip_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
-    "dip_layernorm_split": (i32, [vp, vp, vp, vp, Rows, vp, vp, i64, vp]),
+    "dip_layernorm_split": (i32, [vp, vp, vp, vp, Rows, vp, vp, i64, i32, vp]),
     "dip_gemm_tc_planes": (i32, [C.POINTER(GemmArgs), vp, vp, vp, vp, vp]),
     "dip_gemm_tc": (i32, [C.POINTER(GemmArgs), vp, vp, C.POINTER(Rows), vp, vp, vp, vp, vp]),
     "dip_time_token": (i32, [vp, i32, i32, f32, vp, vp, vp]),
-    "dip_decoder_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "dip_decoder_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp]),
     "dip_decoder_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "dip_guidance": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i64, vp]),
     "dip_round_feasibility": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
@@ -106,8 +107,14 @@ PROTOTYPES = {
     "dip_engine_set_denoiser": (i32, [vp, vp, vp, vp, vp, C.POINTER(BlockWeights), i32, vp]),
     "dip_engine_set_decoder": (i32, [vp, C.POINTER(BlockWeights), i32, vp, vp, vp]),
     "dip_engine_set_instance": (i32, [vp, C.POINTER(Instance), vp]),
+    "dip_engine_set_instances": (i32, [vp, C.POINTER(Instance), i32, vp]),
+    "dip_engine_set_wave_map": (i32, [vp, vp, i32, vp]),
+    "dip_engine_n_max": (i32, [vp]),
+    "dip_guidance_multi": (i32, [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]),
+    "dip_round_feasibility_multi": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dip_engine_set_precision": (i32, [vp, i32]),
     "dip_engine_workspace_bytes": (sz, [vp, i32]),
+    "dip_engine_reset_cache": (i32, [vp]),
     "dip_engine_denoise": (i32, [vp, vp, vp, i32, f32, vp, sz, vp]),
     "dip_engine_decode": (i32, [vp, vp, vp, vp, i32, vp, sz, vp]),
     "dip_engine_guidance_grad": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, vp, sz, vp]),
@@ -140,7 +147,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dip_abi_version() != 1:
+    if lib.dip_abi_version() != 2:
         raise DipError("libdip_b200.so ABI version mismatch")
     _lib = lib
     return lib

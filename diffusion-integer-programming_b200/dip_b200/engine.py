@@ -211,6 +211,36 @@ class Engine:
         self.inst = prepared["info"]
         return self.inst
 
+    def use_instances(self, prepared_list, inst_of=None):
+        """Several prepared instances of one family resident at once + (optionally) the wave map: inst_of[s] = index into
+        `prepared_list` of the instance sample s of the following waves belongs to (sample_partialsol.py draws 15 samples per
+        instance: a wave then mixes several instances instead of leaving the GPU two thirds idle).  Per-sample outputs of width n
+        become n_max wide, zero padded."""
+        if len(prepared_list) == 0:
+            raise _lib.DipError("use_instances: empty list")
+        arr = (_lib.Instance * len(prepared_list))(*[p["struct"] for p in prepared_list])
+        with torch.cuda.device(self.device):
+            check(self.lib.dip_engine_set_instances(self.h, arr, len(prepared_list), _stream(self.device)))
+        self._current_key = None
+        self._keep["inst"] = list(prepared_list)
+        infos = [p["info"] for p in prepared_list]
+        self.inst = {"L": infos[0]["L"], "n": max(i["n"] for i in infos), "M": max(i["M"] for i in infos),
+                     "nnz": sum(i["nnz"] for i in infos), "has_int": all(i["has_int"] for i in infos), "n_inst": len(infos),
+                     "n_of": [i["n"] for i in infos]}
+        if inst_of is not None:
+            self.set_wave_map(inst_of)
+        return self.inst
+
+    def set_wave_map(self, inst_of):
+        """inst_of: sequence / array of instance indices, one per sample of the waves that follow (None clears the map)."""
+        with torch.cuda.device(self.device):
+            if inst_of is None:
+                check(self.lib.dip_engine_set_wave_map(self.h, None, 0, _stream(self.device)))
+                return
+            m = np.ascontiguousarray(np.asarray(inst_of, dtype=np.int32))
+            check(self.lib.dip_engine_set_wave_map(self.h, ptr(m), int(m.size), _stream(self.device)))
+            torch.cuda.current_stream().synchronize()           # the host array is read by an async copy
+
     def set_instance(self, mip, kpm, rows, cols, vals, M, b, c, a_int=None, b_int=None, c_int=None):
         """prepare_instance + use_instance."""
         return self.use_instance(self.prepare_instance(mip, kpm, rows, cols, vals, M, b, c, a_int=a_int, b_int=b_int, c_int=c_int))
@@ -238,6 +268,10 @@ class Engine:
         base = self._ws.data_ptr()
         off = (-base) % 256
         return base + off, self._ws.numel() - off
+
+    def reset_cache(self):
+        """Forget the wave constants kept in the workspace (needed only if something else wrote into the workspace tensor)."""
+        check(self.lib.dip_engine_reset_cache(self.h))
 
     def _x(self, x):
         if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):

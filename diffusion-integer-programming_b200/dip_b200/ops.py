@@ -221,10 +221,12 @@ def time_token(B, T, t, W1, b1, out=None):
 
 
 def decoder_head_fwd(y, B, T, L, w, beta, kpm):
+    """kpm: (L,) one mask for the wave, or (B, L) one per sample."""
     lib = _lib.load()
     p = torch.empty((B, L), dtype=torch.float32, device=y.device)
     km = kpm.to(torch.uint8).contiguous()
-    check(lib.dip_decoder_head_fwd(ptr(p), ptr(_f32(y)), B, T, L, ptr(w), ptr(beta), ptr(km), _stream()))
+    stride = L if km.dim() == 2 else 0
+    check(lib.dip_decoder_head_fwd(ptr(p), ptr(_f32(y)), B, T, L, ptr(w), ptr(beta), ptr(km), stride, _stream()))
     return p
 
 
@@ -309,18 +311,20 @@ def block_forward(x, w, key_mask=None):
     return gemm_nt(g, w["mlp.c_proj.weight"], w["mlp.c_proj.bias"], res=xm).view(B, T, D)
 
 
-def layernorm_split(x, gamma, beta, shared=None, T=0, split=0, rows=None, want_stats=False):
-    """LayerNorm(x) as bf16 (hi, lo) planes (rows, 128); x optionally two-source like layernorm_fwd."""
+def layernorm_split(x, gamma, beta, shared=None, T=0, split=0, rows=None, want_stats=False, t_begin=0):
+    """LayerNorm(x) as bf16 (hi, lo) planes (rows, 128); x optionally two-source like layernorm_fwd.  t_begin > 0: only the tokens
+    t >= t_begin of every sample (T rows each), planes compact over them."""
     lib = _lib.load()
     x = _f32(x)
     rows = x.numel() // D if rows is None else rows
     dev = x.device
-    hi = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
-    lo = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+    live = rows // T * (T - t_begin) if t_begin > 0 else rows
+    hi = torch.empty((live, D), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty((live, D), dtype=torch.bfloat16, device=dev)
     mean = torch.empty(rows, dtype=torch.float32, device=dev) if want_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=dev) if want_stats else None
     r = Rows(ptr(shared), ptr(x), int(T), int(split))
-    check(lib.dip_layernorm_split(ptr(hi), ptr(lo), ptr(mean), ptr(rstd), r, ptr(_f32(gamma)), ptr(_f32(beta)), rows, _stream()))
+    check(lib.dip_layernorm_split(ptr(hi), ptr(lo), ptr(mean), ptr(rstd), r, ptr(_f32(gamma)), ptr(_f32(beta)), rows, int(t_begin), _stream()))
     return hi, lo, mean, rstd
 
 

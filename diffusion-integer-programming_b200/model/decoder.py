@@ -119,9 +119,7 @@ class MipConditionalDecorder(torch.nn.Module):
         w = {k: v.detach().contiguous() for k, v in self.select_net.state_dict().items()}
         h = ops.gemm_nt(y.view(B * L, Dm), w["0.weight"], w["0.bias"], act="relu")
         kpm = key_padding_mask if key_padding_mask is not None else torch.zeros((B, L), dtype=torch.bool, device=y.device)
-        sel = torch.empty((B, L), dtype=torch.float32, device=y.device)
-        for i in range(B):              # head kernel takes one shared mask per call
-            sel[i:i + 1] = ops.decoder_head_fwd(h.view(B, L, Dm)[i:i + 1].contiguous(), 1, L, L, w["2.weight"].view(-1), w["2.bias"], kpm[i])
+        sel = ops.decoder_head_fwd(h.view(B, L, Dm), B, L, L, w["2.weight"].view(-1), w["2.bias"], kpm)       # one mask row per sample
         if valid is None:
             return p.reshape(-1), sel.reshape(-1)
         return torch.masked_select(p, valid), torch.masked_select(sel, valid)

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define DIP_D 128
-#define DIP_ABI_VERSION 1
+#define DIP_ABI_VERSION 2
 
 typedef void* dip_stream_t;
 
@@ -62,6 +62,9 @@ typedef struct {
     const float* batch;
     int T;
     int split;
+    /* elements between the shared blocks of consecutive samples: 0 = ONE block for the whole wave (one instance repeated, sample.py:151);
+     * split*128 = a (B, split, 128) tensor, i.e. every sample its own conditions -- a wave that mixes instances */
+    int64_t shared_stride;
 } dip_rows;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -132,6 +135,8 @@ typedef struct {
      * row_off = in_off a Linear is applied in place to the tokens in_off .. in_off+rows_in-1 of every sample only --
      * e.g. the last L tokens of the decoder's 2L, the only ones model/decoder.py:45 keeps. */
     int in_T, in_off;
+    /* elements between the addmat blocks of consecutive samples (rows_in > 0): 0 = one (rows_in, N) block for every sample */
+    int64_t addmat_stride;
 } dip_gemm_args;
 int dip_gemm_nt(const dip_gemm_args* args, dip_stream_t stream);
 
@@ -183,10 +188,13 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
 /* LayerNorm(x) (model/modules.py:280,288) written as the bf16 (hi, lo) planes of its result, (rows,128) each: the A operand of
  * dip_gemm_tc_planes.  The q|k|v in-projection uses this pair instead of the fused-LayerNorm dip_gemm_tc: its three 128-column
  * blocks run on different CTAs, which would each repeat the row loads, the LayerNorm and the split. */
+/* t_begin > 0: only the tokens t >= t_begin of every sample are normalised (rows = B*T, x.T = T); the planes are then COMPACT,
+ * (B*(T-t_begin), 128), while mean / rstd keep the input's row numbering b*T + t. */
 int dip_layernorm_split(void* hi, void* lo, float* mean, float* rstd, dip_rows x, const float* gamma, const float* beta,
-                        int64_t rows, dip_stream_t stream);
+                        int64_t rows, int t_begin, dip_stream_t stream);
 /* C = A . W^T + bias on tcgen05 with A given as bf16 (hi, lo) planes (M,128), fetched by TMA straight into the MMA layout.
- * K == 128, N % 128 == 0, bias-only epilogue; outputs as in dip_gemm_args (C / preact / split planes). */
+ * K == 128, N % 128 == 0, bias-only epilogue; outputs as in dip_gemm_args (C / preact / split planes), including the output row remap
+ * rows_in / rows_out / row_off (compact A rows of a token window written in place into full-length buffers). */
 int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                        dip_stream_t stream);
 
@@ -207,9 +215,10 @@ int dip_time_token(float* out, int B, int T, float t, const float* W1, const flo
 /* decoder head + K2 guidance                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 /* p_full[b,t] = sigmoid(y[b, T-L+t,:].w + beta), 0 at padded t (model/decoder.py:47-50).
- * y: (B, T, 128) -- the last L rows of each sample are used.  kpm: (L) bytes (shared by the wave). */
+ * y: (B, T, 128) -- the last L rows of each sample are used.  kpm: bytes, sample b's L flags start at kpm + b*kpm_stride
+ * (stride 0: one mask shared by the wave). */
 int dip_decoder_head_fwd(float* p_full, const float* y, int B, int T, int L, const float* w, const float* beta,
-                         const uint8_t* kpm, dip_stream_t stream);
+                         const uint8_t* kpm, int64_t kpm_stride, dip_stream_t stream);
 /* dy[b, t, :] = 0 for t < T-L, dz[b, t-(T-L)] * w for the last L rows. */
 int dip_decoder_head_bwd(float* dy, const float* dz, int B, int T, int L, const float* w, dip_stream_t stream);
 
@@ -295,6 +304,24 @@ typedef struct {
 } dip_instance;
 int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_t stream);
 
+/* Waves that mix instances (sample_partialsol.py:55 draws 15 samples per instance and sample.py:134 walks the instances one after the
+ * other; the reference has no such batching -- a wave of 15 leaves most of the GPU idle).  `insts`: n_inst instances of ONE family (same L;
+ * n, M, nnz may differ), pointers borrowed like dip_engine_set_instance.  `inst_of` (HOST array, B entries): the instance of every sample
+ * of the waves that follow; the engine gathers per-sample conditions / masks once per map, not per step.  Per-sample outputs that are
+ * (B, n) for one instance become (B, n_max), rows zero-padded.  set_instance / set_instances with n_inst == 1 clear the map. */
+int dip_engine_set_instances(dip_engine* e, const dip_instance* insts, int n_inst, dip_stream_t stream);
+int dip_engine_set_wave_map(dip_engine* e, const int32_t* inst_of, int B, dip_stream_t stream);
+/* largest n over the resident instances (row width of xbits) */
+int dip_engine_n_max(const dip_engine* e);
+
+/* K2 and the rounding / feasibility check for a wave that mixes instances: `table` is a DEVICE array of dip_instance (device pointers
+ * inside), `inst_of` a DEVICE array with the table index of every sample; p_full / dz are (B, L), xbits (B, n_max), r_out / dp_out
+ * unsupported (pass the single-instance entry points for those). */
+int dip_guidance_multi(float* dz, float* viol, float* obj, const float* p_full, const dip_instance* table, const int32_t* inst_of,
+                       float lam, int B, int L, int n_max, int M_max, dip_stream_t stream);
+int dip_round_feasibility_multi(uint8_t* xbits, float* penalty, int64_t* viol_int, int64_t* obj_int, const float* p_full,
+                                const dip_instance* table, const int32_t* inst_of, int B, int L, int n_max, dip_stream_t stream);
+
 /* Arithmetic of the attention kernels (the >95 % of the FLOPs):
  *   DIP_PRECISION_TC_SPLIT  (default) tcgen05 tensor cores, every fp32 operand carried as bf16 hi + lo planes,
  *                           products hi.hi + hi.lo + lo.hi accumulated in fp32 (one-step error ~1e-5, bar 1e-3);
@@ -303,8 +330,12 @@ int dip_engine_set_instance(dip_engine* e, const dip_instance* inst, dip_stream_
 #define DIP_PRECISION_TC_SPLIT 1
 int dip_engine_set_precision(dip_engine* e, int mode);
 
-/* Scratch the caller provides (torch-allocated) for a wave of B samples. */
+/* Scratch the caller provides (torch-allocated) for a wave of B samples.  Between the calls of one wave the engine keeps wave
+ * constants in it (the q|k|v planes of the instance tokens of decoder layer 0, which depend on neither the latent nor the step): a
+ * caller that lets anything else write into the workspace between two calls must call dip_engine_reset_cache before the next one
+ * (a different workspace address or wave size, and every set_instance / set_instances / set_wave_map / set_decoder, reset it anyway). */
 size_t dip_engine_workspace_bytes(const dip_engine* e, int B);
+int dip_engine_reset_cache(dip_engine* e);
 
 /* x-hat0 / eps = NoisePredictV2.apply_model(x, t, mip, kpm)  (model/diffusion.py:153-180).
  * out: (B, L, 128) contiguous. */

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported_with_matching_arity(lib):
         assert name in _lib.PROTOTYPES, name
         assert len(_lib.PROTOTYPES[name][1]) == nargs, (name, nargs, len(_lib.PROTOTYPES[name][1]))
     assert set(_lib.PROTOTYPES) == set(decl)
-    assert lib.dip_abi_version() == 1
+    assert lib.dip_abi_version() == 2
 
 
 def test_library_holds_sm100a_code_only(lib):

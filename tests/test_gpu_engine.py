@@ -347,3 +347,80 @@ def test_ragged_shapes_and_degenerate_rows(cuda, L, n, M, B):
     assert float(obj.abs().max()) == 0.0
     eng.guided_ddim_step(xg, coeffs(S, 0), gs, lam)
     assert rel_l2(xg[:, :n], ref["x_prev"][:, :n]) < 1e-3
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_waves_mixing_instances_equal_single_instance_waves(cuda, mode):
+    """dip_engine_set_instances + dip_engine_set_wave_map: a wave whose samples belong to three different instances (different n, M,
+    nnz, masks, conditions; same padding_len) must give every sample bit-for-bit what it gets in a wave of its own instance -- guided
+    steps, the one-call sampler, rounding, feasibility and integer objective (sample_partialsol.py:55: 15 samples per instance)."""
+    from dip_b200 import schedule
+    from dip_b200.engine import Engine
+    L, S = 40, 6
+    cases = [small_case(seed=50 + i, L=L, n=n, M=M, nnz=nnz, B=1, dup=0) for i, (n, M, nnz) in enumerate([(40, 9, 30), (33, 14, 50), (25, 5, 12)])]
+    eng = Engine()
+    eng.set_precision(mode)
+    eng.set_denoiser(tw(synth.denoiser_weights(1, seed=1), cuda)); eng.set_decoder(tw(synth.decoder_weights(2, seed=2), cuda))
+
+    def prep(cs):
+        ai = np.rint(cs.vals).astype(np.int32)
+        return eng.prepare_instance(torch.from_numpy(cs.mip).to(cuda), torch.from_numpy(cs.kpm).to(cuda), cs.rows, cs.cols, cs.vals, cs.M, cs.b, cs.c,
+                                    a_int=ai, b_int=np.floor(cs.b).astype(np.int32), c_int=np.rint(100 * cs.c).astype(np.int32))
+
+    preps = [prep(cs) for cs in cases]
+    inst_of = [0, 1, 2, 1, 0, 2, 2, 1]
+    B = len(inst_of)
+    x0 = torch.from_numpy(synth.initial_noise(77, range(B), L)).to(cuda)
+    steps = schedule.ddim_coeffs(100)[:S]
+    gs, lam = 2e4, 0.5
+    # mixed wave
+    info = eng.use_instances(preps, inst_of)
+    assert info["n"] == 40 and info["n_inst"] == 3
+    xm = x0.clone()
+    for k in range(2):
+        eng.guided_ddim_step(xm, steps[k], gs, lam)
+    mixed_step = xm.clone()
+    mixed = eng.sample_guided_ddim(x0.clone(), steps, gs, lam)
+    assert mixed["xbits"].shape == (B, 40)
+    with pytest.raises(_lib_err()):
+        eng.guided_ddim_step(x0[:3].clone(), steps[0], gs, lam)            # the map was set for 8 samples
+    # every instance alone
+    for i, (cs, pr) in enumerate(zip(cases, preps)):
+        idx = [s for s, k in enumerate(inst_of) if k == i]
+        eng.use_instance(pr)
+        xs = x0[idx].clone()
+        for k in range(2):
+            eng.guided_ddim_step(xs, steps[k], gs, lam)
+        assert torch.equal(xs, mixed_step[idx]), i
+        alone = eng.sample_guided_ddim(x0[idx].clone(), steps, gs, lam)
+        assert torch.equal(alone["x"], mixed["x"][idx]), i
+        assert torch.equal(alone["xbits"], mixed["xbits"][idx][:, :cs.n]) and int(mixed["xbits"][idx][:, cs.n:].sum()) == 0
+        for k in ("penalty", "viol_int", "obj_int"):
+            assert torch.equal(alone[k], mixed[k][idx]), (i, k)
+
+
+def _lib_err():
+    from dip_b200 import _lib
+    return _lib.DipError
+
+
+def test_layer0_instance_token_planes_are_hoisted_without_changing_results(cuda):
+    """Tensor-core mode keeps the q|k|v planes of the L instance tokens of decoder layer 0 in the workspace after the first decode of a
+    wave (they depend on the instance and the weights only) and projects just the x tokens afterwards: the second, hoisted, evaluation
+    must equal the first bit for bit, and so must one after an explicit cache reset."""
+    from dip_b200.engine import Engine
+    cs = small_case(seed=3, L=150, n=130, M=30, nnz=200, B=5, dup=0)
+    eng = make_engine(cuda, cs, precision="tc")
+    x = torch.from_numpy(cs.x).to(cuda)
+    g1 = eng.guidance_grad(x, 0.5)          # first evaluation: full layer-0 in-projection
+    g2 = eng.guidance_grad(x, 0.5)          # hoisted
+    eng.reset_cache()
+    g3 = eng.guidance_grad(x, 0.5)
+    for a, b, c in zip(g1, g2, g3):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    x2 = torch.from_numpy(small_case(seed=4, L=150, n=130, M=30, nnz=200, B=5, dup=0).x).to(cuda)
+    h1 = eng.guidance_grad(x2, 0.5)         # other latents through the hoisted path ...
+    eng.reset_cache()
+    h2 = eng.guidance_grad(x2, 0.5)         # ... and through the full one
+    for a, b in zip(h1, h2):
+        assert torch.equal(a, b)

@@ -249,3 +249,18 @@ def test_layernorm_split_and_planes_gemm(cuda, B, T, split, N):
     assert rel_l2(out["C"], ref) < 2e-5, rel_l2(out["C"], ref)
     assert rel_l2(out["hi"].float() + out["lo"].float(), out["C"]) < 1e-5
     assert torch.equal(out["C"], ops.gemm_tc_planes(hi, lo, W.to(cuda), bias.to(cuda))["C"])
+
+
+def test_layernorm_split_token_window(cuda):
+    """t_begin: only the tokens t >= t_begin of every sample are normalised; planes compact, statistics at the input's row numbers."""
+    from dip_b200 import ops
+    B, T, split, tb = 3, 90, 40, 40
+    shared, batch = rnd((split, D), 0, 2.0), rnd((B, T - split, D), 1, 2.0)
+    gamma, beta = 1 + 0.1 * rnd((D,), 2), 0.1 * rnd((D,), 3)
+    args = dict(shared=shared.to(cuda), T=T, split=split, rows=B * T, want_stats=True)
+    hi, lo, mean, rstd = ops.layernorm_split(batch.to(cuda), gamma.to(cuda), beta.to(cuda), **args)
+    hw, lw, mw, rw = ops.layernorm_split(batch.to(cuda), gamma.to(cuda), beta.to(cuda), t_begin=tb, **args)
+    assert hw.shape == (B * (T - tb), D)
+    full = lambda t: t.view(B, T, -1)[:, tb:].reshape(B * (T - tb), -1)
+    assert torch.equal(hw, full(hi)) and torch.equal(lw, full(lo))
+    assert torch.equal(mw.view(B, T)[:, tb:], mean.view(B, T)[:, tb:]) and torch.equal(rw.view(B, T)[:, tb:], rstd.view(B, T)[:, tb:])

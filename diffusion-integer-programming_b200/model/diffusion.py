@@ -224,9 +224,9 @@ class _SamplerBase(torch.nn.Module):
             out.append((key, prep))
         return out
 
-    @staticmethod
-    def _use(eng, keyed):
+    def _use(self, eng, keyed):
         key, prep = keyed
+        self.last_instance = prep            # the prepared device-side instance (CSR / CSC / masks) of the latest wave, for the caller's tail
         if getattr(eng, "_current_key", None) != key:
             eng.use_instance(prep)
             eng._current_key = key

@@ -393,7 +393,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
                       const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64, const uint4* __restrict__ do_hi,
                       const uint4* __restrict__ do_lo, float* __restrict__ dq, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
-                      const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin) {
+                      const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin, int k_hi, int accumulate) {
+    // k_hi: only the keys t < k_hi are streamed; accumulate != 0: the result is ADDED to dq (the keys >= k_hi were handled by the
+    // streaming kernel below, which ran first on the same stream)
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
@@ -403,7 +405,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, r0 = q_begin + blockIdx.x * 128;      // first query of this CTA
     const int row_base = b * T;
-    const int n_tiles = (T + QT - 1) / QT;
+    const int n_tiles = (k_hi + QT - 1) / QT;
     Tracer tracer(threadIdx.x == 0 ? 5 : (lane == 0 && warp == W_PRODUCER) ? 6 : (lane == 0 && warp == W_MMA) ? 7 : -1);
 
     if (threadIdx.x == 0) {
@@ -436,8 +438,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         for (int j = 0; j < n_tiles; ++j) {
             const int sk = j % 3, sv = j & 1;
             const int k0 = j * QT + lane, k1 = k0 + 32;
-            const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
-            const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
+            const bool m0 = (k0 >= k_hi) || (mrow && mrow[k0]);
+            const bool m1 = (k1 >= k_hi) || (mrow && mrow[k1]);
             const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
             if (lane == 0) {
                 TR(40, j);
@@ -618,13 +620,122 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             tmem_ld32(lane_addr + QTM_ACC + h * 64 + ch * 32, t);
             if (row_ok) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+                for (int i = 0; i < 32; i += 4) {
+                    float4 v = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+                    if (accumulate) {
+                        const float4 o = *reinterpret_cast<const float4*>(dst + ch * 32 + i);
+                        v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+                    }
+                    *reinterpret_cast<float4*>(dst + ch * 32 + i) = v;
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// backward, dQ from stored dS: streaming GEMM
+// =============================================================================================
+// The key-stationary kernel below forms every dS tile anyway (it needs it for dK); it also writes it to global memory as bf16 hi/lo
+// planes of dS^T (row = key, column = query).  This kernel then only has to contract them with K:  dQ[128 q x 128 d] += dS K over the
+// keys, 64 at a time -- no score recomputation (the query-stationary kernel above executes S, dP and dQ: three products for one).
+// Both operands come through TMA from a three-stage ring: the dS^T tile is consumed as an MN-major A operand (queries contiguous),
+// the K tile as an MN-major B operand; three bf16 passes (hi.hi, hi.lo, lo.hi) into one TMEM accumulator.  The kernel is bound by the
+// 64 KB per stage it has to pull in (half of it from HBM: dS is 4 bytes per (query, key) pair), not by the 12 MMAs per stage.
+// shared memory per stage: dS^T [plane][query half][64 keys][64 q] (32 KB) | K [d-half][hi,lo][64 keys][64 d] (32 KB)
+constexpr uint32_t SQ_STAGE = 65536, SQ_DS = 0, SQ_K = 32768, SQ_BAR = 3 * SQ_STAGE, SQ_SMEM = SQ_BAR + 256;
+constexpr uint32_t IDESC_SQ = instr_desc(128, 128, 1, 1);
+enum { S_FULL = 0, S_EMPTY = 3, S_DONE = 6 };
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_stream_tc_kernel(const __grid_constant__ CUtensorMap tm_ds_hi, const __grid_constant__ CUtensorMap tm_ds_lo,
+                             const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64, float* __restrict__ dq,
+                             int ld_d, int T, int q_begin, int k_lo, int ds_col0) {
+    // queries q_begin + 128 * blockIdx.x ..., keys k_lo .. T-1; column c of the dS^T buffer is query (q_begin - ds_col0) + c, its row r is key k_lo + r
+    extern __shared__ __align__(1024) uint8_t sm[];
+    require_aligned_smem(sm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SQ_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, r0 = q_begin + blockIdx.x * 128;
+    const int col0 = ds_col0 + blockIdx.x * 128;
+    const int n_tiles = (T - k_lo + QT - 1) / QT;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 3; ++s) { mbar_init(&bars[S_FULL + s], 1); mbar_init(&bars[S_EMPTY + s], 1); }
+        mbar_init(&bars[S_DONE], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == W_PRODUCER) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_ds_hi); tma_prefetch_desc(&tm_ds_lo); tma_prefetch_desc(&tm_qkv_hi64); tma_prefetch_desc(&tm_qkv_lo64);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % 3;
+                if (j >= 3) mbar_wait(&bars[S_EMPTY + s], ((j / 3) - 1) & 1);
+                mbar_expect_tx(&bars[S_FULL + s], SQ_STAGE);
+                uint8_t* st = sm + s * SQ_STAGE;
+                for (int qb = 0; qb < 2; ++qb) {          // rows past the last key and columns past the last query tile read as zero
+                    tma_load_3d(st + SQ_DS + qb * 8192, &tm_ds_hi, &bars[S_FULL + s], col0 + qb * 64, j * QT, b);
+                    tma_load_3d(st + SQ_DS + 16384 + qb * 8192, &tm_ds_lo, &bars[S_FULL + s], col0 + qb * 64, j * QT, b);
+                }
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(st + SQ_K + kb * 16384, &tm_qkv_hi64, &bars[S_FULL + s], 128 + kb * 64, k_lo + j * QT, b);            // K hi, d-half kb
+                    tma_load_3d(st + SQ_K + kb * 16384 + 8192, &tm_qkv_lo64, &bars[S_FULL + s], 128 + kb * 64, k_lo + j * QT, b);     // K lo
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        const uint64_t dA = smem_desc(smem_u32(sm + SQ_DS), 8192, 1024);       // MN-major A: query halves 8192 bytes apart, 16 keys per k-step
+        const uint64_t dB = smem_desc(smem_u32(sm + SQ_K), 16384, 1024);       // MN-major B: d-halves 16384 bytes apart
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j % 3;
+            mbar_wait(&bars[S_FULL + s], (j / 3) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t a = desc_adv(dA, s * SQ_STAGE), k = desc_adv(dB, s * SQ_STAGE);
+                uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass)                        // dS hi, hi, lo x K hi, lo, hi
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc_mma(tmem, desc_adv(a, (pass == 2 ? 16384 : 0) + ks * 2048), desc_adv(k, (pass == 1 ? 8192 : 0) + ks * 2048), IDESC_SQ, acc);
+                        acc = 1;
+                    }
+                tc_commit(&bars[S_EMPTY + s]);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tc_commit(&bars[S_DONE]);
+        __syncwarp();
+    } else if (warp < 8) {
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const int r_idx = r0 + row;
+        mbar_wait(&bars[S_DONE], 0);
+        tc_fence_after();
+        float* dst = dq + ((int64_t)b * T + r_idx) * ld_d + h * 64;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float t[32];
+            tmem_ld32(lane_addr + h * 64 + ch * 32, t);
+            if (r_idx < T) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 // =============================================================================================
@@ -649,7 +760,8 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                       const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64,
                       const __grid_constant__ CUtensorMap tm_do_hi64, const __grid_constant__ CUtensorMap tm_do_lo64, float* __restrict__ dv,
                       float* __restrict__ dk, int ld_d, const float* __restrict__ lse, const float* __restrict__ delta,
-                      const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int k_begin, int q_begin) {
+                      const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int k_begin, int q_begin,
+                      uint8_t* __restrict__ ds_hi, uint8_t* __restrict__ ds_lo, int ds_tq_pad, int ds_q_from) {
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + QOFF_BAR);
@@ -863,6 +975,18 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[E_DSFULL]);
+                // dS^T for the streaming dQ kernel: row = this key, 32 consecutive queries = 64 contiguous bytes per plane (the MN-major
+                // A operand of dQ = dS K needs exactly this [key][query] order); query tiles entirely below ds_q_from are never read
+                if (ds_hi != nullptr && r_idx < T && q_begin + j * QT + QT > ds_q_from) {
+                    const size_t off = (((size_t)b * (size_t)(T - k_begin) + (size_t)(r_idx - k_begin)) * (size_t)ds_tq_pad + (size_t)(j * QT + h * 32)) * 2u;
+                    uint4* ph = reinterpret_cast<uint4*>(ds_hi + off);
+                    uint4* pl = reinterpret_cast<uint4*>(ds_lo + off);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        ph[c] = make_uint4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]);
+                        pl[c] = make_uint4(dl[4 * c], dl[4 * c + 1], dl[4 * c + 2], dl[4 * c + 3]);
+                    }
+                }
             }
             TR(35, j);
         }
@@ -990,9 +1114,15 @@ int dip_debug_set_trace(unsigned long long* device_buffer) {
 }
 #endif
 
+size_t dip_attn_bwd_tc_ds_bytes(int B, int T, int do_begin, int k_begin) {
+    if (B <= 0 || T <= 0 || do_begin < 0 || do_begin >= T || k_begin < 0 || k_begin >= T) return 0;
+    const size_t tq_pad = (size_t)cdiv(T - do_begin, tcattn::QT) * tcattn::QT;
+    return 2u * (size_t)B * (size_t)(T - k_begin) * tq_pad * 2u;
+}
+
 int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo, const void* do_hi, const void* do_lo,
                     const float* o, const float* d_o, const float* lse, const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T,
-                    int do_begin, int q_begin, int k_begin, dip_stream_t stream) {
+                    int do_begin, int q_begin, int k_begin, void* ds_ws, size_t ds_ws_bytes, dip_stream_t stream) {
     DIP_REQUIRE(dq && dk && dv && qkv_hi && qkv_lo && do_hi && do_lo && o && d_o && lse && delta_ws && B > 0 && T > 0,
                 "dip_attn_bwd_tc: null/empty argument");
     DIP_REQUIRE(ld_d % 4 == 0 && B <= 65535, "dip_attn_bwd_tc: bad ld_d / B");
@@ -1002,8 +1132,16 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     if (!attr) {
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
+        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_dq_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::SQ_SMEM));
         attr = true;
     }
+    // with a dS workspace the key-stationary kernel stores dS^T and dQ is a streaming GEMM over it (no score recomputation)
+    const size_t ds_need = dip_attn_bwd_tc_ds_bytes(B, T, do_begin, k_begin);
+    const bool stream_dq = ds_ws != nullptr && ds_ws_bytes >= ds_need && ds_need > 0;
+    DIP_REQUIRE(ds_ws == nullptr || (reinterpret_cast<uintptr_t>(ds_ws) & 127) == 0, "dip_attn_bwd_tc: dS workspace must be 128-byte aligned");
+    const int tq_pad = cdiv(T - do_begin, tcattn::QT) * tcattn::QT;
+    uint8_t* ds_hi = stream_dq ? reinterpret_cast<uint8_t*>(ds_ws) : nullptr;
+    uint8_t* ds_lo = stream_dq ? ds_hi + ds_need / 2 : nullptr;
     cudaStream_t st = as_stream(stream);
     CUtensorMap q_hi128, q_lo128;
     DIP_TRY(make_tmap_bf16_3d(&q_hi128, qkv_hi, B, T, 3 * D, 3 * D, 128, 64));
@@ -1025,15 +1163,33 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
         dim3 grid(cdiv(T - k_begin, 128), B);      // keys k_begin.. stationary, queries do_begin.. streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DKDV, stream);
         tcattn::attn_bwd_kv_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, d_hi64, d_lo64, dv, dk, ld_d, lse,
-                                                                                       delta_ws, key_mask, mask_stride, T, k_begin, do_begin);
+                                                                                       delta_ws, key_mask, mask_stride, T, k_begin, do_begin, ds_hi, ds_lo, tq_pad,
+                                                                                       q_begin);
         DIP_LAUNCHED();
     }
-    {
-        dim3 grid(cdiv(T - q_begin, 128), B);      // queries q_begin.. stationary, all keys streamed
-        DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
+    dim3 grid(cdiv(T - q_begin, 128), B);          // 128 stationary queries per CTA
+    if (stream_dq) {
+        CUtensorMap s_hi, s_lo;
+        DIP_TRY(make_tmap_bf16_3d(&s_hi, ds_hi, B, T - k_begin, tq_pad, tq_pad, 64, 64));
+        DIP_TRY(make_tmap_bf16_3d(&s_lo, ds_lo, B, T - k_begin, tq_pad, tq_pad, 64, 64));
+        {
+            DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);    // keys k_begin .. T-1 from the stored dS
+            tcattn::attn_bwd_dq_stream_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::SQ_SMEM, st>>>(s_hi, s_lo, q_hi64, q_lo64, dq, ld_d, T, q_begin, k_begin,
+                                                                                                  q_begin - do_begin);
+            DIP_LAUNCHED();
+        }
+        if (k_begin > 0) {                             // keys below k_begin have no stationary CTA (their dK / dV are not wanted): recompute path, added on top
+            DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);
+            tcattn::attn_bwd_dq_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, reinterpret_cast<const uint4*>(do_hi),
+                                                                                           reinterpret_cast<const uint4*>(do_lo), dq, ld_d, lse, delta_ws, key_mask,
+                                                                                           mask_stride, T, q_begin, k_begin, 1);
+            DIP_LAUNCHED();
+        }
+    } else {
+        DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);        // queries q_begin.. stationary, all keys streamed, S and dP recomputed
         tcattn::attn_bwd_dq_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, reinterpret_cast<const uint4*>(do_hi),
                                                                                        reinterpret_cast<const uint4*>(do_lo), dq, ld_d, lse, delta_ws, key_mask,
-                                                                                       mask_stride, T, q_begin);
+                                                                                       mask_stride, T, q_begin, T, 0);
         DIP_LAUNCHED();
     }
     return 0;

@@ -156,6 +156,8 @@ struct Workspace {
     float *h, *h2;
     float *dxa, *dxb, *dxm, *dt1, *dt2, *dao, *dqkv, *delta;
     float *p_full, *dz, *viol, *obj, *mean_buf;
+    void* ds;             // dS^T planes of one attention backward (tensor-core mode), see dip_attn_bwd_tc
+    size_t ds_bytes;
     size_t bytes;
 };
 
@@ -203,6 +205,14 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
     w.viol = c.take<float>(B);
     w.obj = c.take<float>(B);
     w.mean_buf = c.take<float>((size_t)B * L * D);
+    // dS^T scratch: the largest of the decoder layers' backward launches (layer 0: keys >= L, all queries unless it is also the last
+    // layer; last layer: all keys, queries >= L)
+    w.ds_bytes = 0;
+    for (int l = 0; l < e->n_dec; ++l) {
+        const size_t need = dip_attn_bwd_tc_ds_bytes(B, (int)T2, l == e->n_dec - 1 ? (int)L : 0, l == 0 ? (int)L : 0);
+        w.ds_bytes = need > w.ds_bytes ? need : w.ds_bytes;
+    }
+    w.ds = c.take<uint8_t>(w.ds_bytes);
     w.bytes = (c.off + 255) & ~(size_t)255;
     return w;
 }
@@ -301,8 +311,8 @@ static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float
 // out-projection) runs on t >= do_begin, the attention backward streams queries t >= do_begin only and produces
 // dK, dV for t >= t_min and dQ for t >= max(t_min, do_begin), the in-projection backward runs on t >= t_min.
 static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin, const LayerSave& s, const uint8_t* mask, int64_t mask_stride, int B, int T, float* dt1,
-                     float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, float* dxin, int t_min, int do_begin,
-                     dip_stream_t st) {
+                     float* dt2, float* dxm, float* dao, void* do_hi, void* do_lo, float* dqkv, float* delta, void* ds, size_t ds_bytes, float* dxin, int t_min,
+                     int do_begin, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     if (!tc) do_begin = 0;
@@ -331,7 +341,7 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
             DIP_CUDA(cudaMemset2DAsync(dxm, (size_t)T * D * sizeof(float), 0, (size_t)do_begin * D * sizeof(float), (size_t)B, cs));
         }
         DIP_TRY(dip_attn_bwd_tc(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv_hi, s.qkv_lo, do_hi, do_lo, s.ao, dao, s.lse, mask, mask_stride, delta, B, T,
-                                do_begin, q_begin, t_min, st));
+                                do_begin, q_begin, t_min, ds, ds_bytes, st));
     } else {
         DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, mask_stride, delta, B, T, st));
     }
@@ -459,7 +469,7 @@ static int guidance_grad(dip_engine* e, const Workspace& w, const float* x, int 
         const dip_rows xin = l == 0 ? mip_rows(v, x, T2, L) : plain_rows(w.ls[l - 1].xout, T2);
         // the gradient w.r.t. the (constant) mip tokens of layer 0 is never used, and only the last L tokens of the last
         // layer's output carry a gradient (head_bwd writes zeros elsewhere; in tensor-core mode those rows are not even read)
-        DIP_TRY(block_bwd(e->mode, e->dec[l], dcur, xin, w.ls[l], v.mask_dec, v.mask_dec_stride, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.do_hi, w.do_lo, w.dqkv, w.delta,
+        DIP_TRY(block_bwd(e->mode, e->dec[l], dcur, xin, w.ls[l], v.mask_dec, v.mask_dec_stride, B, T2, w.dt1, w.dt2, w.dxm, w.dao, w.do_hi, w.do_lo, w.dqkv, w.delta, w.ds, w.ds_bytes,
                           dnext, l == 0 ? L : 0, l == e->n_dec - 1 ? L : 0, st));
         float* t = dcur; dcur = dnext; dnext = t;
     }

@@ -87,7 +87,8 @@ PROTOTYPES = {
     "dip_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp, i32, i32, vp]),
     "dip_split_bf16": (i32, [vp, vp, vp, i64, vp]),
     "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
-    "dip_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
+    "dip_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
+    "dip_attn_bwd_tc_ds_bytes": (sz, [i32, i32, i32, i32]),
     "dip_layernorm_split": (i32, [vp, vp, vp, vp, Rows, vp, vp, i64, i32, vp]),
     "dip_gemm_tc_planes": (i32, [C.POINTER(GemmArgs), vp, vp, vp, vp, vp]),
     "dip_gemm_tc": (i32, [C.POINTER(GemmArgs), vp, vp, C.POINTER(Rows), vp, vp, vp, vp, vp]),

@@ -156,8 +156,9 @@ def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None, q_begin=0
     return o, lse
 
 
-def attn_bwd_tc(qkv_hi, qkv_lo, o, d_o, lse, B, T, key_mask=None, mask_stride=None, do_begin=0, q_begin=0, k_begin=0):
-    """Rows outside the windows (dq: t < q_begin; dk, dv: t < k_begin) come back as NaN."""
+def attn_bwd_tc(qkv_hi, qkv_lo, o, d_o, lse, B, T, key_mask=None, mask_stride=None, do_begin=0, q_begin=0, k_begin=0, stream_dq=True):
+    """Rows outside the windows (dq: t < q_begin; dk, dv: t < k_begin) come back as NaN.  stream_dq: give the launcher a dS workspace
+    (dQ as a streaming GEMM over the stored dS^T) instead of running the recompute dQ kernel."""
     lib = _lib.load()
     o, d_o = _f32(o), _f32(d_o)
     do_hi, do_lo = split_bf16(d_o)
@@ -165,8 +166,13 @@ def attn_bwd_tc(qkv_hi, qkv_lo, o, d_o, lse, B, T, key_mask=None, mask_stride=No
     delta = torch.empty(B * T, dtype=torch.float32, device=o.device)
     km, ms = _mask(key_mask, B, T, mask_stride)
     dbase = dqkv.data_ptr()
+    ds, ds_bytes = None, 0
+    if stream_dq:
+        ds_bytes = lib.dip_attn_bwd_tc_ds_bytes(B, T, int(do_begin), int(k_begin))
+        ds = torch.empty(ds_bytes + 128, dtype=torch.uint8, device=o.device)
+    ds_ptr = None if ds is None else ds.data_ptr() + ((-ds.data_ptr()) % 128)
     check(lib.dip_attn_bwd_tc(dbase, dbase + 4 * D, dbase + 8 * D, 3 * D, ptr(qkv_hi), ptr(qkv_lo), ptr(do_hi), ptr(do_lo), ptr(o), ptr(d_o),
-                              ptr(lse), ptr(km), ms, ptr(delta), B, T, int(do_begin), int(q_begin), int(k_begin), _stream()))
+                              ptr(lse), ptr(km), ms, ptr(delta), B, T, int(do_begin), int(q_begin), int(k_begin), ds_ptr, ds_bytes, _stream()))
     return dqkv
 
 

@@ -180,7 +180,12 @@ int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo
 int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_hi, const void* qkv_lo,
                     const void* do_hi, const void* do_lo, const float* o, const float* d_o, const float* lse,
                     const uint8_t* key_mask, int64_t mask_stride, float* delta_ws, int B, int T,
-                    int do_begin, int q_begin, int k_begin, dip_stream_t stream);
+                    int do_begin, int q_begin, int k_begin, void* ds_ws, size_t ds_ws_bytes, dip_stream_t stream);
+/* ds_ws (nullable, 128-byte aligned, dip_attn_bwd_tc_ds_bytes bytes): scratch for dS^T as bf16 (hi, lo) planes.  When given, the
+ * key-stationary kernel -- which forms every dS tile for dK anyway -- also stores it, and dQ = dS K becomes a streaming GEMM over the
+ * stored tiles instead of a second kernel that recomputes S and dP (5 instead of 7 T^2 D products per backward); without it the
+ * query-stationary recompute kernel runs.  Results agree to fp32 rounding of the accumulation order, both are deterministic. */
+size_t dip_attn_bwd_tc_ds_bytes(int B, int T, int do_begin, int k_begin);
 /* Row windows of dip_attn_bwd_tc (0, 0, 0 = everything): d_o is taken as zero for queries t < do_begin (those rows of
  * d_o / o / lse are never read); dq is written for t >= q_begin only (q_begin >= do_begin); dk, dv for t >= k_begin
  * only.  Unwritten rows keep their previous content. */

@@ -30,8 +30,9 @@ def small_case(seed=0, L=24, n=20, M=12, nnz=44, B=2, dup=4):
     rng = np.random.default_rng(seed)
     rows = rng.integers(0, M, size=nnz)
     cols = rng.integers(0, n, size=nnz)
-    rows[-dup:] = rows[:dup]
-    cols[-dup:] = cols[:dup]
+    if dup > 0:
+        rows[-dup:] = rows[:dup]
+        cols[-dup:] = cols[:dup]
     vals = -np.ones(nnz, dtype=np.float32)
     vals[::5] = 2.0
     b = (-rng.random(M)).astype(np.float32)

@@ -56,6 +56,12 @@ struct Tracer { __device__ Tracer(int) {} };
 #define TR(e, t)
 #endif
 
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+                 "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ void require_aligned_smem(const void* p) {
     if ((smem_u32(p) & 1023u) != 0u) {
         if (threadIdx.x == 0) printf("dip: dynamic shared memory is not 1024-byte aligned\n");
@@ -653,15 +659,17 @@ enum { S_FULL = 0, S_EMPTY = 3, S_DONE = 6 };
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_stream_tc_kernel(const __grid_constant__ CUtensorMap tm_ds_hi, const __grid_constant__ CUtensorMap tm_ds_lo,
                              const __grid_constant__ CUtensorMap tm_qkv_hi64, const __grid_constant__ CUtensorMap tm_qkv_lo64, float* __restrict__ dq,
-                             int ld_d, int T, int q_begin, int k_lo, int ds_col0) {
-    // queries q_begin + 128 * blockIdx.x ..., keys k_lo .. T-1; column c of the dS^T buffer is query (q_begin - ds_col0) + c, its row r is key k_lo + r
+                             int ld_d, int T, int q_begin, int k_lo, int q_origin, int c_start) {
+    // Column c of the dS^T buffer is query q_origin + c, its row r is key k_lo + r.  CTA i works on the 128 columns from c_start + 128 i:
+    // c_start is a multiple of the writer's 64-query tiles (TMA needs 16-byte aligned box origins), so the first CTA may begin below
+    // q_begin -- those rows are computed and dropped.  Keys k_lo .. T-1.
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SQ_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, r0 = q_begin + blockIdx.x * 128;
-    const int col0 = ds_col0 + blockIdx.x * 128;
+    const int col0 = c_start + blockIdx.x * 128;
+    const int b = blockIdx.y, r0 = q_origin + col0;
     const int n_tiles = (T - k_lo + QT - 1) / QT;
     if (threadIdx.x == 0) {
         for (int s = 0; s < 3; ++s) { mbar_init(&bars[S_FULL + s], 1); mbar_init(&bars[S_EMPTY + s], 1); }
@@ -727,7 +735,7 @@ attn_bwd_dq_stream_tc_kernel(const __grid_constant__ CUtensorMap tm_ds_hi, const
         for (int ch = 0; ch < 2; ++ch) {
             float t[32];
             tmem_ld32(lane_addr + h * 64 + ch * 32, t);
-            if (r_idx < T) {
+            if (r_idx < T && r_idx >= q_begin) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
             }
@@ -921,6 +929,23 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         const int r_idx = r0 + row;
         bool row_ok = r_idx < T;
         if (row_ok && mrow && mrow[r_idx]) row_ok = false;          // masked key: its column of P is zero
+        // dS^T for the streaming dQ kernel: row = this key, 32 consecutive queries = 64 contiguous bytes per plane (the MN-major A operand
+        // of dQ = dS K needs exactly this [key][query] order).  The stores of tile j are issued half an iteration later, after P_{j+1}
+        // has been handed to the tensor pipe: right after dS_j they would delay P_{j+1} (every 256-bit store instruction is 32 L1
+        // wavefronts -- 32 different rows) and with it the product the pipe is waiting for; here they fall into the wait for dP_{j+1}.
+        uint32_t dh[16], dl[16];
+        size_t ds_off = 0;
+        bool ds_pending = false;
+        auto flush_ds = [&]() {
+            if (ds_pending) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    st_global_v8(ds_hi + ds_off + 32 * c, dh + 8 * c);
+                    st_global_v8(ds_lo + ds_off + 32 * c, dl + 8 * c);
+                }
+                ds_pending = false;
+            }
+        };
         for (int j = 0; j < n_tiles; ++j) {
             // lane l fetches lse and delta of query h*32 + l of this tile; broadcast by shuffle below
             const int cq = q_begin + j * QT + h * 32 + lane;
@@ -954,13 +979,13 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 tc_fence_before();
                 mbar_arrive(&bars[E_PFULL]);
             }
+            flush_ds();                                             // dS^T of the previous tile
             TR(32, j);
             mbar_wait(&bars[E_G2FULL], j & 1);
             TR(33, j);
             tc_fence_after();
             {
                 float g2[32], t[32];
-                uint32_t dh[16], dl[16];
                 tmem_ld32x2(lane_addr + KTM_G2 + h * 32, g2, lane_addr + KTM_G2 + 64 + h * 32, t);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
@@ -975,21 +1000,15 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[E_DSFULL]);
-                // dS^T for the streaming dQ kernel: row = this key, 32 consecutive queries = 64 contiguous bytes per plane (the MN-major
-                // A operand of dQ = dS K needs exactly this [key][query] order); query tiles entirely below ds_q_from are never read
+                // query tiles entirely below ds_q_from are never read by the dQ kernel
                 if (ds_hi != nullptr && r_idx < T && q_begin + j * QT + QT > ds_q_from) {
-                    const size_t off = (((size_t)b * (size_t)(T - k_begin) + (size_t)(r_idx - k_begin)) * (size_t)ds_tq_pad + (size_t)(j * QT + h * 32)) * 2u;
-                    uint4* ph = reinterpret_cast<uint4*>(ds_hi + off);
-                    uint4* pl = reinterpret_cast<uint4*>(ds_lo + off);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        ph[c] = make_uint4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]);
-                        pl[c] = make_uint4(dl[4 * c], dl[4 * c + 1], dl[4 * c + 2], dl[4 * c + 3]);
-                    }
+                    ds_off = (((size_t)b * (size_t)(T - k_begin) + (size_t)(r_idx - k_begin)) * (size_t)ds_tq_pad + (size_t)(j * QT + h * 32)) * 2u;
+                    ds_pending = true;
                 }
             }
             TR(35, j);
         }
+        flush_ds();
         mbar_wait(&bars[E_DONE], 0);
         tc_fence_after();
         const bool store_ok = r_idx < T;
@@ -1169,13 +1188,15 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     }
     dim3 grid(cdiv(T - q_begin, 128), B);          // 128 stationary queries per CTA
     if (stream_dq) {
+        const int c_start = (q_begin - do_begin) / tcattn::QT * tcattn::QT;
+        dim3 sgrid(cdiv(T - do_begin - c_start, 128), B);
         CUtensorMap s_hi, s_lo;
         DIP_TRY(make_tmap_bf16_3d(&s_hi, ds_hi, B, T - k_begin, tq_pad, tq_pad, 64, 64));
         DIP_TRY(make_tmap_bf16_3d(&s_lo, ds_lo, B, T - k_begin, tq_pad, tq_pad, 64, 64));
         {
             DIP_PROF(DIP_PROF_ATTN_BWD_DQ, stream);    // keys k_begin .. T-1 from the stored dS
-            tcattn::attn_bwd_dq_stream_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::SQ_SMEM, st>>>(s_hi, s_lo, q_hi64, q_lo64, dq, ld_d, T, q_begin, k_begin,
-                                                                                                  q_begin - do_begin);
+            tcattn::attn_bwd_dq_stream_tc_kernel<<<sgrid, tcattn::NTHREADS, tcattn::SQ_SMEM, st>>>(s_hi, s_lo, q_hi64, q_lo64, dq, ld_d, T, q_begin, k_begin,
+                                                                                                   do_begin, c_start);
             DIP_LAUNCHED();
         }
         if (k_begin > 0) {                             // keys below k_begin have no stationary CTA (their dK / dV are not wanted): recompute path, added on top

@@ -15,7 +15,9 @@ from types import SimpleNamespace
 
 import numpy as np
 
-_TERM = re.compile(r"([+-]?)\s*(\d+(?:\.\d*)?(?:[eE][+-]?\d+)?)?\s*\*?\s*([A-Za-z_!\"#$%&()/,;?@'`{}|~][\w!\"#$%&()/,.;?@'`{}|~\[\]]*)")
+_NUM = r"(?:\d+(?:\.\d*)?|\.\d+)(?:[eE][+-]?\d+)?"          # 3, 3., 3.5, .5, 1e3
+_TERM = re.compile(r"([+-]?)\s*(" + _NUM + r")?\s*\*?\s*([A-Za-z_!\"#$%&()/,;?@'`{}|~][\w!\"#$%&()/,.;?@'`{}|~\[\]]*)")
+_ROW = re.compile(r"(?:([A-Za-z_][\w.\[\]]*)\s*:)?\s*([^:<>=]*?)\s*(<=|=<|>=|=>|<|>|=)\s*([+-]?\s*" + _NUM + r")")
 _SECTIONS = ("maximize", "maximise", "max", "minimize", "minimise", "min", "subject to", "such that", "st", "s.t.", "bounds", "bound",
              "binaries", "binary", "bin", "generals", "general", "gen", "end")
 
@@ -50,20 +52,37 @@ def parse_lp(text):
         raise ValueError("no Binaries section: binary programs only")
     index = {v: i for i, v in enumerate(names)}
     c = np.zeros(len(names), dtype=np.int64)
+
+    def col(nm, where):
+        if nm not in index:
+            raise ValueError("%s uses '%s', which is not declared in the Binaries section (binary programs only)" % (where, nm))
+        return index[nm]
+
     for nm, v in _terms(obj_txt):
-        c[index[nm]] += int(round(sense * v))
+        if v != round(v):
+            raise ValueError("objective coefficient %g of %s is not an integer (the exact objective check works on integers)" % (v, nm))
+        c[col(nm, "the objective")] += int(round(sense * v))
+    for b in sections.get("bounds", []):
+        if not re.fullmatch(r"\s*(?:0\s*<=\s*)?\S+\s*<=\s*1\s*|\s*\S+\s*>=\s*0\s*|\s*0\s*<=\s*\S+\s*", b):
+            raise ValueError("only 0/1 bounds are supported (got '%s')" % b)
     rows = []
     cons_txt = " ".join(sections.get("subject to", []))
-    # rows are "name: expr op rhs"; split on the row labels
-    parts = re.split(r"([A-Za-z_][\w.\[\]]*)\s*:", cons_txt)
-    bodies = [(parts[i], parts[i + 1]) for i in range(1, len(parts) - 1, 2)] if len(parts) > 1 else [("r0", cons_txt)]
-    for label, body in bodies:
-        m = re.search(r"(<=|=<|>=|=>|=)\s*([+-]?\s*\d+(?:\.\d*)?)", body)
-        if not m:
-            raise ValueError("row %s has no relational operator" % label)
-        op, rhs = m.group(1), float(m.group(2).replace(" ", ""))
-        coefs = [(index[nm], v) for nm, v in _terms(body[:m.start()])]
-        rows.append((label, coefs, op, rhs))
+    # every row is "[label:] expr op rhs": rows are delimited by their relational operator + right-hand side, so unlabeled rows
+    # are read one by one like labeled ones; anything left between two rows is an error, not silently dropped
+    pos = 0
+    for k, m in enumerate(_ROW.finditer(cons_txt)):
+        if cons_txt[pos:m.start()].strip():
+            raise ValueError("cannot parse '%s' in the constraint section" % cons_txt[pos:m.start()].strip())
+        label = m.group(1) or ("r%d" % k)
+        op = {"<": "<=", ">": ">=", "=<": "<=", "=>": ">="}.get(m.group(3), m.group(3))
+        body = m.group(2)
+        terms = _terms(body)
+        if not terms or _TERM.sub("", body).strip(" +-"):
+            raise ValueError("row %s: cannot parse '%s'" % (label, body))
+        rows.append((label, [(col(nm, "row " + label), v) for nm, v in terms], op, float(m.group(4).replace(" ", ""))))
+        pos = m.end()
+    if cons_txt[pos:].strip():
+        raise ValueError("cannot parse '%s' at the end of the constraint section" % cons_txt[pos:].strip())
     return _assemble(names, c, rows, sense)
 
 
@@ -71,6 +90,7 @@ def parse_mps(text):
     """Free-format MPS of a binary program: ROWS (N, L, G, E), COLUMNS (MARKER lines ignored), RHS, BOUNDS (BV / UP 1 / LO 0)."""
     sec, rows_kind, order, cols, rhs, names = None, {}, [], {}, {}, []
     obj_row, sense = None, 1
+    binary, marked, in_int = set(), set(), False
     for raw in text.splitlines():
         if not raw.strip() or raw.lstrip().startswith("*"):
             continue
@@ -89,11 +109,14 @@ def parse_mps(text):
                 order.append(nm)
         elif sec == "COLUMNS":
             if len(tok) >= 3 and tok[1].upper() == "'MARKER'":
+                in_int = "INTORG" in tok[2].upper()
                 continue
             col = tok[0]
             if col not in cols:
                 cols[col] = {}
                 names.append(col)
+            if in_int:
+                marked.add(col)
             for r, v in zip(tok[1::2], tok[2::2]):
                 cols[col][r] = cols[col].get(r, 0.0) + float(v)
         elif sec == "RHS":
@@ -104,12 +127,24 @@ def parse_mps(text):
             val = float(tok[3]) if len(tok) > 3 else None
             if not (kind == "BV" or (kind == "UP" and val == 1.0) or (kind == "LO" and val == 0.0)):
                 raise ValueError("only 0/1 bounds are supported (got %s)" % raw.strip())
+            if kind in ("BV", "UP"):
+                binary.add(tok[2])
+        elif sec == "RANGES":
+            raise ValueError("a RANGES section is not supported (write ranged rows as two rows)")
+        elif sec not in ("NAME", "OBJSENSE", "ROWS", "COLUMNS", "RHS", "BOUNDS", "ENDATA", "OBJSENSE:"):
+            raise ValueError("MPS section %s is not supported" % sec)
+    loose = [v for v in names if v not in binary]
+    if loose:
+        # a column without a BV / "UP 1" bound is continuous (or, inside integer markers, a general integer) in MPS: not a binary program
+        raise ValueError("columns without a 0/1 bound (binary programs only): %s%s" % (", ".join(loose[:5]), " ..." if len(loose) > 5 else ""))
     index = {v: i for i, v in enumerate(names)}
     c = np.zeros(len(names), dtype=np.int64)
     per_row = {r: [] for r in order}
     for col, ent in cols.items():
         for r, v in ent.items():
             if r == obj_row:
+                if v != round(v):
+                    raise ValueError("objective coefficient %g of %s is not an integer (the exact objective check works on integers)" % (v, col))
                 c[index[col]] += int(round(sense * v))
             else:
                 per_row[r].append((index[col], v))

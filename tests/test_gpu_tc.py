@@ -189,7 +189,7 @@ def test_attention_bwd_tc_windows(cuda, B, T, do_b, q_b, k_b, stream_dq):
     d_o[:, :do_b] = 0
     hi, lo = ops.split_bf16(qkv.to(cuda))
     o, lse = ops.attn_fwd_tc(hi, lo, B, T, mask.to(cuda))
-    full = ops.attn_bwd_tc(hi, lo, o, d_o.reshape(B * T, D).to(cuda), lse, B, T, mask.to(cuda)).view(B, T, 3 * D)
+    full = ops.attn_bwd_tc(hi, lo, o, d_o.reshape(B * T, D).to(cuda), lse, B, T, mask.to(cuda), stream_dq=stream_dq).view(B, T, 3 * D)
     # the windowed launch must not read anything below do_begin: poison those rows of dO, o and lse
     d_o_p, o_p, lse_p = d_o.clone().to(cuda), o.clone().view(B, T, D), lse.clone().view(B, T)
     d_o_p[:, :do_b] = float("nan"); o_p[:, :do_b] = float("nan"); lse_p[:, :do_b] = float("nan")
@@ -199,7 +199,7 @@ def test_attention_bwd_tc_windows(cuda, B, T, do_b, q_b, k_b, stream_dq):
     assert not torch.isnan(win[:, q_b:, :D]).any() and not torch.isnan(win[:, k_b:, D:]).any()
     # dq: the same products whatever the window (with a dS workspace and k_begin > 0 the keys below k_begin go through the recompute
     # kernel and are added on top: another summation order); dk / dv sum over fewer (all-zero) query tiles
-    assert rel_l2(win[:, q_b:, :D], full[:, q_b:, :D]) < 2e-6
+    assert rel_l2(win[:, q_b:, :D], full[:, q_b:, :D]) < 2e-5
     assert rel_l2(win[:, k_b:, D:], full[:, k_b:, D:]) < 1e-6
     if T <= 300:
         ref_in = qkv.double().requires_grad_(True)

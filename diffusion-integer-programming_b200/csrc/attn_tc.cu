@@ -92,10 +92,19 @@ constexpr float RESCALE_THRESHOLD = 8.0f;                   // log2 units: P sta
 
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17 };
 
+// Key-prefix hoisting (decoder layer 0): the first L of the 2L tokens are the instance embedding, the same for every step of a wave, so
+// for a query that is itself an instance token the scores against the instance keys -- and with them the running maximum, the running
+// sum and the un-normalised P.V accumulator after those key tiles -- never change.  A "save" launch (state_out) runs the key tiles
+// [0, j_split) once per wave and writes that state; afterwards CTAs whose 128 queries all lie below hoist_rows start from it and stream
+// the key tiles from j_split on only.  The state is exactly what the full loop holds at that point, so results are bit-identical.
+// state layout: per (sample, query row) 132 floats = 128 accumulator columns | m_used | l_part of key half 0 | l_part of key half 1 | pad
+constexpr int STATE_W = 132;
+
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_constant__ CUtensorMap tm_lo128,
                    const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64, float* __restrict__ o,
-                   float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin) {
+                   float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin,
+                   const float* __restrict__ state_in, float* __restrict__ state_out, int j_split, int hoist_rows) {
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint8_t* sQ = sm;
@@ -109,7 +118,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, q0 = q_begin + blockIdx.x * BM;      // queries q_begin .. T-1 only
     const int row_base = b * T;
-    const int n_tiles = (T + BN - 1) / BN;
+    // key tiles jb .. je-1 (CTA-uniform): a save launch stops at the split, a hoisted CTA starts there
+    const bool hoisted = state_in != nullptr && q0 + BM <= hoist_rows;
+    const int jb = hoisted ? j_split : 0;
+    const int je = state_out != nullptr ? j_split : (T + BN - 1) / BN;
+    const int n_loop = je - jb;                                     // ring slots and barrier phases count from jb (jj = j - jb)
     Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && (warp == W_PRODUCER || warp == W_PRODUCER_V)) ? (warp == W_PRODUCER ? 1 : 4) : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
 
     if (threadIdx.x == 0) {
@@ -135,16 +148,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
         // ------------------------------------------------------------------ TMA producer + mask ballots
         const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
         auto load_K = [&](int j) {      // all lanes: ballot the mask of tile j; lane 0: wait for the stage, issue the 4 boxes
-            const int s = j % K_STAGES;
+            const int jj = j - jb, s = jj % K_STAGES;
             const int k0 = j * BN + lane, k1 = k0 + 32;
             const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
             const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
             const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
             if (lane == 0) {
                 TR(40, j);
-                if (j >= K_STAGES) mbar_wait(&bars[B_KEMPTY + s], ((j / K_STAGES) - 1) & 1);
+                if (jj >= K_STAGES) mbar_wait(&bars[B_KEMPTY + s], ((jj / K_STAGES) - 1) & 1);
                 TR(41, j);
-                bits_ring[j & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
+                bits_ring[jj & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
                 mbar_expect_tx(&bars[B_KFULL + s], K_STAGE);
                 uint8_t* dst = sK + s * K_STAGE;
                 for (int kb = 0; kb < 2; ++kb) {
@@ -164,14 +177,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
         }
         // K runs up to three tiles ahead, independent of the V ring: a single producer thread alternating between the two rings
         // stalled the K loads behind the V ring's empty-waits and left the TMA queue idle a third of the time (tools/ktrace.py)
-        for (int j = 0; j < n_tiles; ++j) load_K(j);
+        for (int j = jb; j < je; ++j) load_K(j);
     } else if (warp == W_PRODUCER_V) {
         // ------------------------------------------------------------------ TMA producer of the V ring
         if (lane == 0) {
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
+            for (int j = jb; j < je; ++j) {
+                const int jj = j - jb, s = jj & 1;
                 TR(42, j);
-                if (j >= 2) mbar_wait(&bars[B_VEMPTY + s], ((j >> 1) - 1) & 1);
+                if (jj >= 2) mbar_wait(&bars[B_VEMPTY + s], ((jj >> 1) - 1) & 1);
                 TR(43, j);
                 mbar_expect_tx(&bars[B_VFULL + s], V_STAGE);
                 uint8_t* dst = sV + s * V_STAGE;
@@ -186,13 +199,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
         const uint64_t dQ = smem_desc(smem_u32(sQ), 16, 1024), dK = smem_desc(smem_u32(sK), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
         if (warp == W_MMA) {
             mbar_wait(&bars[B_QFULL], 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j % K_STAGES, sb = j & 1;
-                TR(20, j);
-                mbar_wait(&bars[B_KFULL + s], (j / K_STAGES) & 1);
-                TR(21, j);
-                if (j >= 2) mbar_wait(&bars[B_SFREE + sb], ((j >> 1) - 1) & 1);
-                TR(22, j);
+            for (int jj = 0; jj < n_loop; ++jj) {
+                const int s = jj % K_STAGES, sb = jj & 1;
+                TR(20, jj);
+                mbar_wait(&bars[B_KFULL + s], (jj / K_STAGES) & 1);
+                TR(21, jj);
+                if (jj >= 2) mbar_wait(&bars[B_SFREE + sb], ((jj >> 1) - 1) & 1);
+                TR(22, jj);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t kbase = desc_adv(dK, s * K_STAGE);
@@ -210,16 +223,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                     tc_commit(&bars[B_KEMPTY + s]);
                 }
                 __syncwarp();
-                TR(23, j);
+                TR(23, jj);
             }
         } else {
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                TR(24, j);
-                mbar_wait(&bars[B_VFULL + s], (j >> 1) & 1);
-                TR(25, j);
-                mbar_wait(&bars[B_PFULL + s], (j >> 1) & 1);       // P_j stored AND the previous P.V tile folded by the row warps
-                TR(26, j);
+            for (int jj = 0; jj < n_loop; ++jj) {
+                const int s = jj & 1;
+                TR(24, jj);
+                mbar_wait(&bars[B_VFULL + s], (jj >> 1) & 1);
+                TR(25, jj);
+                mbar_wait(&bars[B_PFULL + s], (jj >> 1) & 1);       // P_j stored AND the previous P.V tile folded by the row warps
+                TR(26, jj);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t vbase = desc_adv(dVmn, s * V_STAGE);
@@ -238,7 +251,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                     tc_commit(&bars[B_VEMPTY + s]);
                 }
                 __syncwarp();
-                TR(28, j);
+                TR(28, jj);
             }
         }
     } else {
@@ -246,15 +259,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
         const int q = warp & 3, h = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const int t_q = q0 + row;
         float oacc[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) oacc[i] = 0.f;
         float m_used = -INFINITY, l_part = 0.f;
-        for (int j = 0; j < n_tiles; ++j) {
-            const int s = j & 1;
-            TR(30, j);
-            mbar_wait(&bars[B_SFULL + s], (j >> 1) & 1);
-            TR(31, j);
+        if (hoisted) {
+            // resume from the state the save launch left after the key tiles [0, j_split)
+            const float* st = state_in + ((int64_t)b * hoist_rows + t_q) * STATE_W;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(st + h * 64 + i);
+                oacc[i] = v.x; oacc[i + 1] = v.y; oacc[i + 2] = v.z; oacc[i + 3] = v.w;
+            }
+            m_used = st[128];
+            l_part = st[129 + h];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) oacc[i] = 0.f;
+        }
+        for (int jj = 0; jj < n_loop; ++jj) {
+            const int s = jj & 1;
+            TR(30, jj);
+            mbar_wait(&bars[B_SFULL + s], (jj >> 1) & 1);
+            TR(31, jj);
             tc_fence_after();
             float sv[32];
             {
@@ -265,8 +291,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             }
             tc_fence_before();
             mbar_arrive(&bars[B_SFREE + s]);
-            TR(32, j);
-            const uint32_t mb = (uint32_t)(bits_ring[j & 7] >> (32 * h));
+            TR(32, jj);
+            const uint32_t mb = (uint32_t)(bits_ring[jj & 7] >> (32 * h));
             float mx = -INFINITY;
             if (mb == 0u) {
 #pragma unroll
@@ -281,7 +307,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             // the two key halves of a row agree on the tile maximum through shared memory
             xm[(s * 2 + h) * 128 + row] = mx;
             named_bar_sync(1, ROW_THREADS);
-            TR(33, j);
+            TR(33, jj);
             const float m_tile = fmaxf(mx, xm[(s * 2 + (h ^ 1)) * 128 + row]) * SC2;
             // lazy rescaling: the exponent base only moves when the row maximum grew by more than 2^8
             const bool need = m_tile > m_used + RESCALE_THRESHOLD;
@@ -302,14 +328,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             m_used = m_new;
             // P_j -> tensor memory (A operand of P.V): this half's 32 keys = 16 packed columns per plane.
             // Buffer s was last read by P_{j-2}.V_{j-2}, whose completion this thread observed one iteration ago.
-            TR(34, j);
+            TR(34, jj);
             tmem_st16(lane_addr + TM_P + s * 64 + h * 16, phi);
             tmem_st16(lane_addr + TM_P + s * 64 + 32 + h * 16, plo);
             tmem_st_wait();
-            TR(35, j);
-            if (j > 0) {
-                mbar_wait(&bars[B_PVFULL], (j - 1) & 1);
-                TR(36, j);
+            TR(35, jj);
+            if (jj > 0) {
+                mbar_wait(&bars[B_PVFULL], (jj - 1) & 1);
+                TR(36, jj);
                 tc_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
@@ -322,35 +348,58 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
 #pragma unroll
                         for (int i = 0; i < 32; ++i) oacc[ch * 32 + i] += t[i];
                     }
-                }
-                TR(37, j);
+                } 
+                TR(37, jj);
+            } else if (hoisted && any_need) {
+                // first tile after a resume: no P.V product is pending, but the restored accumulator still follows the exponent base
+#pragma unroll
+                for (int i = 0; i < 64; ++i) oacc[i] *= alpha;
             }
             // one arrival publishes both facts the accumulate issuer needs: P_j is in tensor memory and the P.V tile is free again
             tc_fence_before();
             mbar_arrive(&bars[B_PFULL + s]);
         }
-        mbar_wait(&bars[B_PVFULL], (n_tiles - 1) & 1);
+        mbar_wait(&bars[B_PVFULL], (n_loop - 1) & 1);
         tc_fence_after();
-        // total row sum = the two halves' partial sums
-        named_bar_sync(1, ROW_THREADS);
-        xm[h * 128 + row] = l_part;
-        named_bar_sync(1, ROW_THREADS);
-        const float l_run = l_part + xm[(h ^ 1) * 128 + row];
-        const float inv = 1.0f / l_run;
-        const int t_q = q0 + row;
+        if (state_out != nullptr) {
+            // save launch: the raw state after the key tiles [0, j_split) -- accumulator with the last product folded in, base, partial sums
+            float* st = state_out + ((int64_t)b * hoist_rows + t_q) * STATE_W;
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            float t[32];
-            tmem_ld32(lane_addr + TM_PV + h * 64 + ch * 32, t);
-            if (t_q < T) {
-                float* orow = o + ((int64_t)row_base + t_q) * D + h * 64 + ch * 32;
+            for (int ch = 0; ch < 2; ++ch) {
+                float t[32];
+                tmem_ld32(lane_addr + TM_PV + h * 64 + ch * 32, t);
+                if (t_q < hoist_rows) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(orow + i) = make_float4((oacc[ch * 32 + i] + t[i]) * inv, (oacc[ch * 32 + i + 1] + t[i + 1]) * inv,
-                                                                       (oacc[ch * 32 + i + 2] + t[i + 2]) * inv, (oacc[ch * 32 + i + 3] + t[i + 3]) * inv);
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(st + h * 64 + ch * 32 + i) = make_float4(oacc[ch * 32 + i] + t[i], oacc[ch * 32 + i + 1] + t[i + 1],
+                                                                                            oacc[ch * 32 + i + 2] + t[i + 2], oacc[ch * 32 + i + 3] + t[i + 3]);
+                }
             }
+            if (t_q < hoist_rows) {
+                if (h == 0) st[128] = m_used;
+                st[129 + h] = l_part;
+            }
+        } else {
+            // total row sum = the two halves' partial sums
+            named_bar_sync(1, ROW_THREADS);
+            xm[h * 128 + row] = l_part;
+            named_bar_sync(1, ROW_THREADS);
+            const float l_run = l_part + xm[(h ^ 1) * 128 + row];
+            const float inv = 1.0f / l_run;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float t[32];
+                tmem_ld32(lane_addr + TM_PV + h * 64 + ch * 32, t);
+                if (t_q < T) {
+                    float* orow = o + ((int64_t)row_base + t_q) * D + h * 64 + ch * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(orow + i) = make_float4((oacc[ch * 32 + i] + t[i]) * inv, (oacc[ch * 32 + i + 1] + t[i + 1]) * inv,
+                                                                           (oacc[ch * 32 + i + 2] + t[i + 2]) * inv, (oacc[ch * 32 + i + 3] + t[i + 3]) * inv);
+                }
+            }
+            if (lse && h == 0 && t_q < T) lse[(int64_t)row_base + t_q] = m_used * LN2 + logf(l_run);
         }
-        if (lse && h == 0 && t_q < T) lse[(int64_t)row_base + t_q] = m_used * LN2 + logf(l_run);
     }
     tc_fence_before();
     __syncthreads();
@@ -1104,11 +1153,24 @@ using namespace dip;
 
 extern "C" {
 
+size_t dip_attn_fwd_tc_state_bytes(int B, int prefix_keys) {
+    if (B <= 0 || prefix_keys < tcattn::BM) return 0;
+    return (size_t)B * (size_t)(prefix_keys / tcattn::BM * tcattn::BM) * tcattn::STATE_W * sizeof(float);
+}
+
 int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo, const uint8_t* key_mask, int64_t mask_stride, int B, int T,
-                    int q_begin, dip_stream_t stream) {
-    DIP_REQUIRE(o && qkv_hi && qkv_lo && B > 0 && T > 0, "dip_attn_fwd_tc: null/empty argument");
+                    int q_begin, float* prefix_state, int prefix_keys, int prefix_mode, dip_stream_t stream) {
+    DIP_REQUIRE(qkv_hi && qkv_lo && B > 0 && T > 0, "dip_attn_fwd_tc: null/empty argument");
     DIP_REQUIRE(q_begin >= 0 && q_begin < T, "dip_attn_fwd_tc: q_begin %d outside [0, T)", q_begin);
     DIP_REQUIRE(B <= 65535, "dip_attn_fwd_tc: B too large for one launch");
+    DIP_REQUIRE(prefix_mode >= 0 && prefix_mode <= 2, "dip_attn_fwd_tc: prefix_mode must be 0, 1 (save) or 2 (use)");
+    const int hoist_rows = prefix_keys / tcattn::BM * tcattn::BM, j_split = prefix_keys / tcattn::BN;
+    if (prefix_mode != 0) {
+        DIP_REQUIRE(prefix_state && q_begin == 0 && prefix_keys > 0 && prefix_keys < T && hoist_rows > 0 && j_split > 0 && j_split < cdiv(T, tcattn::BN),
+                    "dip_attn_fwd_tc: key-prefix hoisting needs a state buffer, q_begin == 0 and 128 <= prefix_keys < T");
+        DIP_REQUIRE((reinterpret_cast<uintptr_t>(prefix_state) & 15) == 0, "dip_attn_fwd_tc: prefix_state must be 16-byte aligned");
+    }
+    DIP_REQUIRE(prefix_mode == 1 || o, "dip_attn_fwd_tc: null output");
     static bool attr = false;
     if (!attr) {
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::FWD_SMEM));
@@ -1119,9 +1181,11 @@ int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo
     DIP_TRY(make_tmap_bf16_3d(&lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&hi64, qkv_hi, B, T, 3 * D, 3 * D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
-    dim3 grid(cdiv(T - q_begin, tcattn::BM), B);
+    dim3 grid(prefix_mode == 1 ? hoist_rows / tcattn::BM : cdiv(T - q_begin, tcattn::BM), B);
     DIP_PROF(DIP_PROF_ATTN_FWD, stream);
-    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::FWD_THREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T, q_begin);
+    tcattn::attn_fwd_tc_kernel<<<grid, tcattn::FWD_THREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(
+        hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T, q_begin, prefix_mode == 2 ? prefix_state : nullptr,
+        prefix_mode == 1 ? prefix_state : nullptr, j_split, hoist_rows);
     DIP_LAUNCHED();
     return 0;
 }

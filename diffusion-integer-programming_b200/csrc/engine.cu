@@ -158,6 +158,7 @@ struct Workspace {
     float *p_full, *dz, *viol, *obj, *mean_buf;
     void* ds;             // dS^T planes of one attention backward (tensor-core mode), see dip_attn_bwd_tc
     size_t ds_bytes;
+    float* fstate;        // softmax state of decoder layer 0's instance-token queries after the instance keys (dip_attn_fwd_tc, key-prefix hoisting)
     size_t bytes;
 };
 
@@ -213,6 +214,7 @@ static Workspace carve(const dip_engine* e, int B, void* base) {
         w.ds_bytes = need > w.ds_bytes ? need : w.ds_bytes;
     }
     w.ds = c.take<uint8_t>(w.ds_bytes);
+    w.fstate = c.take<float>(dip_attn_fwd_tc_state_bytes(B, (int)L) / sizeof(float));
     w.bytes = (c.off + 255) & ~(size_t)255;
     return w;
 }
@@ -265,7 +267,7 @@ static void window(dip_gemm_args& g, int B, int T, int w) {
 // out-projection and the MLP; keys and values still cover the whole sequence.
 static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float* xout, float* h, float* h2, void* ln_hi, void* ln_lo, float* qkv,
                      void* qkv_hi, void* qkv_lo, float* ao, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2, float* u, const uint8_t* mask,
-                     int64_t mask_stride, int B, int T, int win, int in_begin, dip_stream_t st) {
+                     int64_t mask_stride, int B, int T, int win, int in_begin, float* fstate, int prefix_keys, dip_stream_t st) {
     const int64_t R = (int64_t)B * T;
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     DIP_REQUIRE(R < (1ll << 31), "wave too large: B*T = %lld rows", (long long)R);
@@ -282,8 +284,18 @@ static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float
     } else {
         DIP_TRY(linear(mode, g, w.in_w, &xin, w.ln1_w, w.ln1_b, mean1, rstd1, h, st));
     }
-    if (tc) DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, mask_stride, B, T, win, st));
-    else DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, mask_stride, B, T, st));
+    if (tc) {
+        // prefix_keys > 0 (decoder layer 0, not also the last layer): the first prefix_keys tokens are wave constants.  in_begin > 0 means
+        // their planes -- and the softmax state of their queries against them -- are already in place: resume; otherwise compute in full
+        // and save the state for the following calls of the wave.
+        const bool hoist = prefix_keys >= 128 && win == 0 && fstate != nullptr;
+        DIP_TRY(dip_attn_fwd_tc(ao, lse, qkv_hi, qkv_lo, mask, mask_stride, B, T, win, hoist ? fstate : nullptr, hoist ? prefix_keys : 0,
+                                hoist && in_begin > 0 ? 2 : 0, st));
+        if (hoist && in_begin == 0)
+            DIP_TRY(dip_attn_fwd_tc(nullptr, nullptr, qkv_hi, qkv_lo, mask, mask_stride, B, T, 0, fstate, prefix_keys, 1, st));
+    } else {
+        DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, mask_stride, B, T, st));
+    }
     // x_mid = x + attn . W_out^T + b_out
     g = gemm(ao, D, xmid, D, R, D, D, w.out_b, DIP_ACT_NONE);
     g.res = xin;
@@ -429,7 +441,7 @@ static int denoise(dip_engine* e, const Workspace& w, const float* x, int B, flo
     DIP_TRY(linear(e->mode, g, e->w2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     for (int l = 0; l < e->n_den; ++l)
         DIP_TRY(block_fwd(e->mode, e->den[l], plain_rows(w.hd, T1), w.hd, w.hd, w.tmp, w.tmp2, w.ln_hi, w.ln_lo, w.qkv1, w.qkv1_hi, w.qkv1_lo, w.ao1, nullptr, nullptr,
-                          nullptr, nullptr, nullptr, nullptr, v.mask_den, v.mask_den_stride, B, T1, 0, 0, st));
+                          nullptr, nullptr, nullptr, nullptr, v.mask_den, v.mask_den_stride, B, T1, 0, 0, nullptr, 0, st));
     return 0;
 }
 
@@ -443,7 +455,8 @@ static int decode(dip_engine* e, const Workspace& w, const float* x, int B, dip_
         // layer 0: the mip tokens' planes are in place after the first decode into this workspace
         const bool hoisted = l == 0 && e->mode == DIP_PRECISION_TC_SPLIT && e->dec0_ws == (const void*)s.qkv_hi && e->dec0_B == B;
         DIP_TRY(block_fwd(e->mode, e->dec[l], xin, s.xmid, s.xout, w.h, w.h2, w.ln_hi, w.ln_lo, s.qkv, s.qkv_hi, s.qkv_lo, s.ao, s.lse, s.mean1, s.rstd1, s.mean2,
-                          s.rstd2, s.u, v.mask_dec, v.mask_dec_stride, B, T2, l == e->n_dec - 1 ? L : 0, hoisted ? L : 0, st));
+                          s.rstd2, s.u, v.mask_dec, v.mask_dec_stride, B, T2, l == e->n_dec - 1 ? L : 0, hoisted ? L : 0, l == 0 ? w.fstate : nullptr,
+                          l == 0 ? L : 0, st));
         if (l == 0 && e->mode == DIP_PRECISION_TC_SPLIT) { e->dec0_ws = s.qkv_hi; e->dec0_B = B; }
     }
     DIP_TRY(dip_decoder_head_fwd(w.p_full, w.ls[e->n_dec - 1].xout, B, T2, L, e->proj_w, e->proj_b, v.kpm, v.kpm_stride, st));

@@ -86,7 +86,8 @@ PROTOTYPES = {
     "dip_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp]),
     "dip_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp, i32, i32, vp]),
     "dip_split_bf16": (i32, [vp, vp, vp, i64, vp]),
-    "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "dip_attn_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32, i32, vp]),
+    "dip_attn_fwd_tc_state_bytes": (sz, [i32, i32]),
     "dip_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
     "dip_attn_bwd_tc_ds_bytes": (sz, [i32, i32, i32, i32]),
     "dip_layernorm_split": (i32, [vp, vp, vp, vp, Rows, vp, vp, i64, i32, vp]),

@@ -145,14 +145,21 @@ def split_bf16(x):
     return hi, lo
 
 
-def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None, q_begin=0):
+def attn_fwd_tc(qkv_hi, qkv_lo, B, T, key_mask=None, mask_stride=None, q_begin=0, prefix_keys=0):
     """tcgen05 attention forward on the bf16 (hi, lo) planes of the packed (B*T, 384) qkv.  Rows t < q_begin of
-    every sample are not computed (returned as NaN so that a test reading them fails)."""
+    every sample are not computed (returned as NaN so that a test reading them fails).  prefix_keys > 0: key-prefix hoisting --
+    a "save" launch over the first prefix_keys keys, then the resuming launch (see dip_attn_fwd_tc)."""
     lib = _lib.load()
     o = torch.full((B * T, D), float("nan"), dtype=torch.float32, device=qkv_hi.device)
     lse = torch.full((B * T,), float("nan"), dtype=torch.float32, device=qkv_hi.device)
     km, ms = _mask(key_mask, B, T, mask_stride)
-    check(lib.dip_attn_fwd_tc(ptr(o), ptr(lse), ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, int(q_begin), _stream()))
+    if prefix_keys > 0:
+        nb = lib.dip_attn_fwd_tc_state_bytes(B, int(prefix_keys))
+        state = torch.full((nb // 4,), float("nan"), dtype=torch.float32, device=qkv_hi.device)
+        check(lib.dip_attn_fwd_tc(None, None, ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, 0, ptr(state), int(prefix_keys), 1, _stream()))
+        check(lib.dip_attn_fwd_tc(ptr(o), ptr(lse), ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, 0, ptr(state), int(prefix_keys), 2, _stream()))
+        return o, lse
+    check(lib.dip_attn_fwd_tc(ptr(o), ptr(lse), ptr(qkv_hi), ptr(qkv_lo), ptr(km), ms, B, T, int(q_begin), None, 0, 0, _stream()))
     return o, lse
 
 

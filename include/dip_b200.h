@@ -173,7 +173,15 @@ int dip_split_bf16(void* hi, void* lo, const float* x, int64_t n, dip_stream_t s
 /* q_begin: only the queries t >= q_begin of every sample are computed (o / lse rows below are not written) -- the last
  * decoder layer needs just the L tokens model/decoder.py:45 keeps. */
 int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo, const uint8_t* key_mask,
-                    int64_t mask_stride, int B, int T, int q_begin, dip_stream_t stream);
+                    int64_t mask_stride, int B, int T, int q_begin, float* prefix_state, int prefix_keys, int prefix_mode,
+                    dip_stream_t stream);
+/* Key-prefix hoisting: when the first `prefix_keys` tokens of every sample do not change between calls (the instance tokens of the
+ * decoder's [mip ; x] sequence, model/decoder.py:40: constants of a wave), a query that is itself one of them sees the same scores
+ * against them every time.  prefix_mode 1 ("save", once per wave): run those key tiles for the queries below
+ * floor(prefix_keys/128)*128 and keep the softmax state (running maximum, running sums, un-normalised P.V) in `prefix_state`
+ * (dip_attn_fwd_tc_state_bytes bytes; o / lse are not written).  prefix_mode 2 ("use"): those queries resume from the state and stream
+ * only the remaining keys -- bit-identical to prefix_mode 0, a quarter less work for the layer.  q_begin must be 0. */
+size_t dip_attn_fwd_tc_state_bytes(int B, int prefix_keys);
 
 /* Same contract as dip_attn_bwd on split planes; do_hi/do_lo: planes of d_o (B*T,128).  Two tcgen05
  * kernels (key-stationary dK/dV, query-stationary dQ); deterministic. */

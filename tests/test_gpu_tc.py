@@ -268,3 +268,22 @@ def test_layernorm_split_token_window(cuda):
     full = lambda t: t.view(B, T, -1)[:, tb:].reshape(B * (T - tb), -1)
     assert torch.equal(hw, full(hi)) and torch.equal(lw, full(lo))
     assert torch.equal(mw.view(B, T)[:, tb:], mean.view(B, T)[:, tb:]) and torch.equal(rw.view(B, T)[:, tb:], rstd.view(B, T)[:, tb:])
+
+
+@pytest.mark.parametrize("B,T,prefix,masked", [(2, 600, 300, True), (1, 4000, 2000, False), (3, 257, 129, True), (2, 1500, 1000, True)])
+def test_attention_fwd_tc_key_prefix_hoisting(cuda, B, T, prefix, masked):
+    """dip_attn_fwd_tc prefix modes: the queries below floor(prefix/128)*128 resume from the softmax state a "save" launch left after
+    the first floor(prefix/64) key tiles; everything must equal the plain launch bit for bit (same operations, same order)."""
+    from dip_b200 import ops
+    qkv = rnd((B * T, 3 * D), T + prefix, 1.3)
+    mask = None
+    if masked:
+        mask = torch.zeros((B, T), dtype=torch.bool)
+        mask[:, prefix - 7:prefix] = True          # padding at the end of the prefix block and of the sequence, like [kpm | kpm]
+        mask[:, T - 7:] = True
+        mask[:, 3] = True
+    hi, lo = ops.split_bf16(qkv.to(cuda))
+    km = None if mask is None else mask.to(cuda)
+    o0, l0 = ops.attn_fwd_tc(hi, lo, B, T, km)
+    o1, l1 = ops.attn_fwd_tc(hi, lo, B, T, km, prefix_keys=prefix)
+    assert torch.equal(o0, o1) and torch.equal(l0, l1)

@@ -1,0 +1,553 @@
+// The row-wise half of a ResidualAttentionBlock as ONE kernel (model/modules.py:293-296 after the attention itself):
+//
+//     forward :  x_mid = x_in + attn . W_out^T + b_out ;  u = LN2(x_mid) . W_fc^T + b_fc ;  x_out = x_mid + QuickGELU(u) . W_proj^T + b_proj
+//     backward:  dU = (dx_out . W_proj) * gelu'(u) ;  dH = dU . W_fc ;  dx_mid = dx_out + LN2'(dH) ;  d_attn = dx_mid . W_out   (input gradients only)
+//
+// As three separate Linear launches (+ LayerNorm kernels in the backward) every stage reads a 512-byte row and writes one: 9 row passes
+// forward and 12 backward, all HBM-bound (32 FLOP per byte).  With D = 128 a 128-row tile carries whole feature vectors, so the chain can
+// stay on chip: here a tile makes ONE trip -- 2 rows in, the rows the backward pass needs (x_mid, u) and x_out out.
+//
+// Layout of the work (one persistent CTA per SM, 18 warps):
+//   * the three weights (bf16 hi/lo planes, 64 KB each) are resident in shared memory (TMA, SWIZZLE_128B) -- that is 192 of the 227 KB, so
+//     the A operands cannot be staged there: they live in TENSOR MEMORY (tcgen05.mma with the A operand in TMEM: lane = row, a 32-bit column
+//     = a bf16 pair), written by the same threads that own the rows;
+//   * two independent GROUPS of 8 row warps, each with its own tile, TMEM slot (A planes 128 columns + accumulator 128) and issuer warp:
+//     while one group waits for memory or for the tensor pipe the other computes.  Row thread = (row, column half);
+//   * every stage walks its 64 columns in four 16-column CHUNKS inside a rolled loop: accumulator chunk out of TMEM, bias / residual /
+//     activation in registers, next A operand chunk back into TMEM.  The first version unrolled whole rows (64 values per thread): 170 KB of
+//     straight-line code per kernel, 54 % of the warp stalls were instruction fetch (ncu `stall_no_inst`; the instruction cache holds
+//     32 KB).  Values a later pass of the same stage needs again (x_mid for the LayerNorm statistics, dH . gamma and x_hat for LayerNorm')
+//     are parked in TMEM columns that are free at that moment instead of in registers;
+//   * A-plane layout: k-step j (16 features) has its hi words in columns 16j .. 16j+7 and its lo words in 16j+8 .. 16j+15, so the fp32
+//     chunk a thread parks in the A region is replaced IN PLACE by the planes made from it;
+//   * global rows move through a 2 KB per-warp staging block (XOR-swizzled 32 x 16 fp32 transposes): a warp access is 8 rows x 64
+//     contiguous bytes (whole sectors) although a thread owns a whole row; the loads of the next chunk are in flight while the current one
+//     is worked on, and the first chunk of a stage is requested before the wait for the product it is combined with.
+// Numerics: "bf16x2 split" like gemm_tc.cu (tc_common.cuh), every product 3 passes; LayerNorm in fp32 (two passes over the row, rsqrt +
+// one Newton step as in the GEMM loader).
+#include <string.h>
+#include "tc_common.cuh"
+
+namespace dip {
+namespace tcchain {
+
+using namespace tc;
+
+constexpr int GROUPS = 2, GROUP_WARPS = 8, GROUP_THREADS = GROUP_WARPS * 32, ROW_WARPS = GROUPS * GROUP_WARPS, NT = (ROW_WARPS + GROUPS) * 32;
+constexpr uint32_t W_BLOCK = 16384, W_PLANE = 32768, W_ONE = 65536;          // [plane][k-block][128 rows][64] bf16
+constexpr uint32_t OFF_STG = 3 * W_ONE, STG_WARP = 2048, OFF_PAR = OFF_STG + ROW_WARPS * STG_WARP, OFF_BAR = OFF_PAR + 5 * 512;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+static_assert(SMEM_BYTES <= 232448, "chain kernel shared memory");
+constexpr uint32_t TM_A = 0, TM_ACC = 128, TM_SLOT = 256;                     // per slot: A planes (k-step j: hi 16j, lo 16j+8), accumulator 128
+constexpr uint32_t IDESC = instr_desc(128, 128, 0, 0);
+enum { B_W = 0, B_AFULL = 1, B_CFULL = 3 };
+enum { PAR_B0 = 0, PAR_B1 = 128, PAR_B2 = 256, PAR_G = 384, PAR_BETA = 512 };  // per-column parameter vectors in shared memory (float offsets)
+
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1u ? n : (__umulhi(n, mul) >> shr); }
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1ull << lg) < d) ++lg;
+        const int p = 31 + lg;
+        f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+        f.shr = (uint32_t)(p - 32);
+    }
+    return f;
+}
+
+struct Params {
+    int n_live, n_tiles;                 // live rows (tokens t >= win of every sample) and 128-row tiles over them
+    FastDiv live_T, full_T;              // T - win, T
+    uint32_t T, win;
+    // forward: a = attn, r_* = x_in (two-source);  backward: a = dx_out, u_in = u, xm_in = x_mid
+    const float* a;
+    const float *r_shared, *r_batch; uint32_t r_split; int64_t r_sstride;
+    const float *b0, *b1, *b2;           // biases of the three Linears (forward)
+    const float *ln_g, *ln_b;
+    float *xmid, *mean2, *rstd2, *u, *xout;          // forward outputs (stats / u nullable)
+    const float *u_in, *xm_in, *mean_in, *rstd_in;   // backward inputs
+    float *dxm, *dao; void *do_hi, *do_lo;           // backward outputs (planes nullable)
+};
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float z) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+
+// live row index -> global row (b*T + t)
+__device__ __forceinline__ uint32_t grow(const Params& P, uint32_t i) {
+    const uint32_t b = P.live_T.div(i);
+    return b * P.T + P.win + (i - b * P.live_T.d);
+}
+__device__ __forceinline__ const float* rsrc_row(const Params& P, uint32_t g) {
+    if (P.r_split == 0) return P.r_batch + (size_t)g * D;
+    const uint32_t b = P.full_T.div(g), t = g - b * P.T;
+    return t < P.r_split ? P.r_shared + (int64_t)b * P.r_sstride + (size_t)t * D : P.r_batch + ((size_t)b * (P.T - P.r_split) + (t - P.r_split)) * D;
+}
+
+// ---- staged row I/O.  A warp moves a 32-row x 16-column fp32 block (one chunk of its 32 rows) between global memory and the
+// "thread = row" register layout through its private 2 KB shared-memory block.  Global side: lane = (row & 7, 16-byte piece), four rows
+// 8 apart per lane -> 8 rows x 64 contiguous bytes per instruction.  Both sides are bank-conflict free with the XOR below. -------------
+struct Lane {
+    int lane;
+    uint32_t so_own, sx_own;      // owner side: float offset of the row, XOR of the 16-byte piece index
+    uint32_t so_glb;              // global side: float offset of (row = lane >> 2, swizzled piece lane & 3); rows 8 apart are +128 floats
+    __device__ __forceinline__ Lane(int l) : lane(l) {
+        so_own = (uint32_t)l * 16u; sx_own = (uint32_t)(l >> 1) & 3u;
+        const uint32_t r8 = (uint32_t)l >> 2, c4 = (uint32_t)l & 3u;
+        so_glb = r8 * 16u + 4u * (c4 ^ ((r8 >> 1) & 3u));
+    }
+};
+__device__ __forceinline__ void to_owner(float (&v)[16], const float4 (&t)[4], float* stg, const Lane& L) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + L.so_glb + i * 128) = t[i];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(stg + L.so_own + 4u * ((uint32_t)k ^ L.sx_own));
+        v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void from_owner(float4 (&t)[4], const float (&v)[16], float* stg, const Lane& L) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(stg + L.so_own + 4u * ((uint32_t)k ^ L.sx_own)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const float4*>(stg + L.so_glb + i * 128);
+    __syncwarp();
+}
+// the four rows a lane moves: element offsets of their first column (+ this lane's 16-byte piece), validity bits
+struct TileRows {
+    uint32_t off[4];
+    uint32_t valid;
+};
+__device__ __forceinline__ void ld_issue(float4 (&t)[4], const float* base, const TileRows& R, int col) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const float4*>(base + R.off[i] + col);
+}
+__device__ __forceinline__ void st_rows(float* base, const TileRows& R, int col, const float4 (&t)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (R.valid & (1u << i)) *reinterpret_cast<float4*>(base + R.off[i] + col) = t[i];
+}
+__device__ __forceinline__ void store_chunk(float* base, const TileRows& R, int col, const float (&v)[16], float* stg, const Lane& L) {
+    float4 t[4];
+    from_owner(t, v, stg, L);
+    st_rows(base, R, col, t);
+}
+
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&x)[16]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(x[i]);
+    tmem_st16(taddr, w);
+}
+// one fp32 chunk (16 features = one k-step) -> its packed bf16 hi words (8 columns) and lo words (8 columns) in the A region
+__device__ __forceinline__ void put_chunk(uint32_t taddr, const float (&x)[16]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) split2(x[2 * c], x[2 * c + 1], w[c], w[8 + c]);
+    tmem_st16(taddr, w);
+}
+
+// 24 MMAs of one product: A (TMEM planes of the slot) . W^T (resident weight w), fp32 accumulate into the slot's accumulator
+__device__ __forceinline__ void issue_product(uint32_t tmem_slot_addr, uint64_t dW, int w) {
+    const uint64_t dw = desc_adv(dW, w * W_ONE);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass)                                 // A hi, hi, lo x W hi, lo, hi
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                tc_mma_ts(tmem_slot_addr + TM_ACC, tmem_slot_addr + TM_A + (kb * 4 + ks) * 16 + (pass == 2 ? 8 : 0),
+                          desc_adv(dw, (pass == 1 ? W_PLANE : 0) + kb * W_BLOCK + ks * 32), IDESC, acc);
+                acc = 1;
+            }
+}
+
+// BWD = false: forward chain (weights out_w, fc_w, proj_w);  BWD = true: input-gradient chain (weights proj_wT, fc_wT, out_wT)
+template <bool BWD>
+__global__ void __launch_bounds__(NT, 1)
+chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_constant__ CUtensorMap tm_w0_lo, const __grid_constant__ CUtensorMap tm_w1_hi,
+                const __grid_constant__ CUtensorMap tm_w1_lo, const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+                const Params P) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    if ((smem_u32(sm) & 1023u) != 0u) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    float* par = reinterpret_cast<float*>(sm + OFF_PAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[B_W], 1);
+        for (int s = 0; s < GROUPS; ++s) { mbar_init(&bars[B_AFULL + s], GROUP_THREADS); mbar_init(&bars[B_CFULL + s], 1); }
+        mbar_fence_init();
+    }
+    if (warp == ROW_WARPS) tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < 5 * 128; i += NT) {
+        const float* src = i < PAR_B1 ? P.b0 : i < PAR_B2 ? P.b1 : i < PAR_G ? P.b2 : i < PAR_BETA ? P.ln_g : P.ln_b;
+        par[i] = src ? src[i & 127] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // tiles of this CTA: blockIdx.x + k * gridDim.x
+
+    if (warp >= ROW_WARPS) {
+        // ------------------------------------------------------------------ issuer of group g: weights (once), then the three products of every tile
+        const int g = warp - ROW_WARPS;
+        if (g == 0 && lane == 0) {
+            mbar_expect_tx(&bars[B_W], 3 * W_ONE);
+            const CUtensorMap* maps[6] = {&tm_w0_hi, &tm_w0_lo, &tm_w1_hi, &tm_w1_lo, &tm_w2_hi, &tm_w2_lo};
+            for (int w = 0; w < 3; ++w)
+                for (int pl = 0; pl < 2; ++pl)
+                    for (int kb = 0; kb < 2; ++kb) tma_load_2d(sm + w * W_ONE + pl * W_PLANE + kb * W_BLOCK, maps[2 * w + pl], &bars[B_W], kb * 64, 0);
+        }
+        __syncwarp();
+        const uint64_t dW = smem_desc(smem_u32(sm), 16, 1024);
+        mbar_wait(&bars[B_W], 0);
+        uint32_t ph = 0;
+        for (int k = g; k < n_my; k += GROUPS)
+            for (int w = 0; w < 3; ++w) {
+                mbar_wait(&bars[B_AFULL + g], ph & 1);
+                ph++;
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_product(tmem + g * TM_SLOT, dW, w);
+                    tc_commit(&bars[B_CFULL + g]);
+                }
+                __syncwarp();
+            }
+    } else {
+        // ------------------------------------------------------------------ row warps: thread = (row, column half) of its group's tile
+        const int g = warp >> 3, wg = warp & 7, q = wg & 3, h = wg >> 2;
+        const Lane L(lane);
+        float* stg = reinterpret_cast<float*>(sm + OFF_STG + warp * STG_WARP);
+        float* stg_partner = reinterpret_cast<float*>(sm + OFF_STG + (warp ^ 4) * STG_WARP);      // same rows, other column half
+        const uint32_t slot = tmem + ((uint32_t)(q * 32) << 16) + g * TM_SLOT;
+        const int c0 = h * 64;                                                                     // this thread's columns: c0 .. c0 + 63
+        const int cl = c0 + 4 * (lane & 3);                                                        // + its 16-byte piece on the global side
+        const uint32_t a_reg = slot + TM_A + c0, acc_reg = slot + TM_ACC + c0;                      // chunk ch at + 16 ch in both regions
+        const int bar_id = 1 + g;
+        uint32_t cph = 0;                                                                          // CFULL phase
+        for (int k = g; k < n_my; k += GROUPS) {
+            const uint32_t live0 = (uint32_t)(blockIdx.x + k * gridDim.x) * 128u + q * 32;
+            TileRows R;
+            R.valid = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t li = live0 + 8 * i + (lane >> 2);
+                if (li < (uint32_t)P.n_live) R.valid |= 1u << i;
+                R.off[i] = grow(P, min(li, (uint32_t)P.n_live - 1u)) * (uint32_t)D;
+            }
+            const bool own_valid = live0 + lane < (uint32_t)P.n_live;
+            const uint32_t g_own = grow(P, min(live0 + lane, (uint32_t)P.n_live - 1u));
+            float4 nx[4];
+            // ---------------- stage 0: the first A operand (forward: attention output rows, backward: dx_out rows)
+            ld_issue(nx, P.a, R, cl);
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[16];
+                to_owner(v, nx, stg, L);
+                if (ch < 3) ld_issue(nx, P.a, R, cl + 16 * (ch + 1));
+                put_chunk(a_reg + 16 * ch, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[B_AFULL + g]);
+            // ---------------- stage 1
+            if (!BWD) {
+                // x_mid = attn . W_out^T + b_out + x_in ; LayerNorm 2 -> A
+                const float* rp[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rp[i] = rsrc_row(P, R.off[i] / (uint32_t)D) + cl;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nx[i] = *reinterpret_cast<const float4*>(rp[i]);
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+                float sum = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    to_owner(x, nx, stg, L);
+                    if (ch < 3) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) nx[i] = *reinterpret_cast<const float4*>(rp[i] + 16 * (ch + 1));
+                    }
+                    float acc[16];
+                    tmem_ld16(acc_reg + 16 * ch, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        x[i] += acc[i] + par[PAR_B0 + c0 + 16 * ch + i];
+                        sum += x[i];
+                    }
+                    tmem_st16f(acc_reg + 16 * ch, x);                    // parked for the two LayerNorm passes
+                    store_chunk(P.xmid, R, cl + 16 * ch, x, stg, L);
+                }
+                tmem_st_wait();
+                stg[lane] = sum;
+                named_bar_sync(bar_id, GROUP_THREADS);
+                const float mu = (sum + stg_partner[lane]) * (1.0f / D);
+                float sq = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    tmem_ld16(acc_reg + 16 * ch, x);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { const float d = x[i] - mu; sq += d * d; }
+                }
+                stg[32 + lane] = sq;
+                named_bar_sync(bar_id, GROUP_THREADS);
+                const float var = (sq + stg_partner[32 + lane]) * (1.0f / D);
+                float rs = rsqrtf(var + 1e-5f);
+                rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
+                if (P.mean2 && h == 0 && own_valid) { P.mean2[g_own] = mu; P.rstd2[g_own] = rs; }
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    tmem_ld16(acc_reg + 16 * ch, x);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] = (x[i] - mu) * rs * par[PAR_G + c0 + 16 * ch + i] + par[PAR_BETA + c0 + 16 * ch + i];
+                    put_chunk(a_reg + 16 * ch, x);
+                }
+            } else {
+                // dU = (dx_out . W_proj) * gelu'(u) -> A
+                ld_issue(nx, P.u_in, R, cl);
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float uu[16];
+                    to_owner(uu, nx, stg, L);
+                    if (ch < 3) ld_issue(nx, P.u_in, R, cl + 16 * (ch + 1));
+                    float acc[16];
+                    tmem_ld16(acc_reg + 16 * ch, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float sg = fast_sigmoid(1.702f * uu[i]);
+                        acc[i] *= sg * (1.0f + 1.702f * uu[i] * (1.0f - sg));
+                    }
+                    put_chunk(a_reg + 16 * ch, acc);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[B_AFULL + g]);
+            // ---------------- stage 2
+            if (!BWD) {
+                // u = LN2(x_mid) . W_fc^T + b_fc (saved) ; QuickGELU -> A
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    tmem_ld16(acc_reg + 16 * ch, x);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] += par[PAR_B1 + c0 + 16 * ch + i];
+                    if (P.u) store_chunk(P.u, R, cl + 16 * ch, x, stg, L);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] *= fast_sigmoid(1.702f * x[i]);
+                    put_chunk(a_reg + 16 * ch, x);
+                }
+            } else {
+                // dx_mid = dx_out + LN2'(dH):  gg = dH * gamma ;  dx = rstd * (gg - mean(gg) - xhat * mean(gg * xhat))
+                ld_issue(nx, P.xm_in, R, cl);
+                const float mu = P.mean_in[g_own], rs = P.rstd_in[g_own];
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float xh[16];
+                    to_owner(xh, nx, stg, L);
+                    if (ch < 3) ld_issue(nx, P.xm_in, R, cl + 16 * (ch + 1));
+                    float gg[16];
+                    tmem_ld16(acc_reg + 16 * ch, gg);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        xh[i] = (xh[i] - mu) * rs;
+                        gg[i] *= par[PAR_G + c0 + 16 * ch + i];
+                        s1 += gg[i];
+                        s2 += gg[i] * xh[i];
+                    }
+                    tmem_st16f(acc_reg + 16 * ch, gg);                   // both parked for the second pass: gg in place, xhat in the (free) A region
+                    tmem_st16f(a_reg + 16 * ch, xh);
+                }
+                tmem_st_wait();
+                ld_issue(nx, P.a, R, cl);                                // + dx_out
+                stg[lane] = s1;
+                stg[32 + lane] = s2;
+                named_bar_sync(bar_id, GROUP_THREADS);
+                const float m1 = (s1 + stg_partner[lane]) * (1.0f / D);
+                const float m2 = (s2 + stg_partner[32 + lane]) * (1.0f / D);
+                named_bar_sync(bar_id, GROUP_THREADS);                   // the staging blocks go back to row I/O
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    to_owner(x, nx, stg, L);
+                    if (ch < 3) ld_issue(nx, P.a, R, cl + 16 * (ch + 1));
+                    float gg[16], xh[16];
+                    tmem_ld16(acc_reg + 16 * ch, gg);
+                    tmem_ld16(a_reg + 16 * ch, xh);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] += rs * (gg[i] - m1 - xh[i] * m2);
+                    store_chunk(P.dxm, R, cl + 16 * ch, x, stg, L);
+                    put_chunk(a_reg + 16 * ch, x);                        // replaces the parked xhat chunk
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[B_AFULL + g]);
+            // ---------------- stage 3
+            if (!BWD) {
+                // x_out = x_mid + QuickGELU(u) . W_proj^T + b_proj   (x_mid re-read: this thread wrote it a moment ago, it is L2-resident)
+                ld_issue(nx, P.xmid, R, cl);
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    to_owner(x, nx, stg, L);
+                    if (ch < 3) ld_issue(nx, P.xmid, R, cl + 16 * (ch + 1));
+                    float acc[16];
+                    tmem_ld16(acc_reg + 16 * ch, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] += acc[i] + par[PAR_B2 + c0 + 16 * ch + i];
+                    store_chunk(P.xout, R, cl + 16 * ch, x, stg, L);
+                }
+            } else {
+                // d_attn = dx_mid . W_out (+ its bf16 planes for the attention backward)
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    tmem_ld16(acc_reg + 16 * ch, x);
+                    store_chunk(P.dao, R, cl + 16 * ch, x, stg, L);
+                    if (P.do_hi) {
+                        // the chunk's hi words (32 bytes per row) and lo words through the same transpose: pieces 0-1 -> hi plane, 2-3 -> lo plane
+                        float w[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t hi, lo;
+                            split2(x[2 * c], x[2 * c + 1], hi, lo);
+                            w[c] = __uint_as_float(hi); w[8 + c] = __uint_as_float(lo);
+                        }
+                        float4 t[4];
+                        from_owner(t, w, stg, L);
+                        uint16_t* plane = reinterpret_cast<uint16_t*>((lane & 2) ? P.do_lo : P.do_hi);
+                        const int pc = c0 + 16 * ch + 8 * (lane & 1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (R.valid & (1u << i)) *reinterpret_cast<float4*>(plane + R.off[i] + pc) = t[i];
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == ROW_WARPS) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tcchain
+}  // namespace dip
+
+using namespace dip;
+
+static int chain_launch(bool bwd, const tcchain::Params& P, const void* const w_hi[3], const void* const w_lo[3], cudaStream_t st) {
+    CUtensorMap m[6];
+    for (int i = 0; i < 3; ++i) {
+        DIP_TRY(make_tmap_bf16_2d(&m[2 * i], w_hi[i], D, D, D, 128, 64));
+        DIP_TRY(make_tmap_bf16_2d(&m[2 * i + 1], w_lo[i], D, D, D, 128, 64));
+    }
+    static bool attr = false;
+    if (!attr) {
+        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
+        attr = true;
+    }
+    int grid = sm_count();
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    if (bwd) tcchain::chain_tc_kernel<true><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    else tcchain::chain_tc_kernel<false><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    return 0;
+}
+
+static int chain_rows(tcchain::Params& P, int B, int T, int win) {
+    DIP_REQUIRE(B > 0 && T > 0 && win >= 0 && win < T, "dip_block_chain: bad sizes B=%d T=%d win=%d", B, T, win);
+    DIP_REQUIRE((int64_t)B * T * D < (1ll << 32), "dip_block_chain: B*T*128 must stay below 2^32");
+    P.n_live = B * (T - win);
+    P.n_tiles = cdiv(P.n_live, 128);
+    P.live_T = tcchain::make_fastdiv((uint32_t)(T - win));
+    P.full_T = tcchain::make_fastdiv((uint32_t)T);
+    P.T = (uint32_t)T; P.win = (uint32_t)win;
+    return 0;
+}
+
+extern "C" {
+
+int dip_block_chain_fwd_tc(float* xout, float* xmid, float* mean2, float* rstd2, float* u, const float* attn, dip_rows xin, const void* out_w_hi,
+                           const void* out_w_lo, const float* out_b, const float* ln2_g, const float* ln2_b, const void* fc_w_hi, const void* fc_w_lo,
+                           const float* fc_b, const void* proj_w_hi, const void* proj_w_lo, const float* proj_b, int B, int T, int win,
+                           dip_stream_t stream) {
+    DIP_REQUIRE(xout && xmid && attn && xin.batch && out_w_hi && out_w_lo && out_b && ln2_g && ln2_b && fc_w_hi && fc_w_lo && fc_b && proj_w_hi &&
+                    proj_w_lo && proj_b,
+                "dip_block_chain_fwd_tc: null argument");
+    DIP_REQUIRE((mean2 == nullptr) == (rstd2 == nullptr), "dip_block_chain_fwd_tc: mean2 and rstd2 go together");
+    DIP_REQUIRE(xin.split == 0 || (xin.shared && xin.T == T && xin.split < T), "dip_block_chain_fwd_tc: bad residual row source");
+    tcchain::Params P;
+    memset(&P, 0, sizeof(P));
+    DIP_TRY(chain_rows(P, B, T, win));
+    P.a = attn;
+    P.r_shared = xin.shared; P.r_batch = xin.batch; P.r_split = (uint32_t)xin.split; P.r_sstride = xin.shared ? xin.shared_stride : 0;
+    P.b0 = out_b; P.b1 = fc_b; P.b2 = proj_b; P.ln_g = ln2_g; P.ln_b = ln2_b;
+    P.xmid = xmid; P.mean2 = mean2; P.rstd2 = rstd2; P.u = u; P.xout = xout;
+    const void* hi[3] = {out_w_hi, fc_w_hi, proj_w_hi};
+    const void* lo[3] = {out_w_lo, fc_w_lo, proj_w_lo};
+    DIP_PROF(DIP_PROF_GEMM, stream);
+    DIP_TRY(chain_launch(false, P, hi, lo, as_stream(stream)));
+    DIP_LAUNCHED();
+    return 0;
+}
+
+int dip_block_chain_bwd_tc(float* dxmid, float* dattn, void* dattn_hi, void* dattn_lo, const float* dxout, const float* u, const float* xmid,
+                           const float* mean2, const float* rstd2, const float* ln2_g, const void* proj_wT_hi, const void* proj_wT_lo,
+                           const void* fc_wT_hi, const void* fc_wT_lo, const void* out_wT_hi, const void* out_wT_lo, int B, int T, int win,
+                           dip_stream_t stream) {
+    DIP_REQUIRE(dxmid && dattn && dxout && u && xmid && mean2 && rstd2 && ln2_g && proj_wT_hi && proj_wT_lo && fc_wT_hi && fc_wT_lo && out_wT_hi &&
+                    out_wT_lo,
+                "dip_block_chain_bwd_tc: null argument");
+    DIP_REQUIRE((dattn_hi == nullptr) == (dattn_lo == nullptr), "dip_block_chain_bwd_tc: the two planes go together");
+    tcchain::Params P;
+    memset(&P, 0, sizeof(P));
+    DIP_TRY(chain_rows(P, B, T, win));
+    P.a = dxout; P.u_in = u; P.xm_in = xmid; P.mean_in = mean2; P.rstd_in = rstd2; P.ln_g = ln2_g;
+    P.dxm = dxmid; P.dao = dattn; P.do_hi = dattn_hi; P.do_lo = dattn_lo;
+    const void* hi[3] = {proj_wT_hi, fc_wT_hi, out_wT_hi};
+    const void* lo[3] = {proj_wT_lo, fc_wT_lo, out_wT_lo};
+    DIP_PROF(DIP_PROF_GEMM, stream);
+    DIP_TRY(chain_launch(true, P, hi, lo, as_stream(stream)));
+    DIP_LAUNCHED();
+    return 0;
+}
+
+}  // extern "C"

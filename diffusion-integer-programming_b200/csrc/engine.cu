@@ -2,6 +2,7 @@
 // denoiser forward, decoder forward with saved activations, K2 guidance, decoder input-gradient
 // backward, fused DDIM/DDPM update -- model/diffusion.py:594-644 / 429-454 as a fixed sequence of
 // kernel launches on the caller's stream.  No device synchronisation, no allocation in the step.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -227,6 +228,16 @@ static dip_gemm_args gemm(const float* A, int lda, float* C, int ldc, int64_t M,
     return g;
 }
 
+// DIP_NO_CHAIN=1 falls back to one launch per Linear / LayerNorm for the row-wise half of a block (A/B comparisons, bisecting)
+static bool use_chain() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DIP_NO_CHAIN");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static dip_rows plain_rows(const float* p, int T) {
     dip_rows r;
     r.shared = nullptr; r.batch = p; r.T = T; r.split = 0; r.shared_stride = 0;
@@ -296,6 +307,12 @@ static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float
     } else {
         DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, mask_stride, B, T, st));
     }
+    if (tc && use_chain()) {
+        // out-projection + residual, LayerNorm 2, c_fc, QuickGELU, c_proj + residual in one launch (chain_tc.cu)
+        DIP_TRY(dip_block_chain_fwd_tc(xout, xmid, mean2, rstd2, u, ao, xin, w.out_w.hi, w.out_w.lo, w.out_b, w.ln2_w, w.ln2_b, w.fc_w.hi, w.fc_w.lo, w.fc_b,
+                                       w.proj_w.hi, w.proj_w.lo, w.proj_b, B, T, win, st));
+        return 0;
+    }
     // x_mid = x + attn . W_out^T + b_out
     g = gemm(ao, D, xmid, D, R, D, D, w.out_b, DIP_ACT_NONE);
     g.res = xin;
@@ -329,22 +346,28 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     if (!tc) do_begin = 0;
     cudaStream_t cs = as_stream(st);
+    if (tc && use_chain()) {
+        // c_proj^T, gelu', c_fc^T, LayerNorm-2 backward + residual, out-projection^T (+ dO planes) in one launch (chain_tc.cu)
+        DIP_TRY(dip_block_chain_bwd_tc(dxm, dao, do_hi, do_lo, dxout, s.u, s.xmid, s.mean2, s.rstd2, w.ln2_w, w.proj_wT.hi, w.proj_wT.lo, w.fc_wT.hi, w.fc_wT.lo,
+                                       w.out_wT.hi, w.out_wT.lo, B, T, do_begin, st));
+    } else {
     // dU = (dxout . W_proj) * gelu'(u)
-    dip_gemm_args g = gemm(dxout, D, dt1, D, R, D, D, nullptr, DIP_ACT_MUL_QUICKGELU_GRAD);
-    g.aux = s.u;
-    window(g, B, T, do_begin);
-    DIP_TRY(linear(mode, g, w.proj_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
-    // dH2 = dU . W_fc
-    g = gemm(dt1, D, dt2, D, R, D, D, nullptr, DIP_ACT_NONE);
-    window(g, B, T, do_begin);
-    DIP_TRY(linear(mode, g, w.fc_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
-    // dxmid = dxout + LN2'(dH2)
-    DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, do_begin, st));
-    // dAO = dxmid . W_out   (+ bf16 planes for the tensor-core attention backward)
-    g = gemm(dxm, D, dao, D, R, D, D, nullptr, DIP_ACT_NONE);
-    if (tc) { g.split_hi = do_hi; g.split_lo = do_lo; }
-    window(g, B, T, do_begin);
-    DIP_TRY(linear(mode, g, w.out_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        dip_gemm_args g = gemm(dxout, D, dt1, D, R, D, D, nullptr, DIP_ACT_MUL_QUICKGELU_GRAD);
+        g.aux = s.u;
+        window(g, B, T, do_begin);
+        DIP_TRY(linear(mode, g, w.proj_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        // dH2 = dU . W_fc
+        g = gemm(dt1, D, dt2, D, R, D, D, nullptr, DIP_ACT_NONE);
+        window(g, B, T, do_begin);
+        DIP_TRY(linear(mode, g, w.fc_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        // dxmid = dxout + LN2'(dH2)
+        DIP_TRY(dip_layernorm_bwd(dxm, dt2, plain_rows(s.xmid, T), s.mean2, s.rstd2, w.ln2_w, dxout, R, do_begin, st));
+        // dAO = dxmid . W_out   (+ bf16 planes for the tensor-core attention backward)
+        g = gemm(dxm, D, dao, D, R, D, D, nullptr, DIP_ACT_NONE);
+        if (tc) { g.split_hi = do_hi; g.split_lo = do_lo; }
+        window(g, B, T, do_begin);
+        DIP_TRY(linear(mode, g, w.out_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    }
     if (tc) {
         const int q_begin = t_min > do_begin ? t_min : do_begin;
         if (t_min < do_begin) {
@@ -358,7 +381,7 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
         DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, mask_stride, delta, B, T, st));
     }
     // dH1 = dQKV . W_in
-    g = gemm(dqkv, 3 * D, dt1, D, R, D, 3 * D, nullptr, DIP_ACT_NONE);
+    dip_gemm_args g = gemm(dqkv, 3 * D, dt1, D, R, D, 3 * D, nullptr, DIP_ACT_NONE);
     if (tc) window(g, B, T, t_min);
     DIP_TRY(linear(mode, g, w.in_wT, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     // dxin = dxmid + LN1'(dH1)

@@ -94,6 +94,8 @@ PROTOTYPES = {
     "dip_gemm_tc_planes": (i32, [C.POINTER(GemmArgs), vp, vp, vp, vp, vp]),
     "dip_gemm_tc": (i32, [C.POINTER(GemmArgs), vp, vp, C.POINTER(Rows), vp, vp, vp, vp, vp]),
     "dip_time_token": (i32, [vp, i32, i32, f32, vp, vp, vp]),
+    "dip_block_chain_fwd_tc": (i32, [vp, vp, vp, vp, vp, vp, Rows, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "dip_block_chain_bwd_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dip_decoder_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp]),
     "dip_decoder_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "dip_guidance": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i64, vp]),

@@ -387,3 +387,37 @@ def partial_select(xbits, k, seed, instance_id, sample_base=0, first_sample_valu
     check(lib.dip_partial_select(ptr(mask), ptr(vals), ptr(xbits), B, n, int(k), int(seed), int(instance_id), int(sample_base),
                                  1 if first_sample_values else 0, _stream()))
     return vals, mask
+
+
+def block_chain_fwd_tc(attn, xin, w, B, T, win=0, shared=None, split=0, save=True):
+    """dip_block_chain_fwd_tc: attn (B*T,128), xin (B*T,128) or two-source (shared (split,128) + xin (B*(T-split),128)); w: block
+    state_dict keys.  Returns dict(xout, xmid, mean2, rstd2, u); rows below `win` are NaN."""
+    lib = _lib.load()
+    dev = attn.device
+    nan = lambda *sh: torch.full(sh, float("nan"), dtype=torch.float32, device=dev)
+    out = {"xout": nan(B * T, D), "xmid": nan(B * T, D), "mean2": nan(B * T) if save else None, "rstd2": nan(B * T) if save else None,
+           "u": nan(B * T, D) if save else None}
+    planes = {k: split_bf16(_f32(w[k])) for k in ("attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")}
+    r = Rows(ptr(shared), ptr(_f32(xin)), int(T), int(split))
+    check(lib.dip_block_chain_fwd_tc(ptr(out["xout"]), ptr(out["xmid"]), ptr(out["mean2"]), ptr(out["rstd2"]), ptr(out["u"]), ptr(_f32(attn)), r,
+                                     ptr(planes["attn.out_proj.weight"][0]), ptr(planes["attn.out_proj.weight"][1]), ptr(_f32(w["attn.out_proj.bias"])),
+                                     ptr(_f32(w["ln_2.weight"])), ptr(_f32(w["ln_2.bias"])), ptr(planes["mlp.c_fc.weight"][0]), ptr(planes["mlp.c_fc.weight"][1]),
+                                     ptr(_f32(w["mlp.c_fc.bias"])), ptr(planes["mlp.c_proj.weight"][0]), ptr(planes["mlp.c_proj.weight"][1]),
+                                     ptr(_f32(w["mlp.c_proj.bias"])), B, T, int(win), _stream()))
+    return out
+
+
+def block_chain_bwd_tc(dxout, u, xmid, mean2, rstd2, w, B, T, win=0, planes=True):
+    """dip_block_chain_bwd_tc.  Returns dict(dxmid, dattn, hi, lo); rows below `win` are NaN / untouched."""
+    lib = _lib.load()
+    dev = dxout.device
+    out = {"dxmid": torch.full((B * T, D), float("nan"), dtype=torch.float32, device=dev),
+           "dattn": torch.full((B * T, D), float("nan"), dtype=torch.float32, device=dev),
+           "hi": torch.zeros((B * T, D), dtype=torch.bfloat16, device=dev) if planes else None,
+           "lo": torch.zeros((B * T, D), dtype=torch.bfloat16, device=dev) if planes else None}
+    wt = {k: split_bf16(_f32(w[k]).t().contiguous()) for k in ("mlp.c_proj.weight", "mlp.c_fc.weight", "attn.out_proj.weight")}
+    check(lib.dip_block_chain_bwd_tc(ptr(out["dxmid"]), ptr(out["dattn"]), ptr(out["hi"]), ptr(out["lo"]), ptr(_f32(dxout)), ptr(_f32(u)), ptr(_f32(xmid)),
+                                     ptr(_f32(mean2)), ptr(_f32(rstd2)), ptr(_f32(w["ln_2.weight"])), ptr(wt["mlp.c_proj.weight"][0]),
+                                     ptr(wt["mlp.c_proj.weight"][1]), ptr(wt["mlp.c_fc.weight"][0]), ptr(wt["mlp.c_fc.weight"][1]),
+                                     ptr(wt["attn.out_proj.weight"][0]), ptr(wt["attn.out_proj.weight"][1]), B, T, int(win), _stream()))
+    return out

@@ -220,6 +220,25 @@ int dip_gemm_tc_planes(const dip_gemm_args* args, const void* a_hi, const void* 
 int dip_gemm_tc(const dip_gemm_args* args, const void* w_hi, const void* w_lo, const dip_rows* a_rows,
                 const float* ln_gamma, const float* ln_beta, float* ln_mean, float* ln_rstd, dip_stream_t stream);
 
+/* The row-wise half of one ResidualAttentionBlock in ONE launch (model/modules.py:293-296 after the attention):
+ *   x_mid = x_in + attn . W_out^T + b_out ;  u = LN2(x_mid) . W_fc^T + b_fc ;  x_out = x_mid + QuickGELU(u) . W_proj^T + b_proj
+ * on the tokens t >= win of every sample (B samples of T tokens; all buffers (B*T,128), rows outside the window untouched).  The three
+ * weights (bf16 hi/lo planes of the nn.Linear weights, dip_split_bf16) stay resident in shared memory, the intermediate rows in tensor
+ * memory: per row 2 x 512 bytes in, 3 x 512 out instead of 9 row passes of three separate Linears.  x_mid is always written (x_mid may
+ * alias x_in's batch part and x_out: in place); mean2 / rstd2 (LayerNorm-2 statistics) and u (pre-activation) are optional saves for
+ * dip_block_chain_bwd_tc. */
+int dip_block_chain_fwd_tc(float* xout, float* xmid, float* mean2, float* rstd2, float* u, const float* attn, dip_rows xin,
+                           const void* out_w_hi, const void* out_w_lo, const float* out_b, const float* ln2_g, const float* ln2_b,
+                           const void* fc_w_hi, const void* fc_w_lo, const float* fc_b, const void* proj_w_hi, const void* proj_w_lo,
+                           const float* proj_b, int B, int T, int win, dip_stream_t stream);
+/* Its input-gradient mirror (what autograd runs under loss.backward(), model/diffusion.py:633-634, without the weight gradients):
+ *   dU = (dx_out . W_proj) * gelu'(u) ;  dH = dU . W_fc ;  dx_mid = dx_out + LN2'(dH) ;  d_attn = dx_mid . W_out
+ * weights given as the planes of the TRANSPOSED matrices; d_attn also as bf16 planes (nullable) for dip_attn_bwd_tc. */
+int dip_block_chain_bwd_tc(float* dxmid, float* dattn, void* dattn_hi, void* dattn_lo, const float* dxout, const float* u,
+                           const float* xmid, const float* mean2, const float* rstd2, const float* ln2_g,
+                           const void* proj_wT_hi, const void* proj_wT_lo, const void* fc_wT_hi, const void* fc_wT_lo,
+                           const void* out_wT_hi, const void* out_wT_lo, int B, int T, int win, dip_stream_t stream);
+
 /* Row 0 of every sample of the denoiser's first hidden layer: QuickGELU(W1 . temb(t) + b1) with
  * temb the 256-wide sinusoidal embedding of model/diffusion.py:39-74.  out: (B, T, 128), row 0. */
 int dip_time_token(float* out, int B, int T, float t, const float* W1, const float* b1, dip_stream_t stream);

@@ -287,3 +287,62 @@ def test_attention_fwd_tc_key_prefix_hoisting(cuda, B, T, prefix, masked):
     o0, l0 = ops.attn_fwd_tc(hi, lo, B, T, km)
     o1, l1 = ops.attn_fwd_tc(hi, lo, B, T, km, prefix_keys=prefix)
     assert torch.equal(o0, o1) and torch.equal(l0, l1)
+
+
+def _block_w(seed):
+    g = lambda shape, s, scale: rnd(shape, seed * 100 + s, scale)
+    return {"attn.out_proj.weight": g((D, D), 0, 0.1), "attn.out_proj.bias": g((D,), 1, 0.3), "ln_2.weight": 1 + 0.1 * g((D,), 2, 1.0),
+            "ln_2.bias": 0.1 * g((D,), 3, 1.0), "mlp.c_fc.weight": g((D, D), 4, 0.15), "mlp.c_fc.bias": g((D,), 5, 0.3),
+            "mlp.c_proj.weight": g((D, D), 6, 0.1), "mlp.c_proj.bias": g((D,), 7, 0.3)}
+
+
+def _chain_ref(attn, xin, w):
+    """model/modules.py:293-296 after the attention, fp64."""
+    w = {k: v.double() for k, v in w.items()}
+    xmid = xin + attn @ w["attn.out_proj.weight"].t() + w["attn.out_proj.bias"]
+    u = F.layer_norm(xmid, (D,), w["ln_2.weight"], w["ln_2.bias"], 1e-5) @ w["mlp.c_fc.weight"].t() + w["mlp.c_fc.bias"]
+    xout = xmid + (u * torch.sigmoid(1.702 * u)) @ w["mlp.c_proj.weight"].t() + w["mlp.c_proj.bias"]
+    return xmid, u, xout
+
+
+@pytest.mark.parametrize("B,T,win,split", [(1, 128, 0, 0), (2, 100, 0, 0), (3, 257, 100, 0), (2, 1000, 37, 500), (3, 70, 0, 30), (37, 4000, 2000, 2000),
+                                           (10, 4000, 0, 0)])
+def test_block_chain_tc(cuda, B, T, win, split):
+    """chain_tc.cu: the row-wise half of a block in one launch, forward and input-gradient backward, against fp64 torch + autograd;
+    windows (rows t < win untouched), two-source residual rows, more tiles than 2 x SMs, bitwise determinism."""
+    from dip_b200 import ops
+    w = _block_w(T)
+    attn = rnd((B * T, D), T + 1, 1.0)
+    batch = rnd((B, T - split, D), T + 2, 2.0)
+    shared = rnd((max(split, 1), D), T + 3, 2.0)
+    xin = (torch.cat([shared[None, :split].expand(B, -1, -1), batch], dim=1) if split else batch).reshape(B * T, D)
+    a64 = attn.double().requires_grad_(True)
+    x64 = xin.double().requires_grad_(True)
+    xmid, u, xout = _chain_ref(a64, x64, w)
+    wc = {k: v.to(cuda) for k, v in w.items()}
+    fw = ops.block_chain_fwd_tc(attn.to(cuda), batch.to(cuda), wc, B, T, win=win, shared=shared.to(cuda) if split else None, split=split)
+    live = lambda t: t.view(B, T, -1)[:, win:]
+    dead = lambda t: t.view(B, T, -1)[:, :win]
+    for name, ref in (("xmid", xmid), ("u", u), ("xout", xout)):
+        assert rel_l2(live(fw[name]), live(ref.detach())) < 2e-5, (name, rel_l2(live(fw[name]), live(ref.detach())))
+        assert bool(torch.isnan(dead(fw[name])).all())                   # rows below the window are not written
+    xm = xmid.detach()
+    assert rel_l2(live(fw["mean2"]), live(xm.mean(-1))) < 1e-5
+    assert rel_l2(live(fw["rstd2"]), live(1.0 / torch.sqrt(xm.var(-1, unbiased=False) + 1e-5))) < 1e-5
+    fw2 = ops.block_chain_fwd_tc(attn.to(cuda), batch.to(cuda), wc, B, T, win=win, shared=shared.to(cuda) if split else None, split=split)
+    assert torch.equal(live(fw["xout"]), live(fw2["xout"])) and torch.equal(live(fw["u"]), live(fw2["u"]))
+    # without the optional saves
+    fw3 = ops.block_chain_fwd_tc(attn.to(cuda), batch.to(cuda), wc, B, T, win=win, shared=shared.to(cuda) if split else None, split=split, save=False)
+    assert torch.equal(live(fw["xout"]), live(fw3["xout"]))
+    # backward: gradient of sum(xout * dxout) w.r.t. attn (= d_attn) and the x_mid gradient (= d x_in)
+    dxout = rnd((B * T, D), T + 4, 1.0)
+    dxout.view(B, T, D)[:, :win] = 0.0
+    (xout * dxout.double()).sum().backward()
+    nz = lambda t: torch.nan_to_num(t, nan=0.0)
+    bw = ops.block_chain_bwd_tc(dxout.to(cuda), nz(fw["u"]), nz(fw["xmid"]), nz(fw["mean2"]), nz(fw["rstd2"]), wc, B, T, win=win)
+    assert rel_l2(live(bw["dxmid"]), live(x64.grad)) < 3e-5, rel_l2(live(bw["dxmid"]), live(x64.grad))
+    assert rel_l2(live(bw["dattn"]), live(a64.grad)) < 3e-5, rel_l2(live(bw["dattn"]), live(a64.grad))
+    assert rel_l2(live(bw["hi"].float() + bw["lo"].float()), live(bw["dattn"])) < 1e-5
+    assert bool(torch.isnan(dead(bw["dxmid"])).all()) and bool(torch.isnan(dead(bw["dattn"])).all())
+    bw2 = ops.block_chain_bwd_tc(dxout.to(cuda), nz(fw["u"]), nz(fw["xmid"]), nz(fw["mean2"]), nz(fw["rstd2"]), wc, B, T, win=win, planes=False)
+    assert torch.equal(live(bw["dattn"]), live(bw2["dattn"])) and torch.equal(live(bw["dxmid"]), live(bw2["dxmid"]))

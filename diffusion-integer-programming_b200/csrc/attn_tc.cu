@@ -437,6 +437,8 @@ constexpr uint32_t Q_TILE = 32768;
 constexpr uint32_t QOFF_X = 0, QOFF_Y = 2 * ST_PLANE, QOFF_U = 4 * ST_PLANE, QOFF_W = QOFF_U + 2 * Q_TILE, QOFF_BAR = QOFF_W + Q_TILE;      // dK/dV kernel
 constexpr uint32_t QOFF_BITS = QOFF_BAR + 192;
 constexpr uint32_t DQ_SMEM = QOFF_BAR + 256;
+constexpr uint32_t QOFF_LSD = DQ_SMEM, KV_SMEM = QOFF_LSD + 8 * 256;         // dK/dV kernel: [8 row warps][32 lse*log2e | 32 delta] of the tile's queries
+static_assert(KV_SMEM <= SMEM_LIMIT, "dK/dV kernel shared memory");
 static_assert(QOFF_BAR == 229376 && DQ_SMEM <= SMEM_LIMIT, "backward kernels shared memory");
 constexpr uint32_t DOFF_K = 2 * ST_PLANE, DOFF_V = DOFF_K + 3 * Q_TILE;                                                                      // dQ kernel
 static_assert(DOFF_V + 2 * Q_TILE == QOFF_BAR, "dQ kernel shared memory");
@@ -995,13 +997,31 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 ds_pending = false;
             }
         };
-        for (int j = 0; j < n_tiles; ++j) {
-            // lane l fetches lse and delta of query h*32 + l of this tile; broadcast by shuffle below
-            const int cq = q_begin + j * QT + h * 32 + lane;
-            float q_lse2 = 0.f, q_delta = 0.f;
+        // lse and delta of this warp's 32 queries of a tile: fetched one tile ahead by lane = query, parked in a per-warp block of shared
+        // memory and read back as broadcast float4 (8 + 8 loads per tile instead of 64 shuffles, and no load latency inside the tile)
+        float* lsd = reinterpret_cast<float*>(sm + QOFF_LSD) + warp * 64;
+        const float4* lsd4 = reinterpret_cast<const float4*>(lsd);
+        const bool all_rows_ok = __all_sync(0xffffffffu, row_ok);
+        float n_lse2 = 0.f, n_delta = 0.f;
+        {
+            const int cq = q_begin + h * 32 + lane;
             if (cq < T) {
-                q_lse2 = __ldg(lse + (int64_t)row_base + cq) * LOG2E;
-                q_delta = __ldg(delta + (int64_t)row_base + cq);
+                n_lse2 = __ldg(lse + (int64_t)row_base + cq) * LOG2E;
+                n_delta = __ldg(delta + (int64_t)row_base + cq);
+            }
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            __syncwarp();                                           // every lane is done with the previous tile's values
+            lsd[lane] = n_lse2;
+            lsd[32 + lane] = n_delta;
+            __syncwarp();
+            {
+                const int cq = q_begin + (j + 1) * QT + h * 32 + lane;
+                n_lse2 = 0.f; n_delta = 0.f;
+                if (j + 1 < n_tiles && cq < T) {
+                    n_lse2 = __ldg(lse + (int64_t)row_base + cq) * LOG2E;
+                    n_delta = __ldg(delta + (int64_t)row_base + cq);
+                }
             }
             TR(30, j);
             mbar_wait(&bars[E_G1FULL], j & 1);
@@ -1013,11 +1033,24 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 uint32_t ph[16], pl[16];
                 tmem_ld32x2(lane_addr + KTM_G1 + h * 32, pr, lane_addr + KTM_G1 + 64 + h * 32, t);
                 const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
+                if (all_rows_ok && bad == 0u) {
+                    // no masked key in this warp's rows, no query past the end of the sample: nothing to select (every tile but the last,
+                    // every warp without padding keys)
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float l2 = __shfl_sync(0xffffffffu, q_lse2, c);
-                    const bool ok = row_ok && !((bad >> c) & 1u);
-                    pr[c] = ok ? ex2_approx(fmaf(pr[c] + t[c], SC2, -l2)) : 0.f;
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 l = lsd4[c4];
+                        pr[4 * c4] = ex2_approx(fmaf(pr[4 * c4] + t[4 * c4], SC2, -l.x));
+                        pr[4 * c4 + 1] = ex2_approx(fmaf(pr[4 * c4 + 1] + t[4 * c4 + 1], SC2, -l.y));
+                        pr[4 * c4 + 2] = ex2_approx(fmaf(pr[4 * c4 + 2] + t[4 * c4 + 2], SC2, -l.z));
+                        pr[4 * c4 + 3] = ex2_approx(fmaf(pr[4 * c4 + 3] + t[4 * c4 + 3], SC2, -l.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float l2 = lsd[c];
+                        const bool ok = row_ok && !((bad >> c) & 1u);
+                        pr[c] = ok ? ex2_approx(fmaf(pr[c] + t[c], SC2, -l2)) : 0.f;
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 16; ++c) split2(pr[2 * c], pr[2 * c + 1], ph[c], pl[c]);
@@ -1037,11 +1070,14 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 float g2[32], t[32];
                 tmem_ld32x2(lane_addr + KTM_G2 + h * 32, g2, lane_addr + KTM_G2 + 64 + h * 32, t);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float dl0 = __shfl_sync(0xffffffffu, q_delta, 2 * c), dl1 = __shfl_sync(0xffffffffu, q_delta, 2 * c + 1);
-                    const float d0 = pr[2 * c] * (g2[2 * c] + t[2 * c] - dl0) * SM_SCALE;
-                    const float d1 = pr[2 * c + 1] * (g2[2 * c + 1] + t[2 * c + 1] - dl1) * SM_SCALE;
-                    split2(d0, d1, dh[c], dl[c]);
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 dq4 = lsd4[8 + c4];
+                    const float d0 = pr[4 * c4] * (g2[4 * c4] + t[4 * c4] - dq4.x) * SM_SCALE;
+                    const float d1 = pr[4 * c4 + 1] * (g2[4 * c4 + 1] + t[4 * c4 + 1] - dq4.y) * SM_SCALE;
+                    const float d2 = pr[4 * c4 + 2] * (g2[4 * c4 + 2] + t[4 * c4 + 2] - dq4.z) * SM_SCALE;
+                    const float d3 = pr[4 * c4 + 3] * (g2[4 * c4 + 3] + t[4 * c4 + 3] - dq4.w) * SM_SCALE;
+                    split2(d0, d1, dh[2 * c4], dl[2 * c4]);
+                    split2(d2, d3, dh[2 * c4 + 1], dl[2 * c4 + 1]);
                 }
                 TR(34, j);
                 tmem_st16(lane_addr + KTM_G2 + h * 32, dh);
@@ -1060,18 +1096,27 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         flush_ds();
         mbar_wait(&bars[E_DONE], 0);
         tc_fence_after();
-        const bool store_ok = r_idx < T;
+        // dV, dK: 32 rows x 64 columns per warp, transposed through a private 4 KB block of the (now idle) Q ring so that every global
+        // store instruction writes 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes
+        float* stg = reinterpret_cast<float*>(sm + QOFF_U) + warp * 1024;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            float* dst = (g == 0 ? dv : dk) + ((int64_t)row_base + r_idx) * ld_d + h * 64;
+            float* dst = (g == 0 ? dv : dk) + ((int64_t)row_base + r0 + q * 32) * ld_d + h * 64;
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 float t[32];
                 tmem_ld32(lane_addr + (g == 0 ? KTM_ACC1 : KTM_ACC2) + h * 64 + ch * 32, t);
-                if (store_ok) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+                for (int k = 0; k < 8; ++k)
+                    *reinterpret_cast<float4*>(stg + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_float4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3);
+                    const float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+                    if (r0 + q * 32 + rr < T) *reinterpret_cast<float4*>(dst + (int64_t)rr * ld_d + ch * 32 + (lane & 7) * 4) = x;
                 }
+                __syncwarp();
             }
         }
     }
@@ -1213,7 +1258,7 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
                 "dip_attn_bwd_tc: need 0 <= do_begin <= q_begin < T and 0 <= k_begin < T (got %d, %d, %d)", do_begin, q_begin, k_begin);
     static bool attr = false;
     if (!attr) {
-        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
+        DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::KV_SMEM));
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::DQ_SMEM));
         DIP_CUDA(cudaFuncSetAttribute(tcattn::attn_bwd_dq_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcattn::SQ_SMEM));
         attr = true;
@@ -1245,7 +1290,7 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
     {
         dim3 grid(cdiv(T - k_begin, 128), B);      // keys k_begin.. stationary, queries do_begin.. streamed
         DIP_PROF(DIP_PROF_ATTN_BWD_DKDV, stream);
-        tcattn::attn_bwd_kv_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::DQ_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, d_hi64, d_lo64, dv, dk, ld_d, lse,
+        tcattn::attn_bwd_kv_tc_kernel<<<grid, tcattn::NTHREADS, tcattn::KV_SMEM, st>>>(q_hi128, q_lo128, q_hi64, q_lo64, d_hi64, d_lo64, dv, dk, ld_d, lse,
                                                                                        delta_ws, key_mask, mask_stride, T, k_begin, do_begin, ds_hi, ds_lo, tq_pad,
                                                                                        q_begin);
         DIP_LAUNCHED();

@@ -87,6 +87,9 @@ static_assert(OFF_BAR == 229376 && FWD_SMEM <= SMEM_LIMIT, "forward kernel share
 constexpr uint32_t TM_S = 0, TM_PV = 256, TM_P = 384;
 
 constexpr uint32_t IDESC_S = instr_desc(128, 128, 0, 0);    // Q (K-major) x [K_hi;K_lo] (K-major) -> 128 x 128
+// the lo plane of the A operand meets only the hi half of the stacked tile (N = 64: the first 64 rows of every k-block): lo x lo is the
+// 2^-16 term every other product of the split scheme drops too, and an N = 64 MMA takes as long as an N = 128 one but switches half the MACs
+constexpr uint32_t IDESC_S64 = instr_desc(128, 64, 0, 0);
 constexpr uint32_t IDESC_PV = instr_desc(128, 128, 0, 1);   // P (tensor memory) x V (MN-major) -> 128 x 128
 constexpr float RESCALE_THRESHOLD = 8.0f;                   // log2 units: P stays below 2^8 between rescales
 
@@ -216,7 +219,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                tc_mma(tmem + TM_S + sb * 128, desc_adv(dQ, pl * 32768 + kb * 16384 + ks * 32), desc_adv(kbase, kb * 16384 + ks * 32), IDESC_S, acc);
+                                tc_mma(tmem + TM_S + sb * 128, desc_adv(dQ, pl * 32768 + kb * 16384 + ks * 32), desc_adv(kbase, kb * 16384 + ks * 32), pl == 0 ? IDESC_S : IDESC_S64, acc);
                                 acc = 1;
                             }
                     tc_commit(&bars[B_SFULL + sb]);
@@ -541,7 +544,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            tc_mma(tmem + QTM_G1, desc_adv(dX, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
+                            tc_mma(tmem + QTM_G1, desc_adv(dX, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), pl == 0 ? IDESC_G128 : IDESC_S64, acc);
                             acc = 1;
                         }
                 tc_commit(&bars[D_SFULL]);
@@ -567,7 +570,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            tc_mma_ts(tmem + QTM_G2, tmem + QTM_DO + pl * 64 + (kb * 4 + ks) * 8, desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
+                            tc_mma_ts(tmem + QTM_G2, tmem + QTM_DO + pl * 64 + (kb * 4 + ks) * 8, desc_adv(tp, kb * 16384 + ks * 32), pl == 0 ? IDESC_G128 : IDESC_S64, acc);
                             acc = 1;
                         }
                 tc_commit(&bars[D_DPFULL]);
@@ -812,7 +815,7 @@ attn_bwd_dq_stream_tc_kernel(const __grid_constant__ CUtensorMap tm_ds_hi, const
 // N = 128: 73 cycles for twice the work of the N = 64 MMAs (67 cycles) the 32-query version had to use.
 // tensor memory: [0,128) S^T_j then P_j, [128,256) dP^T_j then dS_j, [256,384) dV, [384,512) dK
 constexpr uint32_t KTM_G1 = 0, KTM_G2 = 128, KTM_ACC1 = 256, KTM_ACC2 = 384;
-enum { E_XFULL = 0, E_UFULL = 1, E_UEMPTY = 3, E_WFULL = 5, E_WEMPTY = 6, E_G1FULL = 7, E_G2FULL = 8, E_PFULL = 9, E_DSFULL = 10, E_DONE = 11 };
+enum { E_XFULL = 0, E_UFULL = 1, E_UEMPTY = 3, E_WFULL = 5, E_WEMPTY = 6, E_G1FULL = 7, E_G2FULL = 8, E_PFULL = 9, E_DSFULL = 10, E_DONE = 11, E_YFULL = 12 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __grid_constant__ CUtensorMap tm_qkv_lo128,
@@ -846,6 +849,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         mbar_init(&bars[E_PFULL], ROW_THREADS);
         mbar_init(&bars[E_DSFULL], ROW_THREADS);
         mbar_init(&bars[E_DONE], 1);
+        mbar_init(&bars[E_YFULL], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -856,13 +860,19 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
 
     if (warp == W_PRODUCER) {
+        // start-up order = order of first use: K, Q_0 (S^T_0), then V, dO_0 (dP^T_0) -- K and V on separate barriers
+        auto load_V = [&]() {
+            mbar_expect_tx(&bars[E_YFULL], 2 * ST_PLANE);
+            for (int kb = 0; kb < 2; ++kb) {
+                tma_load_3d(sm + QOFF_Y + kb * 16384, &tm_qkv_hi128, &bars[E_YFULL], 256 + kb * 64, r0, b);                 // V hi
+                tma_load_3d(sm + QOFF_Y + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[E_YFULL], 256 + kb * 64, r0, b);      // V lo
+            }
+        };
         if (lane == 0) {
-            mbar_expect_tx(&bars[E_XFULL], 4 * ST_PLANE);
+            mbar_expect_tx(&bars[E_XFULL], 2 * ST_PLANE);
             for (int kb = 0; kb < 2; ++kb) {
                 tma_load_3d(sm + QOFF_X + kb * 16384, &tm_qkv_hi128, &bars[E_XFULL], 128 + kb * 64, r0, b);                 // K hi
                 tma_load_3d(sm + QOFF_X + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[E_XFULL], 128 + kb * 64, r0, b);      // K lo
-                tma_load_3d(sm + QOFF_Y + kb * 16384, &tm_qkv_hi128, &bars[E_XFULL], 256 + kb * 64, r0, b);                 // V hi
-                tma_load_3d(sm + QOFF_Y + ST_PLANE + kb * 16384, &tm_qkv_lo128, &bars[E_XFULL], 256 + kb * 64, r0, b);      // V lo
             }
         }
         for (int j = 0; j < n_tiles; ++j) {
@@ -881,6 +891,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                     tma_load_3d(du + kb * 16384 + 8192, &tm_qkv_lo64, &bars[E_UFULL + s], kb * 64, q0, b);        // Q lo
                 }
                 TR(42, j);
+                if (j == 0) load_V();
                 if (j >= 1) mbar_wait(&bars[E_WEMPTY], (j - 1) & 1);
                 TR(43, j);
                 mbar_expect_tx(&bars[E_WFULL], Q_TILE);
@@ -905,7 +916,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        tc_mma(dst, desc_adv(st, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), IDESC_G128, acc);
+                        tc_mma(dst, desc_adv(st, pl * ST_PLANE + kb * 16384 + ks * 32), desc_adv(tp, kb * 16384 + ks * 32), pl == 0 ? IDESC_G128 : IDESC_S64, acc);
                         acc = 1;
                     }
         };
@@ -949,6 +960,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
         };
         mbar_wait(&bars[E_XFULL], 0);
         issue_scores1(0);
+        mbar_wait(&bars[E_YFULL], 0);
         issue_scores2(0);
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(&bars[E_PFULL], j & 1);                                    // dV += P_j^T dO_j
@@ -1024,6 +1036,11 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 }
             }
             TR(30, j);
+            // read back BEFORE the wait: with the tensor pipe streaming its operands out of shared memory an LDS takes hundreds of cycles
+            float4 l4[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) l4[c4] = lsd4[c4];
+            const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
             mbar_wait(&bars[E_G1FULL], j & 1);
             TR(31, j);
             tc_fence_after();
@@ -1032,13 +1049,12 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 float t[32];
                 uint32_t ph[16], pl[16];
                 tmem_ld32x2(lane_addr + KTM_G1 + h * 32, pr, lane_addr + KTM_G1 + 64 + h * 32, t);
-                const uint32_t bad = (uint32_t)(bits_ring[j & 7] >> (32 * h));
                 if (all_rows_ok && bad == 0u) {
                     // no masked key in this warp's rows, no query past the end of the sample: nothing to select (every tile but the last,
                     // every warp without padding keys)
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 l = lsd4[c4];
+                        const float4 l = l4[c4];
                         pr[4 * c4] = ex2_approx(fmaf(pr[4 * c4] + t[4 * c4], SC2, -l.x));
                         pr[4 * c4 + 1] = ex2_approx(fmaf(pr[4 * c4 + 1] + t[4 * c4 + 1], SC2, -l.y));
                         pr[4 * c4 + 2] = ex2_approx(fmaf(pr[4 * c4 + 2] + t[4 * c4 + 2], SC2, -l.z));
@@ -1063,6 +1079,9 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             }
             flush_ds();                                             // dS^T of the previous tile
             TR(32, j);
+            float4 d4[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) d4[c4] = lsd4[8 + c4];
             mbar_wait(&bars[E_G2FULL], j & 1);
             TR(33, j);
             tc_fence_after();
@@ -1071,7 +1090,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
                 tmem_ld32x2(lane_addr + KTM_G2 + h * 32, g2, lane_addr + KTM_G2 + 64 + h * 32, t);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 dq4 = lsd4[8 + c4];
+                    const float4 dq4 = d4[c4];
                     const float d0 = pr[4 * c4] * (g2[4 * c4] + t[4 * c4] - dq4.x) * SM_SCALE;
                     const float d1 = pr[4 * c4 + 1] * (g2[4 * c4 + 1] + t[4 * c4 + 1] - dq4.y) * SM_SCALE;
                     const float d2 = pr[4 * c4 + 2] * (g2[4 * c4 + 2] + t[4 * c4 + 2] - dq4.z) * SM_SCALE;

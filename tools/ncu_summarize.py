@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
-CLASS = [("attn_fwd_tc_kernel", "attn_fwd"), ("attn_bwd_kv_tc_kernel", "attn_bwd_dkdv"), ("attn_bwd_dq_tc_kernel", "attn_bwd_dq"),
+CLASS = [("attn_fwd_tc_kernel", "attn_fwd"), ("attn_bwd_kv_tc_kernel", "attn_bwd_dkdv"), ("attn_bwd_dq_tc_kernel", "attn_bwd_dq"), ("attn_bwd_dq_stream_tc_kernel", "attn_bwd_dq_stream"),
          ("attn_bwd_fused_tc_kernel", "attn_bwd_fused"), ("chain_", "chain"), ("gemm_tc_kernel", "gemm"), ("gemm_nt_kernel", "gemm_simt"),
          ("ln_", "layernorm"), ("ddim_step_kernel", "update"), ("guidance_kernel", "guidance"), ("round_feas_kernel", "round_feas"),
          ("conv_reduce_kernel", "gnn_conv"), ("spmm_csr_kernel", "gnn_spmm"), ("head_", "head"), ("delta_kernel", "delta")]

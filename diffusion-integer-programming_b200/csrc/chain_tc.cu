@@ -20,17 +20,17 @@
 //     are parked in TMEM columns that are free at that moment instead of in registers;
 //   * A-plane layout: k-step j (16 features) has its hi words in columns 16j .. 16j+7 and its lo words in 16j+8 .. 16j+15, so the fp32
 //     chunk a thread parks in the A region is replaced IN PLACE by the planes made from it;
-//   * global rows move through a 2 KB per-warp staging block (XOR-swizzled 32 x 16 fp32 transposes): a warp access is 8 rows x 64
-//     contiguous bytes (whole sectors) although a thread owns a whole row; the loads of the next chunk are in flight while the current one
-//     is worked on, and the first chunk of a stage is requested before the wait for the product it is combined with;
+//   * global rows are moved by their owner thread as 256-bit accesses (32 rows x 32 bytes per warp instruction, whole sectors); the loads
+//     of the next chunk are in flight while the current one is worked on, and the first chunk of a stage is requested before the wait for
+//     the product it is combined with;
 //   * forward: the residual rows are not added after the product but PRELOADED into the accumulator (x_in + b_out before the first
 //     product, x_mid + b_proj before the third), which the MMAs then accumulate onto: the residual loads join the stream of stage-0
 //     loads instead of sitting between a product and the LayerNorm.
 // Measured (B200, 148 000 rows): forward 0.14 ms, backward 0.146 ms = 2.7 / 3.1 TB/s of algorithmic row traffic; the three separate
 // Linear launches they replace take 0.21 ms (+ LayerNorm kernels in the backward).  Tried and dropped: per-thread
 // cp.async.bulk.prefetch.L2 of the next tile's rows (12 % slower: 1 500 small bulk operations per tile pair).
-// Numerics: "bf16x2 split" like gemm_tc.cu (tc_common.cuh), every product 3 passes; LayerNorm in fp32 (two passes over the row, rsqrt +
-// one Newton step as in the GEMM loader).
+// Numerics: "bf16x2 split" like gemm_tc.cu (tc_common.cuh), every product 3 passes; LayerNorm in fp32 (shifted one-pass sums per half
+// row, pairwise combination, rsqrt + one Newton step as in the GEMM loader).
 #include <string.h>
 #include "tc_common.cuh"
 
@@ -41,12 +41,12 @@ using namespace tc;
 
 constexpr int GROUPS = 2, GROUP_WARPS = 8, GROUP_THREADS = GROUP_WARPS * 32, ROW_WARPS = GROUPS * GROUP_WARPS, NT = (ROW_WARPS + GROUPS) * 32;
 constexpr uint32_t W_BLOCK = 16384, W_PLANE = 32768, W_ONE = 65536;          // [plane][k-block][128 rows][64] bf16
-constexpr uint32_t OFF_STG = 3 * W_ONE, STG_WARP = 2048, OFF_PAR = OFF_STG + ROW_WARPS * STG_WARP, OFF_BAR = OFF_PAR + 5 * 512;
+constexpr uint32_t OFF_XCH = 3 * W_ONE, XCH_WARP = 256, OFF_PAR = OFF_XCH + ROW_WARPS * XCH_WARP, OFF_BAR = OFF_PAR + 5 * 512;   // per-warp LayerNorm exchange
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 232448, "chain kernel shared memory");
 constexpr uint32_t TM_A = 0, TM_ACC = 128, TM_SLOT = 256;                     // per slot: A planes (k-step j: hi 16j, lo 16j+8), accumulator 128
 constexpr uint32_t IDESC = instr_desc(128, 128, 0, 0);
-enum { B_W = 0, B_AFULL = 1, B_CFULL = 3 };
+enum { B_W = 0, B_AFULL = 1, B_CFULL = 3, B_STAGGER = 5 };
 enum { PAR_B0 = 0, PAR_B1 = 128, PAR_B2 = 256, PAR_G = 384, PAR_BETA = 512 };  // per-column parameter vectors in shared memory (float offsets)
 
 struct FastDiv {
@@ -98,57 +98,53 @@ __device__ __forceinline__ const float* rsrc_row(const Params& P, uint32_t g) {
     return t < P.r_split ? P.r_shared + (int64_t)b * P.r_sstride + (size_t)t * D : P.r_batch + ((size_t)b * (P.T - P.r_split) + (t - P.r_split)) * D;
 }
 
-// ---- staged row I/O.  A warp moves a 32-row x 16-column fp32 block (one chunk of its 32 rows) between global memory and the
-// "thread = row" register layout through its private 2 KB shared-memory block.  Global side: lane = (row & 7, 16-byte piece), four rows
-// 8 apart per lane -> 8 rows x 64 contiguous bytes per instruction.  Both sides are bank-conflict free with the XOR below. -------------
-struct Lane {
-    int lane;
-    uint32_t so_own, sx_own;      // owner side: float offset of the row, XOR of the 16-byte piece index
-    uint32_t so_glb;              // global side: float offset of (row = lane >> 2, swizzled piece lane & 3); rows 8 apart are +128 floats
-    __device__ __forceinline__ Lane(int l) : lane(l) {
-        so_own = (uint32_t)l * 16u; sx_own = (uint32_t)(l >> 1) & 3u;
-        const uint32_t r8 = (uint32_t)l >> 2, c4 = (uint32_t)l & 3u;
-        so_glb = r8 * 16u + 4u * (c4 ^ ((r8 >> 1) & 3u));
-    }
-};
-__device__ __forceinline__ void to_owner(float (&v)[16], const float4 (&t)[4], float* stg, const Lane& L) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + L.so_glb + i * 128) = t[i];
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(stg + L.so_own + 4u * ((uint32_t)k ^ L.sx_own));
-        v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
-    }
-    __syncwarp();
+// ---- row I/O.  A thread owns a row (its TMEM lane), so it moves its own 16-column chunk as two 256-bit accesses: a warp instruction
+// touches 32 rows x 32 bytes = 32 whole sectors.  That is as many L1 wavefronts per byte as the staged alternative (8 rows x 64 bytes per
+// instruction + a shared-memory transpose: 32 + 32 wavefronts per 2 KB chunk against 2 x 32 here) without its STS -> __syncwarp -> LDS
+// chain, which next to a tensor pipe that streams its B operand out of shared memory cost hundreds of cycles per chunk. --------------
+__device__ __forceinline__ void ld8_stream(float* v, const float* p) {      // read-once inputs: no L1 allocation
+    asm volatile("ld.global.L1::no_allocate.L2::256B.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
 }
-__device__ __forceinline__ void from_owner(float4 (&t)[4], const float (&v)[16], float* stg, const Lane& L) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<float4*>(stg + L.so_own + 4u * ((uint32_t)k ^ L.sx_own)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const float4*>(stg + L.so_glb + i * 128);
-    __syncwarp();
+__device__ __forceinline__ void ld8(float* v, const float* p) {             // coherent: rows this thread wrote earlier in the kernel
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
 }
-// the four rows a lane moves: element offsets of their first column (+ this lane's 16-byte piece), validity bits
-struct TileRows {
-    uint32_t off[4];
-    uint32_t valid;
-};
-__device__ __forceinline__ void ld_issue(float4 (&t)[4], const float* base, const TileRows& R, int col) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const float4*>(base + R.off[i] + col);
+__device__ __forceinline__ void st8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                 "f"(v[6]), "f"(v[7])
+                 : "memory");
 }
-__device__ __forceinline__ void st_rows(float* base, const TileRows& R, int col, const float4 (&t)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (R.valid & (1u << i)) *reinterpret_cast<float4*>(base + R.off[i] + col) = t[i];
+__device__ __forceinline__ void ld16_stream(float (&v)[16], const float* p) { ld8_stream(v, p); ld8_stream(v + 8, p + 8); }
+__device__ __forceinline__ void ld16(float (&v)[16], const float* p) { ld8(v, p); ld8(v + 8, p + 8); }
+__device__ __forceinline__ void st16(float* p, const float (&v)[16], bool ok) {
+    if (ok) { st8(p, v); st8(p + 8, v + 8); }
 }
-__device__ __forceinline__ void store_chunk(float* base, const TileRows& R, int col, const float (&v)[16], float* stg, const Lane& L) {
-    float4 t[4];
-    from_owner(t, v, stg, L);
-    st_rows(base, R, col, t);
+__device__ __forceinline__ void copy16(float (&d)[16], const float (&s)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = s[i];
+}
+
+// tcgen05.ld without the wait, and the wait tied to the registers it guards: a chunk loop asks for the next accumulator chunk before it
+// works on the current one (next to a tensor pipe busy with the other group's product a tcgen05.ld takes ~500 cycles to come back)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
+                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
 }
 
 __device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&x)[16]) {
@@ -191,13 +187,14 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
     float* par = reinterpret_cast<float*>(sm + OFF_PAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[B_W], 1);
         for (int s = 0; s < GROUPS; ++s) { mbar_init(&bars[B_AFULL + s], GROUP_THREADS); mbar_init(&bars[B_CFULL + s], 1); }
+        mbar_init(&bars[B_STAGGER], GROUP_THREADS);
         mbar_fence_init();
     }
     if (warp == ROW_WARPS) tmem_alloc(tmem_slot, 512);
@@ -239,66 +236,57 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
     } else {
         // ------------------------------------------------------------------ row warps: thread = (row, column half) of its group's tile
         const int g = warp >> 3, wg = warp & 7, q = wg & 3, h = wg >> 2;
-        const Lane L(lane);
-        float* stg = reinterpret_cast<float*>(sm + OFF_STG + warp * STG_WARP);
-        float* stg_partner = reinterpret_cast<float*>(sm + OFF_STG + (warp ^ 4) * STG_WARP);      // same rows, other column half
+        float* xch = reinterpret_cast<float*>(sm + OFF_XCH + warp * XCH_WARP);
+        const float* xch_partner = reinterpret_cast<const float*>(sm + OFF_XCH + (warp ^ 4) * XCH_WARP);   // same rows, other column half
         const uint32_t slot = tmem + ((uint32_t)(q * 32) << 16) + g * TM_SLOT;
         const int c0 = h * 64;                                                                     // this thread's columns: c0 .. c0 + 63
-        const int cl = c0 + 4 * (lane & 3);                                                        // + its 16-byte piece on the global side
         const uint32_t a_reg = slot + TM_A + c0, acc_reg = slot + TM_ACC + c0;                      // chunk ch at + 16 ch in both regions
         const int bar_id = 1 + g;
         uint32_t cph = 0;                                                                          // CFULL phase
+        // The two groups run the same sequence of memory-heavy and compute-heavy stages; started together they stay in step and the
+        // stage times ADD (measured: row work 44 us + products 21 + loads 36 + stores 44 = the 140 us of a 148 000-row launch, no
+        // overlap).  Group 1 therefore starts half a tile late: when group 0 has handed over its second operand.
+        if (g == 1 && n_my > 0) mbar_wait(&bars[B_STAGGER], 0);
         for (int k = g; k < n_my; k += GROUPS) {
-            const uint32_t live0 = (uint32_t)(blockIdx.x + k * gridDim.x) * 128u + q * 32;
-            TileRows R;
-            R.valid = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t li = live0 + 8 * i + (lane >> 2);
-                if (li < (uint32_t)P.n_live) R.valid |= 1u << i;
-                R.off[i] = grow(P, min(li, (uint32_t)P.n_live - 1u)) * (uint32_t)D;
-            }
-            const bool own_valid = live0 + lane < (uint32_t)P.n_live;
-            const uint32_t g_own = grow(P, min(live0 + lane, (uint32_t)P.n_live - 1u));
-            float4 nx[4];
+            const uint32_t live = (uint32_t)(blockIdx.x + k * gridDim.x) * 128u + q * 32 + lane;    // this thread's row
+            const bool ok = live < (uint32_t)P.n_live;
+            const uint32_t g_own = grow(P, min(live, (uint32_t)P.n_live - 1u));
+            const size_t off = (size_t)g_own * D + c0;                                              // its 64 columns in every (B*T,128) array
+            float nx[16];
             // ---------------- stage 0: the first A operand (forward: attention output rows, backward: dx_out rows).  Forward: the accumulator
             // is preloaded with x_in + b_out, so the first product (issued on top of it) leaves x_mid itself and the residual rows are
             // fetched here, in one stream with the attention rows, instead of after the wait for the product.
             if (!BWD) {
-                const float* rp[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rp[i] = rsrc_row(P, R.off[i] / (uint32_t)D) + cl;
-                float4 nr[4];
-                ld_issue(nx, P.a, R, cl);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) nr[i] = *reinterpret_cast<const float4*>(rp[i]);
+                const float* ap = P.a + off;
+                const float* rp = rsrc_row(P, g_own) + c0;
+                float nr[16];
+                ld16_stream(nx, ap);
+                ld16_stream(nr, rp);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float v[16];
-                    to_owner(v, nx, stg, L);
-                    if (ch < 3) ld_issue(nx, P.a, R, cl + 16 * (ch + 1));
+                    copy16(v, nx);
+                    if (ch < 3) ld16_stream(nx, ap + 16 * (ch + 1));
                     put_chunk(a_reg + 16 * ch, v);
-                    to_owner(v, nr, stg, L);
-                    if (ch < 3) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) nr[i] = *reinterpret_cast<const float4*>(rp[i] + 16 * (ch + 1));
-                    }
+                    copy16(v, nr);
+                    if (ch < 3) ld16_stream(nr, rp + 16 * (ch + 1));
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += par[PAR_B0 + c0 + 16 * ch + i];
                     tmem_st16f(acc_reg + 16 * ch, v);
                 }
             } else {
-                float4 ny[4];
-                ld_issue(nx, P.a, R, cl);
-                ld_issue(ny, P.a, R, cl + 16);
+                const float* ap = P.a + off;
+                float ny[16];
+                ld16_stream(nx, ap);
+                ld16_stream(ny, ap + 16);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ch += 2) {
                     float v[16];
-                    to_owner(v, nx, stg, L);
-                    if (ch < 2) ld_issue(nx, P.a, R, cl + 16 * (ch + 2));
+                    copy16(v, nx);
+                    if (ch < 2) ld16_stream(nx, ap + 16 * (ch + 2));
                     put_chunk(a_reg + 16 * ch, v);
-                    to_owner(v, ny, stg, L);
-                    if (ch < 2) ld_issue(ny, P.a, R, cl + 16 * (ch + 3));
+                    copy16(v, ny);
+                    if (ch < 2) ld16_stream(ny, ap + 16 * (ch + 3));
                     put_chunk(a_reg + 16 * (ch + 1), v);
                 }
             }
@@ -311,53 +299,63 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
                 mbar_wait(&bars[B_CFULL + g], cph & 1);
                 cph++;
                 tc_fence_after();
-                float sum = 0.f;
+                // statistics in ONE pass over the row (the accumulator is read twice, not three times): sums of x - s and (x - s)^2 with the
+                // shift s = the half-row's first element (the textbook shifted-data form: no cancellation unless |mean - s| >> std), the two
+                // halves of a row combined by the pairwise update  M2 = M2_a + M2_b + (mean_a - mean_b)^2 * 64 * 64 / 128
+                float s1 = 0.f, s2 = 0.f, shift = 0.f;
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float x[16];
-                    tmem_ld16(acc_reg + 16 * ch, x);
+                    tmem_ld_wait16(nacc);
+                    copy16(x, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
+                    if (ch == 0) shift = x[0];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) sum += x[i];
-                    store_chunk(P.xmid, R, cl + 16 * ch, x, stg, L);
+                    for (int i = 0; i < 16; ++i) { const float d = x[i] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+                    st16(P.xmid + off + 16 * ch, x, ok);
                 }
-                stg[lane] = sum;
+                const float mean_h = shift + s1 * (1.0f / 64.0f), m2_h = s2 - s1 * s1 * (1.0f / 64.0f);
+                xch[lane] = mean_h;
+                xch[32 + lane] = m2_h;
+                tmem_ld16_async(acc_reg, nacc);
                 named_bar_sync(bar_id, GROUP_THREADS);
-                const float mu = (sum + stg_partner[lane]) * (1.0f / D);
-                float sq = 0.f;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    float x[16];
-                    tmem_ld16(acc_reg + 16 * ch, x);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { const float d = x[i] - mu; sq += d * d; }
-                }
-                stg[32 + lane] = sq;
-                named_bar_sync(bar_id, GROUP_THREADS);
-                const float var = (sq + stg_partner[32 + lane]) * (1.0f / D);
+                const float mean_p = xch_partner[lane], m2_p = xch_partner[32 + lane];
+                const float mu = 0.5f * (mean_h + mean_p);
+                const float dm = mean_h - mean_p;
+                const float var = fmaxf((m2_h + m2_p + 32.0f * dm * dm) * (1.0f / D), 0.f);
                 float rs = rsqrtf(var + 1e-5f);
                 rs = rs * (1.5f - 0.5f * (var + 1e-5f) * rs * rs);
-                if (P.mean2 && h == 0 && own_valid) { P.mean2[g_own] = mu; P.rstd2[g_own] = rs; }
+                if (P.mean2 && h == 0 && ok) { P.mean2[g_own] = mu; P.rstd2[g_own] = rs; }
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float x[16];
-                    tmem_ld16(acc_reg + 16 * ch, x);
+                    tmem_ld_wait16(nacc);
+                    copy16(x, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] = (x[i] - mu) * rs * par[PAR_G + c0 + 16 * ch + i] + par[PAR_BETA + c0 + 16 * ch + i];
                     put_chunk(a_reg + 16 * ch, x);
                 }
             } else {
                 // dU = (dx_out . W_proj) * gelu'(u) -> A
-                ld_issue(nx, P.u_in, R, cl);
+                const float* up = P.u_in + off;
+                ld16_stream(nx, up);
                 mbar_wait(&bars[B_CFULL + g], cph & 1);
                 cph++;
                 tc_fence_after();
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float uu[16];
-                    to_owner(uu, nx, stg, L);
-                    if (ch < 3) ld_issue(nx, P.u_in, R, cl + 16 * (ch + 1));
+                    copy16(uu, nx);
+                    if (ch < 3) ld16_stream(nx, up + 16 * (ch + 1));
                     float acc[16];
-                    tmem_ld16(acc_reg + 16 * ch, acc);
+                    tmem_ld_wait16(nacc);
+                    copy16(acc, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float sg = fast_sigmoid(1.702f * uu[i]);
@@ -369,45 +367,56 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_AFULL + g]);
+            if (g == 0 && k == 0) mbar_arrive(&bars[B_STAGGER]);
             // ---------------- stage 2
             if (!BWD) {
                 // u = LN2(x_mid) . W_fc^T + b_fc (saved) ; QuickGELU -> A ; the accumulator chunk just read is preloaded with x_mid + b_proj
                 // for the last product (x_mid re-read: this thread wrote it in stage 1, it is L2-resident and requested before the wait)
-                ld_issue(nx, P.xmid, R, cl);
+                const float* xp = P.xmid + off;
+                ld16(nx, xp);
                 mbar_wait(&bars[B_CFULL + g], cph & 1);
                 cph++;
                 tc_fence_after();
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float x[16];
-                    tmem_ld16(acc_reg + 16 * ch, x);
+                    tmem_ld_wait16(nacc);
+                    copy16(x, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] += par[PAR_B1 + c0 + 16 * ch + i];
-                    if (P.u) store_chunk(P.u, R, cl + 16 * ch, x, stg, L);
+                    if (P.u) st16(P.u + off + 16 * ch, x, ok);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] *= fast_sigmoid(1.702f * x[i]);
                     put_chunk(a_reg + 16 * ch, x);
-                    to_owner(x, nx, stg, L);
-                    if (ch < 3) ld_issue(nx, P.xmid, R, cl + 16 * (ch + 1));
+                    copy16(x, nx);
+                    if (ch < 3) ld16(nx, xp + 16 * (ch + 1));
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] += par[PAR_B2 + c0 + 16 * ch + i];
                     tmem_st16f(acc_reg + 16 * ch, x);
                 }
             } else {
                 // dx_mid = dx_out + LN2'(dH):  gg = dH * gamma ;  dx = rstd * (gg - mean(gg) - xhat * mean(gg * xhat))
-                ld_issue(nx, P.xm_in, R, cl);
+                const float* xp = P.xm_in + off;
+                ld16_stream(nx, xp);
                 const float mu = P.mean_in[g_own], rs = P.rstd_in[g_own];
                 mbar_wait(&bars[B_CFULL + g], cph & 1);
                 cph++;
                 tc_fence_after();
                 float s1 = 0.f, s2 = 0.f;
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float xh[16];
-                    to_owner(xh, nx, stg, L);
-                    if (ch < 3) ld_issue(nx, P.xm_in, R, cl + 16 * (ch + 1));
+                    copy16(xh, nx);
+                    if (ch < 3) ld16_stream(nx, xp + 16 * (ch + 1));
                     float gg[16];
-                    tmem_ld16(acc_reg + 16 * ch, gg);
+                    tmem_ld_wait16(nacc);
+                    copy16(gg, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         xh[i] = (xh[i] - mu) * rs;
@@ -419,24 +428,26 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
                     tmem_st16f(a_reg + 16 * ch, xh);
                 }
                 tmem_st_wait();
-                ld_issue(nx, P.a, R, cl);                                // + dx_out
-                stg[lane] = s1;
-                stg[32 + lane] = s2;
+                const float* dp = P.a + off;
+                ld16_stream(nx, dp);                                     // + dx_out
+                xch[lane] = s1;
+                xch[32 + lane] = s2;
                 named_bar_sync(bar_id, GROUP_THREADS);
-                const float m1 = (s1 + stg_partner[lane]) * (1.0f / D);
-                const float m2 = (s2 + stg_partner[32 + lane]) * (1.0f / D);
-                named_bar_sync(bar_id, GROUP_THREADS);                   // the staging blocks go back to row I/O
+                const float m1 = (s1 + xch_partner[lane]) * (1.0f / D);
+                const float m2 = (s2 + xch_partner[32 + lane]) * (1.0f / D);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float x[16];
-                    to_owner(x, nx, stg, L);
-                    if (ch < 3) ld_issue(nx, P.a, R, cl + 16 * (ch + 1));
+                    copy16(x, nx);
+                    if (ch < 3) ld16_stream(nx, dp + 16 * (ch + 1));
                     float gg[16], xh[16];
-                    tmem_ld16(acc_reg + 16 * ch, gg);
-                    tmem_ld16(a_reg + 16 * ch, xh);
+                    tmem_ld16_async(acc_reg + 16 * ch, gg);
+                    tmem_ld16_async(a_reg + 16 * ch, xh);
+                    tmem_ld_wait16(gg);
+                    tmem_ld_wait16(xh);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] += rs * (gg[i] - m1 - xh[i] * m2);
-                    store_chunk(P.dxm, R, cl + 16 * ch, x, stg, L);
+                    st16(P.dxm + off + 16 * ch, x, ok);
                     put_chunk(a_reg + 16 * ch, x);                        // replaces the parked xhat chunk
                 }
             }
@@ -449,38 +460,41 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
                 mbar_wait(&bars[B_CFULL + g], cph & 1);
                 cph++;
                 tc_fence_after();
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float x[16];
-                    tmem_ld16(acc_reg + 16 * ch, x);
-                    store_chunk(P.xout, R, cl + 16 * ch, x, stg, L);
+                    tmem_ld_wait16(nacc);
+                    copy16(x, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
+                    st16(P.xout + off + 16 * ch, x, ok);
                 }
             } else {
                 // d_attn = dx_mid . W_out (+ its bf16 planes for the attention backward)
                 mbar_wait(&bars[B_CFULL + g], cph & 1);
                 cph++;
                 tc_fence_after();
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     float x[16];
-                    tmem_ld16(acc_reg + 16 * ch, x);
-                    store_chunk(P.dao, R, cl + 16 * ch, x, stg, L);
-                    if (P.do_hi) {
-                        // the chunk's hi words (32 bytes per row) and lo words through the same transpose: pieces 0-1 -> hi plane, 2-3 -> lo plane
-                        float w[16];
+                    tmem_ld_wait16(nacc);
+                    copy16(x, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
+                    st16(P.dao + off + 16 * ch, x, ok);
+                    if (P.do_hi && ok) {
+                        float hi[8], lo[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            uint32_t hi, lo;
-                            split2(x[2 * c], x[2 * c + 1], hi, lo);
-                            w[c] = __uint_as_float(hi); w[8 + c] = __uint_as_float(lo);
+                            uint32_t wh, wl;
+                            split2(x[2 * c], x[2 * c + 1], wh, wl);
+                            hi[c] = __uint_as_float(wh); lo[c] = __uint_as_float(wl);
                         }
-                        float4 t[4];
-                        from_owner(t, w, stg, L);
-                        uint16_t* plane = reinterpret_cast<uint16_t*>((lane & 2) ? P.do_lo : P.do_hi);
-                        const int pc = c0 + 16 * ch + 8 * (lane & 1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (R.valid & (1u << i)) *reinterpret_cast<float4*>(plane + R.off[i] + pc) = t[i];
+                        // 16 bf16 = 32 bytes per row and plane
+                        st8(reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(P.do_hi) + off + 16 * ch), hi);
+                        st8(reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(P.do_lo) + off + 16 * ch), lo);
                     }
                 }
             }

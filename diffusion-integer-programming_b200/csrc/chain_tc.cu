@@ -78,6 +78,8 @@ struct Params {
     float *xmid, *mean2, *rstd2, *u, *xout;          // forward outputs (stats / u nullable)
     const float *u_in, *xm_in, *mean_in, *rstd_in;   // backward inputs
     float *dxm, *dao; void *do_hi, *do_lo;           // backward outputs (planes nullable)
+    const float* dres;                               // MODE 2: residual gradient added to the result (a = dQKV rows of 384, dxm = result)
+    int w_col0[3];                                   // first column of weight w inside its tensor map (MODE 2: 0, 128, 256 of W_in^T)
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -178,12 +180,18 @@ __device__ __forceinline__ void issue_product(uint32_t tmem_slot_addr, uint64_t 
             }
 }
 
-// BWD = false: forward chain (weights out_w, fc_w, proj_w);  BWD = true: input-gradient chain (weights proj_wT, fc_wT, out_wT)
-template <bool BWD>
+// MODE 0: forward chain (weights out_w, fc_w, proj_w);  MODE 1: input-gradient chain (weights proj_wT, fc_wT, out_wT);
+// MODE 2: the input gradient of LayerNorm 1 + in-projection, the last piece of a block's backward pass:
+//     dx_in = dx_mid + LN1'( dQKV . W_in )          (model/modules.py:288-291 under autograd, input gradients only)
+// the three 128-column blocks of dQ|dK|dV are three products into ONE accumulator (K = 384: the three resident "weights" are the
+// column blocks of W_in^T), the LayerNorm backward is the epilogue -- instead of a K = 384 Linear launch, a 512-byte row written and
+// read back, and a LayerNorm launch.
+template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_constant__ CUtensorMap tm_w0_lo, const __grid_constant__ CUtensorMap tm_w1_hi,
                 const __grid_constant__ CUtensorMap tm_w1_lo, const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                 const Params P) {
+    constexpr bool BWD = MODE == 1;
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
@@ -216,7 +224,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
             const CUtensorMap* maps[6] = {&tm_w0_hi, &tm_w0_lo, &tm_w1_hi, &tm_w1_lo, &tm_w2_hi, &tm_w2_lo};
             for (int w = 0; w < 3; ++w)
                 for (int pl = 0; pl < 2; ++pl)
-                    for (int kb = 0; kb < 2; ++kb) tma_load_2d(sm + w * W_ONE + pl * W_PLANE + kb * W_BLOCK, maps[2 * w + pl], &bars[B_W], kb * 64, 0);
+                    for (int kb = 0; kb < 2; ++kb) tma_load_2d(sm + w * W_ONE + pl * W_PLANE + kb * W_BLOCK, maps[2 * w + pl], &bars[B_W], P.w_col0[w] + kb * 64, 0);
         }
         __syncwarp();
         const uint64_t dW = smem_desc(smem_u32(sm), 16, 1024);
@@ -228,7 +236,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
                 ph++;
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_product(tmem + g * TM_SLOT, dW, w, (!BWD && w != 1) ? 1u : 0u);
+                    issue_product(tmem + g * TM_SLOT, dW, w, MODE == 0 ? (w != 1 ? 1u : 0u) : MODE == 2 ? (w > 0 ? 1u : 0u) : 0u);
                     tc_commit(&bars[B_CFULL + g]);
                 }
                 __syncwarp();
@@ -252,6 +260,87 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
             const bool ok = live < (uint32_t)P.n_live;
             const uint32_t g_own = grow(P, min(live, (uint32_t)P.n_live - 1u));
             const size_t off = (size_t)g_own * D + c0;                                              // its 64 columns in every (B*T,128) array
+            if constexpr (MODE == 2) {
+                const float* ap = P.a + (size_t)g_own * (3 * D) + c0;
+                float nx[16], ny[16];
+#pragma unroll 1
+                for (int p = 0; p < 3; ++p) {
+                    ld16_stream(nx, ap + D * p);
+                    ld16_stream(ny, ap + D * p + 16);
+                    if (p > 0) {                                          // the A region is free once the previous product has completed
+                        mbar_wait(&bars[B_CFULL + g], cph & 1);
+                        cph++;
+                        tc_fence_after();
+                    }
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ch += 2) {
+                        float v[16];
+                        copy16(v, nx);
+                        if (ch < 2) ld16_stream(nx, ap + D * p + 16 * (ch + 2));
+                        put_chunk(a_reg + 16 * ch, v);
+                        copy16(v, ny);
+                        if (ch < 2) ld16_stream(ny, ap + D * p + 16 * (ch + 3));
+                        put_chunk(a_reg + 16 * (ch + 1), v);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars[B_AFULL + g]);
+                    if (g == 0 && k == 0 && p == 1) mbar_arrive(&bars[B_STAGGER]);
+                }
+                // epilogue: dx_in = dres + LN1'(dH), dH in the accumulator;  gg = dH * gamma ;  dx = rstd * (gg - mean(gg) - xhat * mean(gg * xhat))
+                const float* xp = rsrc_row(P, g_own) + c0;
+                ld16_stream(nx, xp);
+                const float mu = P.mean_in[g_own], rs = P.rstd_in[g_own];
+                mbar_wait(&bars[B_CFULL + g], cph & 1);
+                cph++;
+                tc_fence_after();
+                float s1 = 0.f, s2 = 0.f;
+                float nacc[16];
+                tmem_ld16_async(acc_reg, nacc);
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float xh[16];
+                    copy16(xh, nx);
+                    if (ch < 3) ld16_stream(nx, xp + 16 * (ch + 1));
+                    float gg[16];
+                    tmem_ld_wait16(nacc);
+                    copy16(gg, nacc);
+                    if (ch < 3) tmem_ld16_async(acc_reg + 16 * (ch + 1), nacc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        xh[i] = (xh[i] - mu) * rs;
+                        gg[i] *= par[PAR_G + c0 + 16 * ch + i];
+                        s1 += gg[i];
+                        s2 += gg[i] * xh[i];
+                    }
+                    tmem_st16f(acc_reg + 16 * ch, gg);
+                    tmem_st16f(a_reg + 16 * ch, xh);
+                }
+                tmem_st_wait();
+                const float* dp = P.dres + off;
+                ld16_stream(nx, dp);
+                xch[lane] = s1;
+                xch[32 + lane] = s2;
+                named_bar_sync(bar_id, GROUP_THREADS);
+                const float m1 = (s1 + xch_partner[lane]) * (1.0f / D);
+                const float m2 = (s2 + xch_partner[32 + lane]) * (1.0f / D);
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float x[16];
+                    copy16(x, nx);
+                    if (ch < 3) ld16_stream(nx, dp + 16 * (ch + 1));
+                    float gg[16], xh[16];
+                    tmem_ld16_async(acc_reg + 16 * ch, gg);
+                    tmem_ld16_async(a_reg + 16 * ch, xh);
+                    tmem_ld_wait16(gg);
+                    tmem_ld_wait16(xh);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] += rs * (gg[i] - m1 - xh[i] * m2);
+                    st16(P.dxm + off + 16 * ch, x, ok);
+                }
+                tc_fence_before();
+                continue;
+            }
             float nx[16];
             // ---------------- stage 0: the first A operand (forward: attention output rows, backward: dx_out rows).  Forward: the accumulator
             // is preloaded with x_in + b_out, so the first product (issued on top of it) leaves x_mid itself and the residual rows are
@@ -511,22 +600,25 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_const
 
 using namespace dip;
 
-static int chain_launch(bool bwd, const tcchain::Params& P, const void* const w_hi[3], const void* const w_lo[3], cudaStream_t st) {
+static int chain_launch(int mode, const tcchain::Params& P, const void* const w_hi[3], const void* const w_lo[3], cudaStream_t st) {
     CUtensorMap m[6];
+    const uint64_t w_cols = mode == 2 ? 3 * D : D;               // MODE 2: the three weights are column blocks of one (128, 384) matrix
     for (int i = 0; i < 3; ++i) {
-        DIP_TRY(make_tmap_bf16_2d(&m[2 * i], w_hi[i], D, D, D, 128, 64));
-        DIP_TRY(make_tmap_bf16_2d(&m[2 * i + 1], w_lo[i], D, D, D, 128, 64));
+        DIP_TRY(make_tmap_bf16_2d(&m[2 * i], w_hi[i], D, w_cols, w_cols, 128, 64));
+        DIP_TRY(make_tmap_bf16_2d(&m[2 * i + 1], w_lo[i], D, w_cols, w_cols, 128, 64));
     }
     static bool attr = false;
     if (!attr) {
-        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
-        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
+        DIP_CUDA(cudaFuncSetAttribute(tcchain::chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcchain::SMEM_BYTES));
         attr = true;
     }
     int grid = sm_count();
     if (grid > P.n_tiles) grid = P.n_tiles;
-    if (bwd) tcchain::chain_tc_kernel<true><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
-    else tcchain::chain_tc_kernel<false><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    if (mode == 1) tcchain::chain_tc_kernel<1><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    else if (mode == 2) tcchain::chain_tc_kernel<2><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    else tcchain::chain_tc_kernel<0><<<grid, tcchain::NT, tcchain::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
     return 0;
 }
 
@@ -562,7 +654,7 @@ int dip_block_chain_fwd_tc(float* xout, float* xmid, float* mean2, float* rstd2,
     const void* hi[3] = {out_w_hi, fc_w_hi, proj_w_hi};
     const void* lo[3] = {out_w_lo, fc_w_lo, proj_w_lo};
     DIP_PROF(DIP_PROF_GEMM, stream);
-    DIP_TRY(chain_launch(false, P, hi, lo, as_stream(stream)));
+    DIP_TRY(chain_launch(0, P, hi, lo, as_stream(stream)));
     DIP_LAUNCHED();
     return 0;
 }
@@ -583,7 +675,27 @@ int dip_block_chain_bwd_tc(float* dxmid, float* dattn, void* dattn_hi, void* dat
     const void* hi[3] = {proj_wT_hi, fc_wT_hi, out_wT_hi};
     const void* lo[3] = {proj_wT_lo, fc_wT_lo, out_wT_lo};
     DIP_PROF(DIP_PROF_GEMM, stream);
-    DIP_TRY(chain_launch(true, P, hi, lo, as_stream(stream)));
+    DIP_TRY(chain_launch(1, P, hi, lo, as_stream(stream)));
+    DIP_LAUNCHED();
+    return 0;
+}
+
+int dip_block_in_bwd_tc(float* dxin, const float* dqkv, dip_rows xin, const float* mean1, const float* rstd1, const float* ln1_g, const float* dres,
+                        const void* in_wT_hi, const void* in_wT_lo, int B, int T, int win, dip_stream_t stream) {
+    DIP_REQUIRE(dxin && dqkv && xin.batch && mean1 && rstd1 && ln1_g && dres && in_wT_hi && in_wT_lo, "dip_block_in_bwd_tc: null argument");
+    DIP_REQUIRE(xin.split == 0 || (xin.shared && xin.T == T && xin.split < T), "dip_block_in_bwd_tc: bad row source");
+    tcchain::Params P;
+    memset(&P, 0, sizeof(P));
+    DIP_TRY(chain_rows(P, B, T, win));
+    DIP_REQUIRE((int64_t)B * T * 3 * D < (1ll << 32), "dip_block_in_bwd_tc: B*T*384 must stay below 2^32");
+    P.a = dqkv;
+    P.r_shared = xin.shared; P.r_batch = xin.batch; P.r_split = (uint32_t)xin.split; P.r_sstride = xin.shared ? xin.shared_stride : 0;
+    P.mean_in = mean1; P.rstd_in = rstd1; P.ln_g = ln1_g; P.dres = dres; P.dxm = dxin;
+    P.w_col0[0] = 0; P.w_col0[1] = D; P.w_col0[2] = 2 * D;
+    const void* hi[3] = {in_wT_hi, in_wT_hi, in_wT_hi};
+    const void* lo[3] = {in_wT_lo, in_wT_lo, in_wT_lo};
+    DIP_PROF(DIP_PROF_GEMM, stream);
+    DIP_TRY(chain_launch(2, P, hi, lo, as_stream(stream)));
     DIP_LAUNCHED();
     return 0;
 }

@@ -380,6 +380,11 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
     } else {
         DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, mask_stride, delta, B, T, st));
     }
+    if (tc && use_chain()) {
+        // dxin = dxmid + LN1'(dQKV . W_in) in one launch (chain_tc.cu, mode 2)
+        DIP_TRY(dip_block_in_bwd_tc(dxin, dqkv, xin, s.mean1, s.rstd1, w.ln1_w, dxm, w.in_wT.hi, w.in_wT.lo, B, T, t_min, st));
+        return 0;
+    }
     // dH1 = dQKV . W_in
     dip_gemm_args g = gemm(dqkv, 3 * D, dt1, D, R, D, 3 * D, nullptr, DIP_ACT_NONE);
     if (tc) window(g, B, T, t_min);

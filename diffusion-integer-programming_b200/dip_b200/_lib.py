@@ -96,6 +96,7 @@ PROTOTYPES = {
     "dip_time_token": (i32, [vp, i32, i32, f32, vp, vp, vp]),
     "dip_block_chain_fwd_tc": (i32, [vp, vp, vp, vp, vp, vp, Rows, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dip_block_chain_bwd_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "dip_block_in_bwd_tc": (i32, [vp, vp, Rows, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dip_decoder_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp]),
     "dip_decoder_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "dip_guidance": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i64, vp]),

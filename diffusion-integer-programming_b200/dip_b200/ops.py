@@ -421,3 +421,14 @@ def block_chain_bwd_tc(dxout, u, xmid, mean2, rstd2, w, B, T, win=0, planes=True
                                      ptr(wt["mlp.c_proj.weight"][1]), ptr(wt["mlp.c_fc.weight"][0]), ptr(wt["mlp.c_fc.weight"][1]),
                                      ptr(wt["attn.out_proj.weight"][0]), ptr(wt["attn.out_proj.weight"][1]), B, T, int(win), _stream()))
     return out
+
+
+def block_in_bwd_tc(dqkv, xin, mean1, rstd1, w, dres, B, T, win=0, shared=None, split=0):
+    """dip_block_in_bwd_tc: dx_in = dres + LN1'(dqkv . W_in) on the tokens t >= win.  Rows below `win` are NaN."""
+    lib = _lib.load()
+    out = torch.full((B * T, D), float("nan"), dtype=torch.float32, device=dqkv.device)
+    hi, lo = split_bf16(_f32(w["attn.in_proj_weight"]).t().contiguous())
+    r = Rows(ptr(shared), ptr(_f32(xin)), int(T), int(split))
+    check(lib.dip_block_in_bwd_tc(ptr(out), ptr(_f32(dqkv)), r, ptr(_f32(mean1)), ptr(_f32(rstd1)), ptr(_f32(w["ln_1.weight"])), ptr(_f32(dres)),
+                                  ptr(hi), ptr(lo), B, T, int(win), _stream()))
+    return out

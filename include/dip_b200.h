@@ -239,6 +239,14 @@ int dip_block_chain_bwd_tc(float* dxmid, float* dattn, void* dattn_hi, void* dat
                            const void* proj_wT_hi, const void* proj_wT_lo, const void* fc_wT_hi, const void* fc_wT_lo,
                            const void* out_wT_hi, const void* out_wT_lo, int B, int T, int win, dip_stream_t stream);
 
+/* The last piece of a block's input-gradient backward in ONE launch: dx_in = dx_mid + LN1'(dQKV . W_in) -- the gradient of
+ * `self.attn(self.ln_1(x), ...)` w.r.t. x (model/modules.py:288-291 under loss.backward(), model/diffusion.py:633-634) plus the residual
+ * branch -- on the tokens t >= win of every sample.  dqkv: (B*T, 384) [dQ | dK | dV]; xin: the block's input rows (two-source); mean1 /
+ * rstd1: LayerNorm-1 statistics saved by the forward pass (dip_layernorm_split); in_wT: bf16 planes of the TRANSPOSED in_proj_weight,
+ * (128, 384).  The three 128-column blocks are three tcgen05 products into one accumulator, the LayerNorm backward is the epilogue. */
+int dip_block_in_bwd_tc(float* dxin, const float* dqkv, dip_rows xin, const float* mean1, const float* rstd1, const float* ln1_g,
+                        const float* dres, const void* in_wT_hi, const void* in_wT_lo, int B, int T, int win, dip_stream_t stream);
+
 /* Row 0 of every sample of the denoiser's first hidden layer: QuickGELU(W1 . temb(t) + b1) with
  * temb the 256-wide sinusoidal embedding of model/diffusion.py:39-74.  out: (B, T, 128), row 0. */
 int dip_time_token(float* out, int B, int T, float t, const float* W1, const float* b1, dip_stream_t stream);

@@ -346,3 +346,30 @@ def test_block_chain_tc(cuda, B, T, win, split):
     assert bool(torch.isnan(dead(bw["dxmid"])).all()) and bool(torch.isnan(dead(bw["dattn"])).all())
     bw2 = ops.block_chain_bwd_tc(dxout.to(cuda), nz(fw["u"]), nz(fw["xmid"]), nz(fw["mean2"]), nz(fw["rstd2"]), wc, B, T, win=win, planes=False)
     assert torch.equal(live(bw["dattn"]), live(bw2["dattn"])) and torch.equal(live(bw["dxmid"]), live(bw2["dxmid"]))
+
+
+@pytest.mark.parametrize("B,T,win,split", [(1, 128, 0, 0), (2, 100, 0, 0), (3, 257, 100, 0), (2, 1000, 500, 500), (3, 70, 0, 30), (20, 4000, 2000, 2000)])
+def test_block_in_bwd_tc(cuda, B, T, win, split):
+    """chain_tc.cu mode 2: dx_in = dres + LN1'(dQKV . W_in) in one launch against fp64 autograd of LN1 + in-projection."""
+    from dip_b200 import ops
+    w = {"ln_1.weight": 1 + 0.1 * rnd((D,), T + 1), "ln_1.bias": 0.1 * rnd((D,), T + 2), "attn.in_proj_weight": rnd((3 * D, D), T + 3, 0.1)}
+    batch = rnd((B, T - split, D), T + 4, 2.0)
+    shared = rnd((max(split, 1), D), T + 5, 2.0)
+    xin = (torch.cat([shared[None, :split].expand(B, -1, -1), batch], dim=1) if split else batch).reshape(B * T, D)
+    dqkv, dres = rnd((B * T, 3 * D), T + 6), rnd((B * T, D), T + 7)
+    x64 = xin.double().requires_grad_(True)
+    y = F.layer_norm(x64, (D,), w["ln_1.weight"].double(), w["ln_1.bias"].double(), 1e-5) @ w["attn.in_proj_weight"].double().t()
+    (y * dqkv.double()).sum().backward()
+    ref = x64.grad + dres.double()
+    xd = xin.double()
+    mean1 = xd.mean(-1).float()
+    rstd1 = (1.0 / torch.sqrt(xd.var(-1, unbiased=False) + 1e-5)).float()
+    wc = {k: v.to(cuda) for k, v in w.items()}
+    got = ops.block_in_bwd_tc(dqkv.to(cuda), batch.to(cuda), mean1.to(cuda), rstd1.to(cuda), wc, dres.to(cuda), B, T, win=win,
+                              shared=shared.to(cuda) if split else None, split=split)
+    live = lambda t: t.view(B, T, -1)[:, win:]
+    assert rel_l2(live(got), live(ref)) < 3e-5, rel_l2(live(got), live(ref))
+    assert bool(torch.isnan(got.view(B, T, -1)[:, :win]).all())
+    got2 = ops.block_in_bwd_tc(dqkv.to(cuda), batch.to(cuda), mean1.to(cuda), rstd1.to(cuda), wc, dres.to(cuda), B, T, win=win,
+                               shared=shared.to(cuda) if split else None, split=split)
+    assert torch.equal(live(got), live(got2))

@@ -128,6 +128,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     const int n_loop = je - jb;                                     // ring slots and barrier phases count from jb (jj = j - jb)
     Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && (warp == W_PRODUCER || warp == W_PRODUCER_V)) ? (warp == W_PRODUCER ? 1 : 4) : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
 
+    TR(1, 0);
     if (threadIdx.x == 0) {
         mbar_init(&bars[B_QFULL], 1);
         for (int s = 0; s < K_STAGES; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
@@ -146,6 +147,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    TR(2, 0);
 
     if (warp == W_PRODUCER) {
         // ------------------------------------------------------------------ TMA producer + mask ballots
@@ -362,6 +364,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             tc_fence_before();
             mbar_arrive(&bars[B_PFULL + s]);
         }
+        TR(3, 0);
         mbar_wait(&bars[B_PVFULL], (n_loop - 1) & 1);
         tc_fence_after();
         if (state_out != nullptr) {
@@ -404,8 +407,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             if (lse && h == 0 && t_q < T) lse[(int64_t)row_base + t_q] = m_used * LN2 + logf(l_run);
         }
     }
+    TR(4, 0);
     tc_fence_before();
     __syncthreads();
+    TR(5, 0);
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -836,6 +841,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
     const int n_tiles = (T - q_begin + QT - 1) / QT;                // queries q_begin .. T-1 are streamed
     Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && warp == W_PRODUCER) ? 1 : (lane == 0 && warp == W_MMA) ? 2 : -1);
 
+    TR(1, 0);
     if (threadIdx.x == 0) {
         mbar_init(&bars[E_XFULL], 1);
         for (int s = 0; s < 2; ++s) {
@@ -1113,6 +1119,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             TR(35, j);
         }
         flush_ds();
+        TR(3, 0);
         mbar_wait(&bars[E_DONE], 0);
         tc_fence_after();
         // dV, dK: 32 rows x 64 columns per warp, transposed through a private 4 KB block of the (now idle) Q ring so that every global
@@ -1139,8 +1146,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi128, const __
             }
         }
     }
+    TR(4, 0);
     tc_fence_before();
     __syncthreads();
+    TR(5, 0);
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 // A cluster of GCL CTAs works on one sample: CTA `rank` owns a contiguous slice of the rows (pass 1) and of the columns
 // (pass 2); the hinge indicators of the other slices are fetched through distributed shared memory after a cluster
 // barrier, and the per-CTA partial sums of viol / obj are added by rank 0 in rank order (fixed order -> deterministic).
-constexpr int GCL = 4, GTHREADS = 512;
+constexpr int GCL = 8, GTHREADS = 512;   // 8 x 37 = 296 CTAs, two per SM: the passes are gather-latency bound, more CTAs = more loads in flight (4: 86 us per step)
 
 // lane-group width for a segment pass: the power of two (<= 32) next to the average segment length
 __host__ __device__ inline int pick_group(int64_t nnz, int segments) {

@@ -229,7 +229,7 @@ static dip_gemm_args gemm(const float* A, int lda, float* C, int ldc, int64_t M,
 }
 
 // DIP_NO_CHAIN=1 falls back to one launch per Linear / LayerNorm for the row-wise half of a block (A/B comparisons, bisecting)
-static bool use_chain() {
+static bool use_chain_env() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("DIP_NO_CHAIN");
@@ -237,6 +237,8 @@ static bool use_chain() {
     }
     return v == 1;
 }
+// the chain kernels address rows with 32-bit element offsets (B*T*384 < 2^32): larger waves take the one-launch-per-Linear path
+static bool use_chain(int B, int T) { return use_chain_env() && (int64_t)B * T * 3 * D < (1ll << 32); }
 
 static dip_rows plain_rows(const float* p, int T) {
     dip_rows r;
@@ -307,7 +309,7 @@ static int block_fwd(int mode, const BlockW& w, dip_rows xin, float* xmid, float
     } else {
         DIP_TRY(dip_attn_fwd(ao, lse, qkv, qkv + D, qkv + 2 * D, 3 * D, mask, mask_stride, B, T, st));
     }
-    if (tc && use_chain()) {
+    if (tc && use_chain(B, T)) {
         // out-projection + residual, LayerNorm 2, c_fc, QuickGELU, c_proj + residual in one launch (chain_tc.cu)
         DIP_TRY(dip_block_chain_fwd_tc(xout, xmid, mean2, rstd2, u, ao, xin, w.out_w.hi, w.out_w.lo, w.out_b, w.ln2_w, w.ln2_b, w.fc_w.hi, w.fc_w.lo, w.fc_b,
                                        w.proj_w.hi, w.proj_w.lo, w.proj_b, B, T, win, st));
@@ -346,7 +348,7 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
     const bool tc = mode == DIP_PRECISION_TC_SPLIT;
     if (!tc) do_begin = 0;
     cudaStream_t cs = as_stream(st);
-    if (tc && use_chain()) {
+    if (tc && use_chain(B, T)) {
         // c_proj^T, gelu', c_fc^T, LayerNorm-2 backward + residual, out-projection^T (+ dO planes) in one launch (chain_tc.cu)
         DIP_TRY(dip_block_chain_bwd_tc(dxm, dao, do_hi, do_lo, dxout, s.u, s.xmid, s.mean2, s.rstd2, w.ln2_w, w.proj_wT.hi, w.proj_wT.lo, w.fc_wT.hi, w.fc_wT.lo,
                                        w.out_wT.hi, w.out_wT.lo, B, T, do_begin, st));
@@ -380,7 +382,7 @@ static int block_bwd(int mode, const BlockW& w, const float* dxout, dip_rows xin
     } else {
         DIP_TRY(dip_attn_bwd(dqkv, dqkv + D, dqkv + 2 * D, 3 * D, s.qkv, s.qkv + D, s.qkv + 2 * D, 3 * D, s.ao, dao, s.lse, mask, mask_stride, delta, B, T, st));
     }
-    if (tc && use_chain()) {
+    if (tc && use_chain(B, T)) {
         // dxin = dxmid + LN1'(dQKV . W_in) in one launch (chain_tc.cu, mode 2)
         DIP_TRY(dip_block_in_bwd_tc(dxin, dqkv, xin, s.mean1, s.rstd1, w.ln1_w, dxm, w.in_wT.hi, w.in_wT.lo, B, T, t_min, st));
         return 0;

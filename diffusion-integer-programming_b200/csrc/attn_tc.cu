@@ -26,6 +26,7 @@
 //               throttled to the tensor pipe's rate and an mbarrier wait costs up to ~250 cycles (tools/ktrace.py), two
 //               issuers hide each other's waits.  Backward kernels: warp 9 alone issues everything in an explicit order.
 #include <math.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace dip {
@@ -93,7 +94,7 @@ constexpr uint32_t IDESC_S64 = instr_desc(128, 64, 0, 0);
 constexpr uint32_t IDESC_PV = instr_desc(128, 128, 0, 1);   // P (tensor memory) x V (MN-major) -> 128 x 128
 constexpr float RESCALE_THRESHOLD = 8.0f;                   // log2 units: P stays below 2^8 between rescales
 
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17 };
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SFULL = 11, B_SFREE = 13, B_PFULL = 15, B_PVFULL = 17, B_QFREE = 18 };
 
 // Key-prefix hoisting (decoder layer 0): the first L of the 2L tokens are the instance embedding, the same for every step of a wave, so
 // for a query that is itself an instance token the scores against the instance keys -- and with them the running maximum, the running
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_constant__ CUtensorMap tm_lo128,
                    const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64, float* __restrict__ o,
                    float* __restrict__ lse, const uint8_t* __restrict__ key_mask, int64_t mask_stride, int T, int q_begin,
-                   const float* __restrict__ state_in, float* __restrict__ state_out, int j_split, int hoist_rows) {
+                   const float* __restrict__ state_in, float* __restrict__ state_out, int j_split, int hoist_rows, int n_qx, int n_items) {
     extern __shared__ __align__(1024) uint8_t sm[];
     require_aligned_smem(sm);
     uint8_t* sQ = sm;
@@ -119,13 +120,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
     volatile float* xm = reinterpret_cast<volatile float*>(sm + OFF_XM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, q0 = q_begin + blockIdx.x * BM;      // queries q_begin .. T-1 only
-    const int row_base = b * T;
-    // key tiles jb .. je-1 (CTA-uniform): a save launch stops at the split, a hoisted CTA starts there
-    const bool hoisted = state_in != nullptr && q0 + BM <= hoist_rows;
-    const int jb = hoisted ? j_split : 0;
-    const int je = state_out != nullptr ? j_split : (T + BN - 1) / BN;
-    const int n_loop = je - jb;                                     // ring slots and barrier phases count from jb (jj = j - jb)
+    // PERSISTENT over work items (sample, 128-query tile): CTA c takes the items c, c + gridDim.x, ...  Every warp role walks the same
+    // item sequence; ring slots and barrier phases are numbered by a running tile counter (g0 + jj), so the rings simply keep turning
+    // across items: the producer fetches the next item's Q tile as soon as the last score product of the current one has completed
+    // (B_QFREE) and its first key tiles as the ring frees up, i.e. the next prologue runs under the current item's last products
+    // and epilogue, and there is no CTA exit / launch, TMEM allocation or descriptor fetch between items (per 32-tile item the
+    // one-CTA-per-item form spent 6.6k + 6.8k of 76k cycles there, tools/ktrace_fixed.py).  With gridDim.x == n_items it degenerates
+    // to one item per CTA.  Item order: the long items of a hoisted launch (queries past the instance tokens: all key tiles) first,
+    // the short ones (resume at the split) after them, so every CTA gets the same mix.
+    const int n_h = (state_in != nullptr) ? min(hoist_rows / BM, n_qx) : 0, n_l = n_qx - n_h;
+    struct Item { int b, q0, jb, je, n_loop; bool hoisted; };
+    auto item_of = [&](int idx) {
+        Item it;
+        int qx;
+        const int n_long = n_l * (n_items / n_qx);
+        if (idx < n_long) { it.b = idx / n_l; qx = n_h + idx % n_l; }
+        else { const int r = idx - n_long; it.b = r / n_h; qx = r % n_h; }
+        it.q0 = q_begin + qx * BM;                                  // queries q_begin .. T-1 only
+        // key tiles jb .. je-1 (item-uniform): a save launch stops at the split, a hoisted item starts there
+        it.hoisted = state_in != nullptr && it.q0 + BM <= hoist_rows;
+        it.jb = it.hoisted ? j_split : 0;
+        it.je = state_out != nullptr ? j_split : (T + BN - 1) / BN;
+        it.n_loop = it.je - it.jb;
+        return it;
+    };
     Tracer tracer(threadIdx.x == 0 ? 0 : (lane == 0 && (warp == W_PRODUCER || warp == W_PRODUCER_V)) ? (warp == W_PRODUCER ? 1 : 4) : (lane == 0 && warp == W_MMA) ? 2 : (lane == 0 && warp == W_MMA2) ? 3 : -1);
 
     TR(1, 0);
@@ -140,6 +158,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             mbar_init(&bars[B_PFULL + s], ROW_THREADS);
         }
         mbar_init(&bars[B_PVFULL], 1);
+        mbar_init(&bars[B_QFREE], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -151,65 +170,86 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
 
     if (warp == W_PRODUCER) {
         // ------------------------------------------------------------------ TMA producer + mask ballots
-        const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
-        auto load_K = [&](int j) {      // all lanes: ballot the mask of tile j; lane 0: wait for the stage, issue the 4 boxes
-            const int jj = j - jb, s = jj % K_STAGES;
-            const int k0 = j * BN + lane, k1 = k0 + 32;
-            const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
-            const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
+        if (lane == 0) { tma_prefetch_desc(&tm_hi128); tma_prefetch_desc(&tm_lo128); tma_prefetch_desc(&tm_hi64); tma_prefetch_desc(&tm_lo64); }
+        uint32_t g0 = 0;
+        int n_it = 0;
+        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_it) {
+            const Item I = item_of(idx);
+            const int b = I.b, jb = I.jb;
+            const uint8_t* mrow = key_mask ? key_mask + (int64_t)b * mask_stride : nullptr;
+            auto load_K = [&](int j) {      // all lanes: ballot the mask of tile j; lane 0: wait for the stage, issue the 4 boxes
+                const uint32_t gj = g0 + (uint32_t)(j - jb);
+                const int s = (int)(gj % K_STAGES);
+                const int k0 = j * BN + lane, k1 = k0 + 32;
+                const bool m0 = (k0 >= T) || (mrow && mrow[k0]);
+                const bool m1 = (k1 >= T) || (mrow && mrow[k1]);
+                const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
+                if (lane == 0) {
+                    TR(40, j);
+                    if (gj >= K_STAGES) mbar_wait(&bars[B_KEMPTY + s], ((gj / K_STAGES) - 1) & 1);
+                    TR(41, j);
+                    bits_ring[gj & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
+                    mbar_expect_tx(&bars[B_KFULL + s], K_STAGE);
+                    uint8_t* dst = sK + s * K_STAGE;
+                    for (int kb = 0; kb < 2; ++kb) {
+                        tma_load_3d(dst + kb * 16384, &tm_hi64, &bars[B_KFULL + s], 128 + kb * 64, j * BN, b);           // rows 0-63 of the stacked operand
+                        tma_load_3d(dst + kb * 16384 + 8192, &tm_lo64, &bars[B_KFULL + s], 128 + kb * 64, j * BN, b);    // rows 64-127
+                    }
+                }
+                __syncwarp();
+            };
             if (lane == 0) {
-                TR(40, j);
-                if (jj >= K_STAGES) mbar_wait(&bars[B_KEMPTY + s], ((jj / K_STAGES) - 1) & 1);
-                TR(41, j);
-                bits_ring[jj & 7] = (uint64_t)b0 | ((uint64_t)b1 << 32);     // published by the arrive below (release)
-                mbar_expect_tx(&bars[B_KFULL + s], K_STAGE);
-                uint8_t* dst = sK + s * K_STAGE;
+                if (n_it > 0) mbar_wait(&bars[B_QFREE], (n_it - 1) & 1);     // the previous item's last score product has read its Q tile
+                mbar_expect_tx(&bars[B_QFULL], Q_BYTES);
                 for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_3d(dst + kb * 16384, &tm_hi64, &bars[B_KFULL + s], 128 + kb * 64, j * BN, b);           // rows 0-63 of the stacked operand
-                    tma_load_3d(dst + kb * 16384 + 8192, &tm_lo64, &bars[B_KFULL + s], 128 + kb * 64, j * BN, b);    // rows 64-127
+                    tma_load_3d(sQ + kb * 16384, &tm_hi128, &bars[B_QFULL], kb * 64, I.q0, b);
+                    tma_load_3d(sQ + 32768 + kb * 16384, &tm_lo128, &bars[B_QFULL], kb * 64, I.q0, b);
                 }
             }
             __syncwarp();
-        };
-        if (lane == 0) {
-            tma_prefetch_desc(&tm_hi128); tma_prefetch_desc(&tm_lo128); tma_prefetch_desc(&tm_hi64); tma_prefetch_desc(&tm_lo64);
-            mbar_expect_tx(&bars[B_QFULL], Q_BYTES);
-            for (int kb = 0; kb < 2; ++kb) {
-                tma_load_3d(sQ + kb * 16384, &tm_hi128, &bars[B_QFULL], kb * 64, q0, b);
-                tma_load_3d(sQ + 32768 + kb * 16384, &tm_lo128, &bars[B_QFULL], kb * 64, q0, b);
-            }
+            // K runs up to three tiles ahead, independent of the V ring: a single producer thread alternating between the two rings
+            // stalled the K loads behind the V ring's empty-waits and left the TMA queue idle a third of the time (tools/ktrace.py)
+            for (int j = I.jb; j < I.je; ++j) load_K(j);
+            g0 += (uint32_t)I.n_loop;
         }
-        // K runs up to three tiles ahead, independent of the V ring: a single producer thread alternating between the two rings
-        // stalled the K loads behind the V ring's empty-waits and left the TMA queue idle a third of the time (tools/ktrace.py)
-        for (int j = jb; j < je; ++j) load_K(j);
     } else if (warp == W_PRODUCER_V) {
         // ------------------------------------------------------------------ TMA producer of the V ring
         if (lane == 0) {
-            for (int j = jb; j < je; ++j) {
-                const int jj = j - jb, s = jj & 1;
-                TR(42, j);
-                if (jj >= 2) mbar_wait(&bars[B_VEMPTY + s], ((jj >> 1) - 1) & 1);
-                TR(43, j);
-                mbar_expect_tx(&bars[B_VFULL + s], V_STAGE);
-                uint8_t* dst = sV + s * V_STAGE;
-                for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_3d(dst + kb * 8192, &tm_hi64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, b);            // V hi, d-half kb
-                    tma_load_3d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, b);    // V lo
+            uint32_t g0 = 0;
+            for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+                const Item I = item_of(idx);
+                for (int j = I.jb; j < I.je; ++j) {
+                    const uint32_t gj = g0 + (uint32_t)(j - I.jb);
+                    const int s = (int)(gj & 1);
+                    TR(42, j);
+                    if (gj >= 2) mbar_wait(&bars[B_VEMPTY + s], ((gj >> 1) - 1) & 1);
+                    TR(43, j);
+                    mbar_expect_tx(&bars[B_VFULL + s], V_STAGE);
+                    uint8_t* dst = sV + s * V_STAGE;
+                    for (int kb = 0; kb < 2; ++kb) {
+                        tma_load_3d(dst + kb * 8192, &tm_hi64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, I.b);            // V hi, d-half kb
+                        tma_load_3d(dst + 16384 + kb * 8192, &tm_lo64, &bars[B_VFULL + s], 256 + kb * 64, j * BN, I.b);    // V lo
+                    }
                 }
+                g0 += (uint32_t)I.n_loop;
             }
         }
     } else if (warp == W_MMA || warp == W_MMA2) {
         // ------------------------------------------------------------------ MMA issuers: warp-uniform loops, the elected lane issues
         const uint64_t dQ = smem_desc(smem_u32(sQ), 16, 1024), dK = smem_desc(smem_u32(sK), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
         if (warp == W_MMA) {
-            mbar_wait(&bars[B_QFULL], 0);
+          uint32_t g0 = 0;
+          int n_it = 0;
+          for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_it) {
+            const int n_loop = item_of(idx).n_loop;
+            mbar_wait(&bars[B_QFULL], n_it & 1);
             for (int jj = 0; jj < n_loop; ++jj) {
-                const int s = jj % K_STAGES, sb = jj & 1;
+                const uint32_t gj = g0 + (uint32_t)jj;
+                const int s = (int)(gj % K_STAGES), sb = (int)(gj & 1);
                 TR(20, jj);
-                mbar_wait(&bars[B_KFULL + s], (jj / K_STAGES) & 1);
+                mbar_wait(&bars[B_KFULL + s], (gj / K_STAGES) & 1);
                 TR(21, jj);
-                if (jj >= 2) mbar_wait(&bars[B_SFREE + sb], ((jj >> 1) - 1) & 1);
+                if (gj >= 2) mbar_wait(&bars[B_SFREE + sb], ((gj >> 1) - 1) & 1);
                 TR(22, jj);
                 tc_fence_after();
                 if (elect_one()) {
@@ -226,17 +266,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                             }
                     tc_commit(&bars[B_SFULL + sb]);
                     tc_commit(&bars[B_KEMPTY + s]);
+                    if (jj == n_loop - 1) tc_commit(&bars[B_QFREE]);       // the item's Q tile has been read for the last time
                 }
                 __syncwarp();
                 TR(23, jj);
             }
+            g0 += (uint32_t)n_loop;
+          }
         } else {
+          uint32_t g0 = 0;
+          for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+            const int n_loop = item_of(idx).n_loop;
             for (int jj = 0; jj < n_loop; ++jj) {
-                const int s = jj & 1;
+                const uint32_t gj = g0 + (uint32_t)jj;
+                const int s = (int)(gj & 1);
                 TR(24, jj);
-                mbar_wait(&bars[B_VFULL + s], (jj >> 1) & 1);
+                mbar_wait(&bars[B_VFULL + s], (gj >> 1) & 1);
                 TR(25, jj);
-                mbar_wait(&bars[B_PFULL + s], (jj >> 1) & 1);       // P_j stored AND the previous P.V tile folded by the row warps
+                mbar_wait(&bars[B_PFULL + s], (gj >> 1) & 1);       // P_j stored AND the previous P.V tile folded by the row warps
                 TR(26, jj);
                 tc_fence_after();
                 if (elect_one()) {
@@ -258,13 +305,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 __syncwarp();
                 TR(28, jj);
             }
+            g0 += (uint32_t)n_loop;
+          }
         }
     } else {
         // ------------------------------------------------------------------ row warps: thread = (query row, key half)
         const int q = warp & 3, h = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        const int t_q = q0 + row;
+        uint32_t g0 = 0;
+        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+        const Item I = item_of(idx);
+        const int b = I.b, n_loop = I.n_loop;
+        const bool hoisted = I.hoisted;
+        const int row_base = b * T;
+        const int t_q = I.q0 + row;
         float oacc[64];
         float m_used = -INFINITY, l_part = 0.f;
         if (hoisted) {
@@ -282,9 +337,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             for (int i = 0; i < 64; ++i) oacc[i] = 0.f;
         }
         for (int jj = 0; jj < n_loop; ++jj) {
-            const int s = jj & 1;
+            const uint32_t gj = g0 + (uint32_t)jj;
+            const int s = (int)(gj & 1);
             TR(30, jj);
-            mbar_wait(&bars[B_SFULL + s], (jj >> 1) & 1);
+            mbar_wait(&bars[B_SFULL + s], (gj >> 1) & 1);
             TR(31, jj);
             tc_fence_after();
             float sv[32];
@@ -297,7 +353,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             tc_fence_before();
             mbar_arrive(&bars[B_SFREE + s]);
             TR(32, jj);
-            const uint32_t mb = (uint32_t)(bits_ring[jj & 7] >> (32 * h));
+            const uint32_t mb = (uint32_t)(bits_ring[gj & 7] >> (32 * h));
             float mx = -INFINITY;
             if (mb == 0u) {
 #pragma unroll
@@ -339,7 +395,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             tmem_st_wait();
             TR(35, jj);
             if (jj > 0) {
-                mbar_wait(&bars[B_PVFULL], (jj - 1) & 1);
+                mbar_wait(&bars[B_PVFULL], (gj - 1) & 1);
                 TR(36, jj);
                 tc_fence_after();
 #pragma unroll
@@ -365,7 +421,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             mbar_arrive(&bars[B_PFULL + s]);
         }
         TR(3, 0);
-        mbar_wait(&bars[B_PVFULL], (n_loop - 1) & 1);
+        mbar_wait(&bars[B_PVFULL], (g0 + (uint32_t)n_loop - 1) & 1);
         tc_fence_after();
         if (state_out != nullptr) {
             // save launch: the raw state after the key tiles [0, j_split) -- accumulator with the last product folded in, base, partial sums
@@ -406,6 +462,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             }
             if (lse && h == 0 && t_q < T) lse[(int64_t)row_base + t_q] = m_used * LN2 + logf(l_run);
         }
+        g0 += (uint32_t)n_loop;
+        }       // items
     }
     TR(4, 0);
     tc_fence_before();
@@ -1254,11 +1312,20 @@ int dip_attn_fwd_tc(float* o, float* lse, const void* qkv_hi, const void* qkv_lo
     DIP_TRY(make_tmap_bf16_3d(&lo128, qkv_lo, B, T, 3 * D, 3 * D, 128, 64));
     DIP_TRY(make_tmap_bf16_3d(&hi64, qkv_hi, B, T, 3 * D, 3 * D, 64, 64));
     DIP_TRY(make_tmap_bf16_3d(&lo64, qkv_lo, B, T, 3 * D, 3 * D, 64, 64));
-    dim3 grid(prefix_mode == 1 ? hoist_rows / tcattn::BM : cdiv(T - q_begin, tcattn::BM), B);
+    // work items = (sample, 128-query tile); one persistent CTA per SM walks them (DIP_FWD_PERSIST=0: one CTA per item)
+    const int n_qx = prefix_mode == 1 ? hoist_rows / tcattn::BM : cdiv(T - q_begin, tcattn::BM);
+    DIP_REQUIRE((int64_t)n_qx * B < (1ll << 31), "dip_attn_fwd_tc: too many work items");
+    const int n_items = n_qx * B;
+    static int persist = -1;
+    if (persist < 0) {
+        const char* e = getenv("DIP_FWD_PERSIST");
+        persist = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int grid = persist ? (n_items < sm_count() ? n_items : sm_count()) : n_items;
     DIP_PROF(DIP_PROF_ATTN_FWD, stream);
     tcattn::attn_fwd_tc_kernel<<<grid, tcattn::FWD_THREADS, tcattn::FWD_SMEM, as_stream(stream)>>>(
         hi128, lo128, hi64, lo64, o, lse, key_mask, mask_stride, T, q_begin, prefix_mode == 2 ? prefix_state : nullptr,
-        prefix_mode == 1 ? prefix_state : nullptr, j_split, hoist_rows);
+        prefix_mode == 1 ? prefix_state : nullptr, j_split, hoist_rows, n_qx, n_items);
     DIP_LAUNCHED();
     return 0;
 }

@@ -63,6 +63,13 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
                  : "memory");
 }
 
+// 256-bit store of 8 floats (row-owner epilogues: 32 rows x 32 bytes per warp instruction = whole sectors)
+__device__ __forceinline__ void st_global_v8f(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                 "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ void require_aligned_smem(const void* p) {
     if ((smem_u32(p) & 1023u) != 0u) {
         if (threadIdx.x == 0) printf("dip: dynamic shared memory is not 1024-byte aligned\n");
@@ -453,11 +460,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
                 float t[32];
                 tmem_ld32(lane_addr + TM_PV + h * 64 + ch * 32, t);
                 if (t_q < T) {
+                    // 256-bit stores: a thread owns its row, so a warp instruction is 32 rows x 32 bytes = whole sectors (16-byte stores
+                    // were two instructions per sector)
                     float* orow = o + ((int64_t)row_base + t_q) * D + h * 64 + ch * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(orow + i) = make_float4((oacc[ch * 32 + i] + t[i]) * inv, (oacc[ch * 32 + i + 1] + t[i + 1]) * inv,
-                                                                           (oacc[ch * 32 + i + 2] + t[i + 2]) * inv, (oacc[ch * 32 + i + 3] + t[i + 3]) * inv);
+                    for (int i = 0; i < 32; i += 8) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] = __float_as_uint((oacc[ch * 32 + i + e] + t[i + e]) * inv);
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + i), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                                     "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                     : "memory");
+                    }
                 }
             }
             if (lse && h == 0 && t_q < T) lse[(int64_t)row_base + t_q] = m_used * LN2 + logf(l_run);
@@ -854,7 +868,7 @@ attn_bwd_dq_stream_tc_kernel(const __grid_constant__ CUtensorMap tm_ds_hi, const
             tmem_ld32(lane_addr + h * 64 + ch * 32, t);
             if (r_idx < T && r_idx >= q_begin) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + ch * 32 + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+                for (int i = 0; i < 32; i += 8) st_global_v8f(dst + ch * 32 + i, t + i);
             }
         }
     }
@@ -1348,7 +1362,8 @@ int dip_attn_bwd_tc(float* dq, float* dk, float* dv, int ld_d, const void* qkv_h
                     int do_begin, int q_begin, int k_begin, void* ds_ws, size_t ds_ws_bytes, dip_stream_t stream) {
     DIP_REQUIRE(dq && dk && dv && qkv_hi && qkv_lo && do_hi && do_lo && o && d_o && lse && delta_ws && B > 0 && T > 0,
                 "dip_attn_bwd_tc: null/empty argument");
-    DIP_REQUIRE(ld_d % 4 == 0 && B <= 65535, "dip_attn_bwd_tc: bad ld_d / B");
+    DIP_REQUIRE(ld_d % 8 == 0 && B <= 65535 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 31) == 0,
+                "dip_attn_bwd_tc: ld_d must be a multiple of 8 and dq / dk / dv 32-byte aligned (256-bit stores)");
     DIP_REQUIRE(0 <= do_begin && do_begin <= q_begin && q_begin < T && 0 <= k_begin && k_begin < T,
                 "dip_attn_bwd_tc: need 0 <= do_begin <= q_begin < T and 0 <= k_begin < T (got %d, %d, %d)", do_begin, q_begin, k_begin);
     static bool attr = false;

@@ -54,10 +54,12 @@ def test_attention_fwd_tc(cuda, B, T, masked):
     assert torch.equal(o, o2)                                  # deterministic
 
 
-def test_attention_fwd_tc_full_size(cuda):
-    """Decoder sequence of the Set-Cover config: T = 4000 keys, against the fp32 SIMT kernel."""
+@pytest.mark.parametrize("B", [2, 5])
+def test_attention_fwd_tc_full_size(cuda, B):
+    """Decoder sequence of the Set-Cover config: T = 4000 keys, against the fp32 SIMT kernel.  B = 5: 160 (sample, query-tile) items on
+    148 SMs, so some persistent CTAs walk two items (rings and barrier phases continue across items)."""
     from dip_b200 import ops
-    B, T = 2, 4000
+    T = 4000
     qkv = rnd((B * T, 3 * D), 5, 1.0).to(cuda)
     hi, lo = ops.split_bf16(qkv)
     o, lse = ops.attn_fwd_tc(hi, lo, B, T)
@@ -270,7 +272,7 @@ def test_layernorm_split_token_window(cuda):
     assert torch.equal(mw.view(B, T)[:, tb:], mean.view(B, T)[:, tb:]) and torch.equal(rw.view(B, T)[:, tb:], rstd.view(B, T)[:, tb:])
 
 
-@pytest.mark.parametrize("B,T,prefix,masked", [(2, 600, 300, True), (1, 4000, 2000, False), (3, 257, 129, True), (2, 1500, 1000, True)])
+@pytest.mark.parametrize("B,T,prefix,masked", [(2, 600, 300, True), (1, 4000, 2000, False), (3, 257, 129, True), (2, 1500, 1000, True), (6, 4000, 2000, True)])
 def test_attention_fwd_tc_key_prefix_hoisting(cuda, B, T, prefix, masked):
     """dip_attn_fwd_tc prefix modes: the queries below floor(prefix/128)*128 resume from the softmax state a "save" launch left after
     the first floor(prefix/64) key tiles; everything must equal the plain launch bit for bit (same operations, same order)."""

@@ -454,6 +454,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi128, const __grid_co
             xm[h * 128 + row] = l_part;
             named_bar_sync(1, ROW_THREADS);
             const float l_run = l_part + xm[(h ^ 1) * 128 + row];
+            named_bar_sync(1, ROW_THREADS);                       // persistent: the next item's first tile reuses these exchange slots
             const float inv = 1.0f / l_run;
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {

@@ -6,7 +6,7 @@ set -u
 TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python tools/prof_step.py --steps 1 --wave 37"
+CMD="python tools/prof_step.py --steps 1 --wave ${WAVE:-148}"
 $CMD > $OUT/${TAG}_prof_plain.log 2>&1 || { echo "plain run failed"; tail -n 20 $OUT/${TAG}_prof_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"

@@ -81,6 +81,8 @@ def main():
                         "dram_pct": sum((r["dram_pct"] or 0) for r in rs) / len(rs)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     json.dump(launches, open(os.path.join(ROOT, "profiles", tag + "_ncu_launches.json"), "w"), indent=0)
+    # the shapes the capture ran on (tools/ncu_capture.sh -> tools/prof_step.py): bench.py scales the per-launch bytes to its own wave
+    kernels["_capture"] = {"config": "sc", "wave": int(os.environ.get("WAVE", 148)), "command": "python tools/prof_step.py --steps 1 --wave <wave>"}
     json.dump(kernels, open(os.path.join(ROOT, "profiles", tag + "_ncu_kernels.json"), "w"), indent=1)
     for cls, k in sorted(kernels.items()):
         print("%-16s %-28s n=%3d  dram %8.1f MB/launch  %8.1f us  tensor %5.1f%%  dram %5.1f%%" % (

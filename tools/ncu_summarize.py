@@ -85,6 +85,8 @@ def main():
     kernels["_capture"] = {"config": "sc", "wave": int(os.environ.get("WAVE", 148)), "command": "python tools/prof_step.py --steps 1 --wave <wave>"}
     json.dump(kernels, open(os.path.join(ROOT, "profiles", tag + "_ncu_kernels.json"), "w"), indent=1)
     for cls, k in sorted(kernels.items()):
+        if cls.startswith("_"):
+            continue
         print("%-16s %-28s n=%3d  dram %8.1f MB/launch  %8.1f us  tensor %5.1f%%  dram %5.1f%%" % (
             cls, k["kernel"][:28], k["launches_profiled"], k["dram_bytes_per_launch"] / 1e6, k["duration_us_under_ncu"], k["tensor_pct_elapsed"], k["dram_pct"]))
 

@@ -5,7 +5,7 @@ A "step" is one pass of the hot path over one WAVE of samples: S = 100 guided DD
 feasibility / objective check (sample.py:151-174).  Workloads (`--config`, BASELINE.json `configs`):
 
   sc          configs[1] slice (default): Set Cover 1000 x 2000, nnz 1e5 (ecole SetCoverGenerator shapes), gs 1e5, lambda 0.9,
-              D 128, denoiser 1 layer, decoder 2 layers, random-init weights; wave = 148 samples of one instance (one per SM; 37 for the other configs)
+              D 128, denoiser 1 layer, decoder 2 layers, random-init weights; wave = 148 samples (one per SM; 37 for cf)
   sc1         configs[0]: ONE instance x 100 samples (strong scaling: the 100 samples are split over the ranks)
   is          configs[2]: Independent Set 1500 nodes / 6360 rows with the two checkpoints the reference ships (2 denoiser layers)
   ca, cf      configs[3]: Combinatorial-Auction shapes (1500 bids / 775 rows) and Capacitated Facility Location (5050 / 5151,
@@ -49,15 +49,15 @@ CONFIGS = {
     # sample; the run is power-capped either way, at a lower clock with the larger wave)
     "sc": dict(family="SC", gs=1e5, lam=0.9, n_den=1, ckpt=False, wave=148, spi=None,
                what="configs[1] slice (256 instances x 1000 samples is %(waves)d such waves): Set Cover %(M)dx%(n)d nnz=%(nnz)d"),
-    "sc1": dict(family="SC", gs=1e5, lam=0.9, n_den=1, ckpt=False, wave=37, spi=100,
+    "sc1": dict(family="SC", gs=1e5, lam=0.9, n_den=1, ckpt=False, wave=148, spi=100,
                 what="configs[0]: ONE Set Cover instance %(M)dx%(n)d nnz=%(nnz)d x 100 samples, samples split over the ranks (strong scaling)"),
-    "is": dict(family="IS", gs=2e4, lam=0.5, n_den=2, ckpt=True, wave=37, spi=None,
+    "is": dict(family="IS", gs=2e4, lam=0.5, n_den=2, ckpt=True, wave=148, spi=None,
                what="configs[2]: Independent Set n=%(n)d M=%(M)d nnz=%(nnz)d, the reference's shipped checkpoints (2 denoiser layers, trained)"),
-    "ca": dict(family="CA", gs=2e4, lam=0.7, n_den=1, ckpt=False, wave=37, spi=None,
+    "ca": dict(family="CA", gs=2e4, lam=0.7, n_den=1, ckpt=False, wave=148, spi=None,
                what="configs[3]: Combinatorial-Auction shapes n=%(n)d M=%(M)d nnz=%(nnz)d, encoder + sampler"),
     "cf": dict(family="CF", gs=1e3, lam=0.7, n_den=1, ckpt=False, wave=37, spi=None,
                what="configs[3]: Capacitated Facility Location n=%(n)d M=%(M)d nnz=%(nnz)d (decoder sequence 10100), encoder + sampler"),
-    "partialsol": dict(family="SC", gs=1e5, lam=0.9, n_den=1, ckpt=False, wave=37, spi=15,
+    "partialsol": dict(family="SC", gs=1e5, lam=0.9, n_den=1, ckpt=False, wave=148, spi=15,
                        what="configs[4]: sample_partialsol.py flow, Set Cover %(M)dx%(n)d nnz=%(nnz)d, 15 samples per instance, waves mixing "
                             "instances, coverage 0.2 partial solutions selected and bit-packed on the device, handed to the host"),
 }
@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="sc", choices=sorted(CONFIGS))
-    ap.add_argument("--wave", type=int, default=0, help="samples per wave (0: the config's default: 148 = one per SM for sc, 37 = 148 SMs / 4 for the others)")
+    ap.add_argument("--wave", type=int, default=0, help="samples per wave (0: the config's default: 148 = one per SM; 37 = 148 SMs / 4 for cf, whose decoder sequence is 10 100)")
     ap.add_argument("--ddim-steps", type=int, default=100)
     ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--cols", type=int, default=2000)

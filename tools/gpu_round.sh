@@ -23,7 +23,7 @@ print('$c value',l['value'],'feasible_ratio',l['feasible_ratio'],'e2e',l['e2e'][
 "
 done
 python bench.py --impl reference --steps 1 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"; tail -c 400 $OUT/${TAG}_bench_ref.json
-bash tools/ncu_capture.sh $TAG
+if [ "${2:-}" != "noncu" ]; then bash tools/ncu_capture.sh $TAG; fi
 fi
 nproc > $OUT/${TAG}_nproc.txt
 du -sh $OUT

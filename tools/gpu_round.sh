@@ -15,7 +15,7 @@ print('clocks',l['clocks'])
 "
 if [ "${2:-}" != "quick" ]; then
 for c in is ca cf partialsol sc1; do
-  python bench.py --config $c --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_bench_$c.json 2> $OUT/${TAG}_bench_$c.err; echo "bench $c rc=$?"; tail -c 300 $OUT/${TAG}_bench_$c.err
+  python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_$c.json 2> $OUT/${TAG}_bench_$c.err; echo "bench $c rc=$?"; tail -c 300 $OUT/${TAG}_bench_$c.err
   python -c "
 import json
 l=json.loads(open('$OUT/${TAG}_bench_$c.json').read().strip().splitlines()[-1])
